@@ -1,0 +1,150 @@
+"""ctypes binding of libdccm_b200.so (the C ABI declared in include/dccm_b200.h).
+
+There is no CPU fallback: if the shared library is missing this module raises at import of the
+first symbol, and every compute entry point fails with the library's own error message when no
+sm_100 device is usable.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdccm_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+f64p = C.POINTER(C.c_double)
+i32p = C.POINTER(C.c_int32)
+vp = C.c_void_p
+
+
+class DccmError(RuntimeError):
+    pass
+
+
+class SfcFields(C.Structure):
+    """dccm_sfc_fields of include/dccm_b200.h (device pointers)."""
+    _names = ["WindStressX", "WindStressY", "SenHFlx", "QVapMFlx", "LatHFlx",
+              "SfcVelTransCoef", "SfcTempTransCoef", "SfcQVapTransCoef", "DelVarImplCPL",
+              "SUwRFlx", "LUwRFlx", "SfcHFlx_ns", "SfcHFlx_sr", "DSfcHFlxDTs",
+              "WindU", "WindV", "SfcAirTemp", "QVap1", "SDwRFlx", "LDwRFlx",
+              "ImplCplCoef1", "ImplCplCoef2", "SfcTemp", "SfcAlbedo", "SIceCon", "SfcHeight", "SfcPress"]
+    _fields_ = [(n, vp) for n in _names]
+
+
+def build(force=False, verbose=False):
+    """Compile libdccm_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    srcs.append(os.path.join(_HERE, "..", "include", "dccm_b200.h"))
+    if (not force and os.path.exists(LIB_PATH)
+            and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(s) for s in srcs)):
+        return LIB_PATH
+    r = subprocess.run(["make", "-C", CSRC, "-B"], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode != 0:
+        raise DccmError("building libdccm_b200.so failed")
+    return LIB_PATH
+
+
+_SIGS = {
+    "dccm_last_error": (C.c_char_p, []),
+    "dccm_build_info": (C.c_char_p, []),
+    "dccm_init": (C.c_int, [C.c_int]),
+    "dccm_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "dccm_sync": (C.c_int, [vp]),
+    "dccm_grid_gauss": (C.c_int, [C.c_int, C.c_int, f64p, f64p, f64p, f64p]),
+    "dccm_grid_regular": (C.c_int, [C.c_int, C.c_int, f64p, f64p, f64p, f64p]),
+    "dccm_grid_exchange": (C.c_int, [C.c_int, f64p, f64p, C.c_int, f64p, C.POINTER(C.c_int), f64p, f64p]),
+    "dccm_table_gen_jones99": (C.c_int, [C.c_int, f64p, C.c_int, f64p, C.c_int, f64p, C.c_int, f64p,
+                                         f64p, f64p, C.c_int, C.c_int, C.POINTER(vp)]),
+    "dccm_table_gen_bilinear": (C.c_int, [C.c_int, f64p, C.c_int, f64p, C.c_int, f64p, C.c_int, f64p,
+                                          C.c_int, C.POINTER(vp)]),
+    "dccm_table_write_text": (C.c_int, [vp, C.c_char_p]),
+    "dccm_table_read_text": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+    "dccm_table_write_bin": (C.c_int, [vp, C.c_char_p]),
+    "dccm_table_read_bin": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+    "dccm_table_size": (C.c_int64, [vp]),
+    "dccm_table_get": (C.c_int, [vp, i32p, i32p, i32p, i32p, f64p]),
+    "dccm_table_index": (C.c_int, [vp, C.c_int, C.c_int, i32p, i32p, f64p]),
+    "dccm_table_free": (None, [vp]),
+    "dccm_remap_create": (C.c_int, [C.c_int64, i32p, i32p, f64p, C.c_int, C.c_int, C.POINTER(vp)]),
+    "dccm_remap_destroy": (None, [vp]),
+    "dccm_remap_nnz": (C.c_int64, [vp]),
+    "dccm_remap_kind": (C.c_int, [vp]),
+    "dccm_remap_apply_host": (C.c_int, [vp, f64p, C.c_int, C.c_int, f64p, C.c_int, C.c_int, C.c_int]),
+    "dccm_remap_apply_device": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "dccm_interp_register": (C.c_int, [C.c_int, C.c_int, C.c_int, vp]),
+    "dccm_interpolate_data": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f64p,
+                                        C.c_int, C.c_int, f64p, C.c_int]),
+    "dccm_bulkflux_get_host": (C.c_int, [C.c_int, C.c_int] + [f64p] * 28),
+    "dccm_bulkflux_device": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                       C.POINTER(SfcFields), C.c_double, vp]),
+    "dccm_vdiff_create": (C.c_int, [C.c_int] * 5 + [C.c_double] * 4 + [C.POINTER(vp)]),
+    "dccm_vdiff_destroy": (None, [vp]),
+    "dccm_vdiff_set_mode": (C.c_int, [vp, C.c_int]),
+    "dccm_vdiff_forward_host": (C.c_int, [vp] + [f64p] * 18),
+    "dccm_vdiff_backward_host": (C.c_int, [vp] + [f64p] * 4),
+    "dccm_vdiff_forward_device": (C.c_int, [vp] + [vp] * 18 + [vp]),
+    "dccm_vdiff_backward_device": (C.c_int, [vp] + [vp] * 4 + [vp, vp]),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DccmError(f"{LIB_PATH} is missing: run __graft_entry__.build() "
+                            "(there is no CPU fallback for the exchange path)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)          # AttributeError if the ABI lost a symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def declared_symbols():
+    return sorted(_SIGS)
+
+
+def check(rc):
+    if rc != 0:
+        raise DccmError(f"libdccm_b200 error {rc}: {lib().dccm_last_error().decode()}")
+
+
+def dp(a):
+    """double* of a C-contiguous float64 numpy array."""
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"], "need contiguous float64"
+    return a.ctypes.data_as(f64p)
+
+
+def ip(a):
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"], "need contiguous int32"
+    return a.ctypes.data_as(i32p)
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def tptr(t):
+    """device pointer of a torch CUDA float64 tensor (or None)."""
+    if t is None:
+        return None
+    import torch
+    assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous(), "need contiguous cuda float64"
+    return C.c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

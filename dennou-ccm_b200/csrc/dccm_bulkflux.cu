@@ -1,0 +1,152 @@
+// dccm_bulkflux.cu -- K2: stand-alone bulk-flux kernel, one column per thread.
+// Replaces DSFCM_Util_SfcBulkFlux_Get (ref sfc/DSFCM_Util_SfcBulkFlux_mod.f90:108-439).
+#include <cuda_runtime.h>
+
+#include "dccm_bulkflux.cuh"
+#include "dccm_common.h"
+
+using namespace dccm;
+
+namespace {
+
+struct BulkArgs {
+    dccm_sfc_fields f;
+    int nx, ny, ld;
+    int64_t off, ss;
+    double sig1;
+};
+
+constexpr int kThreads = 128;
+
+__global__ void __launch_bounds__(kThreads) bulkflux_kernel(const BulkArgs a)
+{
+    const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (t >= (int64_t)a.nx * a.ny) return;
+    const int j = (int)(t / a.nx);
+    const int i = (int)(t - (int64_t)j * a.nx);
+    const int64_t c = a.off + i + (int64_t)a.ld * j;
+    const int64_t ss = a.ss;
+    const dccm_sfc_fields &f = a.f;
+
+    BulkIn in;
+    in.WindU = f.WindU[c]; in.WindV = f.WindV[c]; in.SfcAirTemp = f.SfcAirTemp[c]; in.QVap1 = f.QVap1[c];
+    in.SDwRFlx = f.SDwRFlx[c]; in.LDwRFlx = f.LDwRFlx[c];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { in.Coef1[k] = f.ImplCplCoef1[c + k * ss]; in.Coef2[k] = f.ImplCplCoef2[c + k * ss]; }
+#pragma unroll
+    for (int n = 0; n < 2; n++) { in.SfcTemp[n] = f.SfcTemp[c + n * ss]; in.SfcAlbedo[n] = f.SfcAlbedo[c + n * ss]; }
+    in.SIceCon = f.SIceCon[c];
+    in.SfcHeight = f.SfcHeight ? f.SfcHeight[c] : 0.0;
+    in.SfcPress = f.SfcPress[c];
+
+    BulkOut o;
+    bulk_column(in, a.sig1, o);
+
+#define ST3(ptr, v)                                                            \
+    if (f.ptr) { f.ptr[c] = o.v[0]; f.ptr[c + ss] = o.v[1]; f.ptr[c + 2 * ss] = o.v[2]; }
+#define ST2(ptr, v)                                                            \
+    if (f.ptr) { f.ptr[c] = o.v[0]; f.ptr[c + ss] = o.v[1]; }
+    ST3(WindStressX, WindStressX) ST3(WindStressY, WindStressY) ST3(SenHFlx, SenHFlx)
+    ST3(QVapMFlx, QVapMFlx) ST3(LatHFlx, LatHFlx)
+    ST3(SfcVelTransCoef, VelTC) ST3(SfcTempTransCoef, TempTC) ST3(SfcQVapTransCoef, QVapTC)
+    ST3(SUwRFlx, SUwRFlx) ST3(LUwRFlx, LUwRFlx)
+    ST2(SfcHFlx_ns, HFlx_ns) ST2(SfcHFlx_sr, HFlx_sr) ST2(DSfcHFlxDTs, DHFlxDTs)
+#undef ST3
+#undef ST2
+    if (f.DelVarImplCPL) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) f.DelVarImplCPL[c + k * ss] = o.Del[k];
+    }
+    f.SfcTemp[c + 2 * ss] = o.SfcTemp3;
+    f.SfcAlbedo[c + 2 * ss] = o.SfcAlbedo3;
+}
+
+DevBuf g_buf;   // scratch of the host entry point
+
+}  // namespace
+
+extern "C" int dccm_bulkflux_device(int nx, int ny, int ld, int64_t off, int64_t slot_stride,
+                                    const dccm_sfc_fields *f, double sig1, void *stream)
+{
+    if (!f) return fail(DCCM_ERR_ARG, "dccm_bulkflux: null field table");
+    if (nx < 1 || ny < 1 || ld < nx) return fail(DCCM_ERR_ARG, "dccm_bulkflux: bad extents nx=%d ny=%d ld=%d", nx, ny, ld);
+    if (!f->WindU || !f->WindV || !f->SfcAirTemp || !f->QVap1 || !f->SDwRFlx || !f->LDwRFlx || !f->ImplCplCoef1 ||
+        !f->ImplCplCoef2 || !f->SfcTemp || !f->SfcAlbedo || !f->SIceCon || !f->SfcPress)
+        return fail(DCCM_ERR_ARG, "dccm_bulkflux: a required input pointer is NULL");
+    int rc = ensure_device();
+    if (rc) return rc;
+    BulkArgs a;
+    a.f = *f; a.nx = nx; a.ny = ny; a.ld = ld; a.off = off; a.ss = slot_stride; a.sig1 = sig1;
+    const int64_t n = (int64_t)nx * ny;
+    const unsigned grid = (unsigned)((n + kThreads - 1) / kThreads);
+    bulkflux_kernel<<<grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    DCCM_CUDA_TRY(cudaGetLastError());
+    return DCCM_OK;
+}
+
+// Host (drop-in) form: explicit-shape (IA,JA[,n]) arrays with halo 1, interior IS:IE,JS:JE
+// (ref sfc/DSFCM_Admin_Grid_mod.f90:39-50).  Halo cells of the caller's arrays are untouched:
+// only the interior rows are moved back (2-D copies), as the reference only writes IS:IE,JS:JE.
+extern "C" int dccm_bulkflux_get_host(int IA, int JA,
+    double *WSX, double *WSY, double *SenH, double *QVapM, double *LatH,
+    double *VelTC, double *TempTC, double *QVapTC, double *Del,
+    double *SUw, double *LUw, double *HFns, double *HFsr, double *DHFDTs,
+    const double *WindU, const double *WindV, const double *SfcAirTemp, const double *QVap1,
+    const double *SDw, const double *LDw, const double *Coef1, const double *Coef2,
+    double *SfcTemp, double *SfcAlbedo, const double *SIceCon,
+    const double *Sig1Info, const double *SfcHeight, const double *SfcPress)
+{
+    if (IA < 3 || JA < 3) return fail(DCCM_ERR_ARG, "dccm_bulkflux_get: IA, JA must include the halo (>= 3)");
+    int rc = ensure_device();
+    if (rc) return rc;
+    const size_t N2 = (size_t)IA * JA;
+    // device mirror: 14 outputs (13 x 3 slots + Del x 4) + inputs (9 x 1 + 2 x 4 + 2 x 3)
+    const size_t n_out = 13 * 3 + 4, n_in = 9 + 8 + 6;
+    rc = g_buf.reserve(sizeof(double) * N2 * (n_out + n_in));
+    if (rc) return rc;
+    double *d = g_buf.as<double>();
+    size_t pos = 0;
+    auto take = [&](size_t slots) { double *p = d + pos * N2; pos += slots; return p; };
+    dccm_sfc_fields f;
+    f.WindStressX = take(3); f.WindStressY = take(3); f.SenHFlx = take(3); f.QVapMFlx = take(3); f.LatHFlx = take(3);
+    f.SfcVelTransCoef = take(3); f.SfcTempTransCoef = take(3); f.SfcQVapTransCoef = take(3);
+    f.DelVarImplCPL = take(4);
+    f.SUwRFlx = take(3); f.LUwRFlx = take(3); f.SfcHFlx_ns = take(3); f.SfcHFlx_sr = take(3); f.DSfcHFlxDTs = take(3);
+    double *dWindU = take(1), *dWindV = take(1), *dT1 = take(1), *dQ1 = take(1), *dSDw = take(1), *dLDw = take(1);
+    double *dC1 = take(4), *dC2 = take(4), *dTs = take(3), *dAl = take(3), *dIce = take(1), *dH = take(1), *dPs = take(1);
+    f.WindU = dWindU; f.WindV = dWindV; f.SfcAirTemp = dT1; f.QVap1 = dQ1; f.SDwRFlx = dSDw; f.LDwRFlx = dLDw;
+    f.ImplCplCoef1 = dC1; f.ImplCplCoef2 = dC2; f.SfcTemp = dTs; f.SfcAlbedo = dAl; f.SIceCon = dIce;
+    f.SfcHeight = dH; f.SfcPress = dPs;
+
+    cudaStream_t st = 0;
+    auto h2d = [&](double *dst, const double *src, size_t slots) {
+        return cudaMemcpyAsync(dst, src, sizeof(double) * N2 * slots, cudaMemcpyHostToDevice, st);
+    };
+    DCCM_CUDA_TRY(h2d(dWindU, WindU, 1)); DCCM_CUDA_TRY(h2d(dWindV, WindV, 1));
+    DCCM_CUDA_TRY(h2d(dT1, SfcAirTemp, 1)); DCCM_CUDA_TRY(h2d(dQ1, QVap1, 1));
+    DCCM_CUDA_TRY(h2d(dSDw, SDw, 1)); DCCM_CUDA_TRY(h2d(dLDw, LDw, 1));
+    DCCM_CUDA_TRY(h2d(dC1, Coef1, 4)); DCCM_CUDA_TRY(h2d(dC2, Coef2, 4));
+    DCCM_CUDA_TRY(h2d(dTs, SfcTemp, 3)); DCCM_CUDA_TRY(h2d(dAl, SfcAlbedo, 3));
+    DCCM_CUDA_TRY(h2d(dIce, SIceCon, 1)); DCCM_CUDA_TRY(h2d(dH, SfcHeight, 1)); DCCM_CUDA_TRY(h2d(dPs, SfcPress, 1));
+
+    const int nx = IA - 2, ny = JA - 2;
+    rc = dccm_bulkflux_device(nx, ny, IA, (int64_t)IA + 1, (int64_t)N2, &f, Sig1Info[0], st);
+    if (rc) return rc;
+
+    // interior only, slot by slot
+    auto d2h = [&](double *dst, const double *src, int slot) {
+        const size_t o = (size_t)slot * N2 + IA + 1;
+        return cudaMemcpy2DAsync(dst + o, sizeof(double) * IA, src + o, sizeof(double) * IA,
+                                 sizeof(double) * nx, ny, cudaMemcpyDeviceToHost, st);
+    };
+    struct { double *h; const double *d; int first, last; } outs[] = {
+        {WSX, f.WindStressX, 0, 2}, {WSY, f.WindStressY, 0, 2}, {SenH, f.SenHFlx, 0, 2}, {QVapM, f.QVapMFlx, 0, 2},
+        {LatH, f.LatHFlx, 0, 2}, {VelTC, f.SfcVelTransCoef, 0, 2}, {TempTC, f.SfcTempTransCoef, 0, 2},
+        {QVapTC, f.SfcQVapTransCoef, 0, 2}, {Del, f.DelVarImplCPL, 0, 3}, {SUw, f.SUwRFlx, 0, 2}, {LUw, f.LUwRFlx, 0, 2},
+        {HFns, f.SfcHFlx_ns, 0, 1}, {HFsr, f.SfcHFlx_sr, 0, 1}, {DHFDTs, f.DSfcHFlxDTs, 0, 1},
+        {SfcTemp, f.SfcTemp, 2, 2}, {SfcAlbedo, f.SfcAlbedo, 2, 2}};
+    for (auto &o : outs)
+        for (int s = o.first; s <= o.last; s++) DCCM_CUDA_TRY(d2h(o.h, o.d, s));
+    DCCM_CUDA_TRY(cudaStreamSynchronize(st));
+    return DCCM_OK;
+}

@@ -1,0 +1,204 @@
+// dccm_bulkflux.cuh -- per-column bulk surface flux + implicit surface-layer update, in
+// registers.  Shared by the stand-alone kernel (dccm_bulkflux.cu) and the fused
+// remap -> bulk-flux kernel (dccm_exchange.cu).
+//
+// Restates DSFCM_Util_SfcBulkFlux_Get + BulkCoefL82 for ONE column
+// (ref sfc/DSFCM_Util_SfcBulkFlux_mod.f90:194-415, :478-568), keeping the reference's
+// operation order (the library is compiled with -fmad=false), so the only differences from
+// the reference arithmetic are the last-ulp differences of exp/log/pow.
+// The reference's ~25 full-grid temporaries (:157-186) and six OpenMP passes collapse into
+// registers: each input is read once and each output written once.
+#pragma once
+
+namespace dccm {
+
+// ref sfc/DSFCM_Util_SfcBulkFlux_mod.f90:35-58 (note: these are the SFC component's own
+// constants -- CpDry = 1616, MolWt 0.018 -- not DCPAM's; reproduced, not reconciled)
+namespace sfc {
+constexpr double FKarm = 0.4;
+constexpr double GasRUniv = 8.3144621;
+constexpr double StB = 5.670373e-8;
+constexpr double Grav = 9.8;
+constexpr double MolWtDry = 1.8e-2;
+constexpr double MolWtWet = 1.8e-2;
+constexpr double CpDry = 1616.0;
+constexpr double LatentHeat = 2425300.0;
+constexpr double LatentHeatFusion = 334000.0;
+constexpr double RefPress = 1e5;
+constexpr double GasRDry = GasRUniv / MolWtDry;
+constexpr double GasRWet = GasRUniv / MolWtWet;
+constexpr double EpsV = MolWtWet / MolWtDry;
+constexpr double Es0 = 611.0;
+constexpr double HumidCoef = 1.0;
+constexpr double RoughLength = 1e-4;
+constexpr double RoughLenHeatFactor = 1.0;
+// limits, ref :574-591 (read_config: hard-coded, not namelist)
+constexpr double VelMinForRi = 0.01, VelMinForVel = 0.01, VelMinForTemp = 0.01, VelMinForQVap = 0.01;
+constexpr double VelMaxForVel = 1000.0, VelMaxForTemp = 1000.0, VelMaxForQVap = 1000.0;
+constexpr double VelBulkCoefMin = 0.0, TempBulkCoefMin = 0.0, QVapBulkCoefMin = 0.0;
+constexpr double VelBulkCoefMax = 1.0, TempBulkCoefMax = 1.0, QVapBulkCoefMax = 1.0;
+}  // namespace sfc
+
+struct BulkIn {
+    double WindU, WindV, SfcAirTemp, QVap1, SDwRFlx, LDwRFlx;
+    double Coef1[4], Coef2[4];
+    double SfcTemp[2], SfcAlbedo[2];
+    double SIceCon, SfcHeight, SfcPress;
+};
+
+struct BulkOut {
+    double WindStressX[3], WindStressY[3], SenHFlx[3], QVapMFlx[3], LatHFlx[3];
+    double VelTC[3], TempTC[3], QVapTC[3];
+    double Del[4];
+    double SUwRFlx[3], LUwRFlx[3];
+    double HFlx_ns[2], HFlx_sr[2], DHFlxDTs[2];
+    double SfcTemp3, SfcAlbedo3;
+};
+
+__device__ __forceinline__ void bulk_column(const BulkIn &in, double sig1, BulkOut &o)
+{
+    using namespace sfc;
+    const double LatentHeatLocal[2] = {LatentHeat, LatentHeat + LatentHeatFusion};   // :198-199
+    const double z0m = RoughLength;                                                  // :194-196
+    const double z0h = RoughLenHeatFactor * z0m;
+    const double HumdCoef = 1.0;
+
+    double Frac[2], QVapSat[2], SfcVirTemp[2];
+    Frac[0] = 1.0 - in.SIceCon;                                                      // :205-206
+    Frac[1] = in.SIceCon;
+#pragma unroll
+    for (int n = 0; n < 2; n++) {                                                    // :208-213
+        QVapSat[n] = EpsV * Es0 / in.SfcPress
+                   * exp(LatentHeatLocal[n] / GasRWet * (1.0 / 273.0 - 1.0 / in.SfcTemp[n]));
+        SfcVirTemp[n] = in.SfcTemp[n] * (1.0 + (((1.0 / EpsV) - 1.0) * QVapSat[n]));
+    }
+    const double VirTemp = in.SfcAirTemp * (1.0 + (((1.0 / EpsV) - 1.0) * in.QVap1));   // :215
+    const double Press1 = in.SfcPress * sig1;                                        // :217
+    const double Exner = pow(Press1 / RefPress, GasRDry / CpDry);                    // :218
+    const double SfcExner = pow(in.SfcPress / RefPress, GasRDry / CpDry);            // :219
+    const double VelAbs = sqrt(in.WindU * in.WindU + in.WindV * in.WindV);           // :221
+    const double Height = in.SfcHeight + GasRDry / Grav * VirTemp * (1.0 - sig1);    // :223-224
+
+    o.WindStressX[2] = 0.0; o.WindStressY[2] = 0.0; o.SenHFlx[2] = 0.0; o.LatHFlx[2] = 0.0;   // :226-240
+    o.QVapMFlx[2] = 0.0; o.SUwRFlx[2] = 0.0; o.LUwRFlx[2] = 0.0;
+    o.SfcTemp3 = 0.0; o.SfcAlbedo3 = 0.0;
+    o.VelTC[2] = 0.0; o.TempTC[2] = 0.0; o.QVapTC[2] = 0.0;
+
+#pragma unroll
+    for (int n = 0; n < 2; n++) {                                                    // :244
+        const double tmp = FKarm / log((Height - in.SfcHeight + z0m) / z0m);         // :250-253
+        const double CMn = tmp * tmp;
+        const double CHn = tmp * (FKarm / log((Height - in.SfcHeight + z0h) / z0h)); // :255-259
+        const double vr = fmax(VelAbs, VelMinForRi);
+        const double Ri = Grav / (SfcVirTemp[n] / SfcExner)                          // :261-266
+                        * (VirTemp / Exner - SfcVirTemp[n] / SfcExner)
+                        / (vr * vr)
+                        * (Height - in.SfcHeight);
+        const bool flag = (n == 0) ? true : (Frac[n] > 1e-12);                       // :268-272
+
+        // ---- BulkCoefL82 (:485-568) ----
+        double CM, CH, CQ;
+        if (flag) {
+            if (Ri > 0.0) {
+                CM = CMn / (1.0 + 10.0 * Ri / sqrt(1.0 + 5.0 * Ri));
+                CH = CHn / (1.0 + 15.0 * Ri * sqrt(1.0 + 5.0 * Ri));
+                CQ = CH;
+            } else {
+                CM = CMn * (1.0 - 10.0 * Ri
+                     / (1.0 + 75.0 * CMn * sqrt(-(Height - in.SfcHeight + z0m) / z0m * Ri)));
+                CH = CHn * (1.0 - 15.0 * Ri
+                     / (1.0 + 75.0 * CHn * sqrt(-(Height - in.SfcHeight + z0h) / z0h * Ri)));
+                CQ = CH;
+            }
+        } else {
+            CM = 0.0; CH = 0.0; CQ = 0.0;
+        }
+        CM = fmax(fmin(CM, VelBulkCoefMax), VelBulkCoefMin);
+        CH = fmax(fmin(CH, TempBulkCoefMax), TempBulkCoefMin);
+        CQ = fmax(fmin(CQ, QVapBulkCoefMax), QVapBulkCoefMin);
+
+        // ---- transfer coefficients and fluxes (:286-349) ----
+        o.VelTC[n] = CM * in.SfcPress / (GasRDry * SfcVirTemp[n])
+                   * fmin(fmax(VelAbs, VelMinForVel), VelMaxForVel);
+        o.TempTC[n] = CH * in.SfcPress / (GasRDry * SfcVirTemp[n])
+                    * fmin(fmax(VelAbs, VelMinForTemp), VelMaxForTemp);
+        o.QVapTC[n] = CQ * in.SfcPress / (GasRDry * SfcVirTemp[n])
+                    * fmin(fmax(VelAbs, VelMinForQVap), VelMaxForQVap);
+        if (flag) {
+            o.WindStressX[n] = -o.VelTC[n] * in.WindU;
+            o.WindStressY[n] = -o.VelTC[n] * in.WindV;
+            o.SenHFlx[n] = -CpDry * SfcExner * o.TempTC[n]
+                         * (in.SfcAirTemp / Exner - in.SfcTemp[n] / SfcExner);
+            o.QVapMFlx[n] = -HumdCoef * o.QVapTC[n] * (in.QVap1 - QVapSat[n]);
+            o.LatHFlx[n] = LatentHeatLocal[n] * o.QVapMFlx[n];
+            const double t2 = in.SfcTemp[n] * in.SfcTemp[n];
+            const double t4 = t2 * t2;
+            o.LUwRFlx[n] = StB * t4;
+            o.SUwRFlx[n] = in.SfcAlbedo[n] * in.SDwRFlx;
+
+            o.SfcTemp3 = o.SfcTemp3 + Frac[n] * t4;
+            o.SfcAlbedo3 = o.SfcAlbedo3 + Frac[n] * in.SfcAlbedo[n];
+            o.WindStressX[2] = o.WindStressX[2] + Frac[n] * o.WindStressX[n];
+            o.WindStressY[2] = o.WindStressY[2] + Frac[n] * o.WindStressY[n];
+            o.SenHFlx[2] = o.SenHFlx[2] + Frac[n] * o.SenHFlx[n];
+            o.QVapMFlx[2] = o.QVapMFlx[2] + Frac[n] * o.QVapMFlx[n];
+            o.LatHFlx[2] = o.LatHFlx[2] + Frac[n] * o.LatHFlx[n];
+            o.LUwRFlx[2] = o.LUwRFlx[2] + Frac[n] * o.LUwRFlx[n];
+            o.SUwRFlx[2] = o.SUwRFlx[2] + Frac[n] * o.SUwRFlx[n];
+            o.VelTC[2] = o.VelTC[2] + Frac[n] * o.VelTC[n];
+            o.TempTC[2] = o.TempTC[2] + Frac[n] * o.TempTC[n];
+            o.QVapTC[2] = o.QVapTC[2] + Frac[n] * o.QVapTC[n];
+        } else {
+            o.WindStressX[n] = 0.0; o.WindStressY[n] = 0.0; o.SenHFlx[n] = 0.0; o.QVapMFlx[n] = 0.0;
+            o.LatHFlx[n] = 0.0; o.LUwRFlx[n] = 0.0; o.SUwRFlx[n] = 0.0;
+        }
+    }
+
+    // ---- implicit surface-layer update (:353-382) ----
+    {
+        const double DFsDT1 = -CpDry * SfcExner * o.TempTC[2] / Exner;
+        const double g0 = 1.0 / (in.Coef1[0] + o.VelTC[2]);
+        const double g1 = 1.0 / (in.Coef1[1] + o.VelTC[2]);
+        const double g2 = 1.0 / (in.Coef1[2] - DFsDT1);
+        const double g3 = 1.0 / (in.Coef1[3] + HumdCoef * o.QVapTC[2]);
+        o.Del[0] = g0 * (o.WindStressX[2] + in.Coef2[0]);
+        o.Del[1] = g1 * (o.WindStressY[2] + in.Coef2[1]);
+        o.Del[2] = g2 * (o.SenHFlx[2] + in.Coef2[2]);
+        o.Del[3] = g3 * (o.QVapMFlx[2] + in.Coef2[3]);
+        double lat3 = 0.0;
+#pragma unroll
+        for (int n = 0; n < 3; n++) {
+            o.WindStressX[n] = o.WindStressX[n] - o.VelTC[n] * o.Del[0];
+            o.WindStressY[n] = o.WindStressY[n] - o.VelTC[n] * o.Del[1];
+            o.SenHFlx[n] = o.SenHFlx[n] - CpDry * SfcExner / Exner * o.TempTC[n] * o.Del[2];
+            o.QVapMFlx[n] = o.QVapMFlx[n] - HumdCoef * o.QVapTC[n] * o.Del[3];
+            if (n < 2) {
+                o.LatHFlx[n] = LatentHeatLocal[n] * o.QVapMFlx[n];
+                lat3 = lat3 + Frac[n] * o.LatHFlx[n];
+            } else {
+                // The reference indexes a_LatentHeatLocal(3) out of bounds here (:181,:370,:379);
+                // store the area-weighted composite of the corrected slots instead.
+                o.LatHFlx[n] = lat3;
+            }
+        }
+    }
+
+    // ---- net heat fluxes and dF/dTs for ocean / sea ice (:384-415) ----
+#pragma unroll
+    for (int n = 0; n < 2; n++) {
+        const bool flag = (n == 0) ? true : (Frac[n] > 1e-12);
+        if (flag) {
+            o.HFlx_ns[n] = +o.LUwRFlx[n] - in.LDwRFlx + o.LatHFlx[n] + o.SenHFlx[n];
+            o.HFlx_sr[n] = o.SUwRFlx[n] - in.SDwRFlx;
+            const double t = in.SfcTemp[n];
+            o.DHFlxDTs[n] = +4.0 * StB * (t * t * t)
+                          + CpDry * o.TempTC[n]
+                          + LatentHeatLocal[n] * HumdCoef * o.QVapTC[n]
+                            * (LatentHeatLocal[n] * QVapSat[n] / (GasRWet * (t * t)));
+        } else {
+            o.HFlx_ns[n] = 0.0; o.HFlx_sr[n] = 0.0; o.DHFlxDTs[n] = 0.0;
+        }
+    }
+}
+
+}  // namespace dccm

@@ -1,0 +1,461 @@
+// dccm_tables.cpp -- host side of the mapping tables: grid axes, Jones (1999) and bilinear
+// generators, exchange-grid construction, text/binary table files.
+//
+// One-time (init) work: the hot path only consumes the finished tables.  The generators keep
+// the reference's floating-point expressions and emission order so that indices are identical
+// and weights bit-identical to the reference algorithm, but the searches are hoisted: the
+// latitude overlap range depends only on the destination row and the longitude range only on
+// the destination column, so they are found once per row / column instead of once per cell
+// (the reference rescans both for every cell, common/grid_mapping_util_jones99.f90:230-235).
+#include <cmath>
+#include <algorithm>
+
+#include "dccm_common.h"
+
+struct dccm_table {
+    std::vector<int32_t> iD, jD, iS, jS;
+    std::vector<double> coef;
+    void push(int a, int b, int c, int d, double w)
+    {
+        iD.push_back(a); jD.push_back(b); iS.push_back(c); jS.push_back(d); coef.push_back(w);
+    }
+    void reserve(size_t n)
+    {
+        iD.reserve(n); jD.reserve(n); iS.reserve(n); jS.reserve(n); coef.reserve(n);
+    }
+};
+
+using namespace dccm;
+
+namespace {
+
+const double kPi = std::acos(-1.0);
+
+// Gauss-Legendre nodes/weights by Newton iteration on P_n (ascending nodes, sum(w) = 2).
+void gauss_legendre(int n, std::vector<double> &mu, std::vector<double> &w)
+{
+    mu.assign(n, 0.0);
+    w.assign(n, 0.0);
+    auto eval = [n](double x, double &pn, double &pnm1) {
+        double p0 = 1.0, p1 = x;
+        for (int l = 2; l <= n; l++) {
+            double p2 = ((2.0 * l - 1.0) * x * p1 - (l - 1.0) * p0) / l;
+            p0 = p1;
+            p1 = p2;
+        }
+        pn = p1;
+        pnm1 = p0;
+    };
+    for (int i = 0; i < (n + 1) / 2; i++) {
+        double x = std::cos(kPi * (i + 0.75) / (n + 0.5));
+        double pn, pm, dp = 1.0;
+        for (int it = 0; it < 100; it++) {
+            eval(x, pn, pm);
+            dp = n * (x * pn - pm) / (x * x - 1.0);
+            double dx = pn / dp;
+            x -= dx;
+            if (std::fabs(dx) < 1e-16) break;
+        }
+        eval(x, pn, pm);
+        dp = n * (x * pn - pm) / (x * x - 1.0);
+        double wi = 2.0 / ((1.0 - x * x) * dp * dp);
+        mu[i] = -x; mu[n - 1 - i] = x;
+        w[i] = wi;  w[n - 1 - i] = wi;
+    }
+    if (n % 2 == 1) mu[n / 2] = 0.0;
+}
+
+// cell edges, ref common/grid_mapping_util_jones99.f90:88-97 (halo), :142-151
+std::vector<double> lon_edges(int n, const double *x)
+{
+    std::vector<double> xc(n + 2), u(n + 1);
+    for (int i = 0; i < n; i++) xc[i + 1] = x[i];
+    xc[0] = xc[n] - 2.0 * kPi;
+    xc[n + 1] = xc[1] + 2.0 * kPi;
+    for (int i = 0; i <= n; i++) u[i] = 0.5 * (xc[i] + xc[i + 1]);
+    return u;
+}
+
+std::vector<double> lat_edges(int n, const double *wt)
+{
+    std::vector<double> v(n + 1);
+    v[0] = -kPi / 2.0;
+    for (int j = 1; j <= n - 1; j++) v[j] = std::asin(wt[j - 1] + std::sin(v[j - 1]));
+    v[n] = kPi / 2.0;
+    return v;
+}
+
+// search_OverwrapRange for one axis, ref :410-429 (first hit of the upper bound ends the scan;
+// the lower bound keeps the last hit seen before that).
+bool overlap_range(const std::vector<double> &e, int n, double lo, double hi, int &r1, int &r2)
+{
+    r1 = -1; r2 = -1;
+    for (int j = 1; j <= n; j++) {
+        if (e[j - 1] <= lo && lo <= e[j]) r1 = j;
+        if (e[j - 1] <= hi && hi <= e[j]) { r2 = j; break; }
+    }
+    return r1 > 0 && r2 > 0;
+}
+
+struct LatRow {             // per destination latitude row
+    int ry1 = 0, nyr = 0;
+    std::vector<double> w1, w2;
+};
+
+}  // namespace
+
+extern "C" int dccm_grid_gauss(int im, int jm, double *x_Lon, double *y_Lat, double *x_LonWt, double *y_LatWt)
+{
+    if (im < 1 || jm < 1) return fail(DCCM_ERR_ARG, "dccm_grid_gauss: bad size %d x %d", im, jm);
+    std::vector<double> mu, w;
+    gauss_legendre(jm, mu, w);
+    for (int j = 0; j < jm; j++) { y_Lat[j] = std::asin(mu[j]); y_LatWt[j] = w[j]; }
+    for (int i = 0; i < im; i++) { x_Lon[i] = 2.0 * kPi * i / im; x_LonWt[i] = 2.0 * kPi / im; }
+    return DCCM_OK;
+}
+
+extern "C" int dccm_grid_regular(int im, int jm, double *x_Lon, double *y_Lat, double *x_LonWt, double *y_LatWt)
+{
+    if (im < 1 || jm < 1) return fail(DCCM_ERR_ARG, "dccm_grid_regular: bad size %d x %d", im, jm);
+    for (int j = 0; j < jm; j++) {
+        double e0 = -0.5 * kPi + kPi * j / jm, e1 = -0.5 * kPi + kPi * (j + 1) / jm;
+        if (j == jm - 1) e1 = 0.5 * kPi;
+        y_Lat[j] = 0.5 * (e0 + e1);
+        y_LatWt[j] = std::sin(e1) - std::sin(e0);
+    }
+    for (int i = 0; i < im; i++) { x_Lon[i] = 2.0 * kPi * i / im; x_LonWt[i] = 2.0 * kPi / im; }
+    return DCCM_OK;
+}
+
+// ref tool/gmapgen/gmapgen_main.f90:336-405.  The O(n^2) exchange sort (:407-426) is replaced
+// by std::sort: same ascending result.
+extern "C" int dccm_grid_exchange(int jma, const double *y_LatA, const double *y_IntWtLatA,
+                                  int jmo, const double *y_IntWtLatO,
+                                  int *jms, double *y_LatS, double *y_IntWtLatS)
+{
+    if (jma < 1 || jmo < 1) return fail(DCCM_ERR_ARG, "dccm_grid_exchange: bad sizes");
+    if (jma == jmo) {
+        *jms = jmo;
+        for (int j = 0; j < jmo; j++) { y_LatS[j] = y_LatA[j]; y_IntWtLatS[j] = y_IntWtLatA[j]; }
+        return DCCM_OK;
+    }
+    std::vector<double> fa = lat_edges(jma, y_IntWtLatA), fo = lat_edges(jmo, y_IntWtLatO);
+    std::vector<double> fs;
+    fs.reserve(jma + jmo);
+    for (int j = 0; j <= jma - 1; j++) fs.push_back(fa[j]);
+    for (int j = 1; j <= jmo; j++) fs.push_back(fo[j]);
+    std::sort(fs.begin(), fs.end());
+    int n = 0;
+    for (size_t j = 1; j < fs.size(); j++) {
+        double intWt = std::sin(fs[j]) - std::sin(fs[j - 1]);
+        if (std::fabs(intWt) > 1e-12) {
+            y_LatS[n] = 0.5 * (fs[j - 1] + fs[j]);
+            y_IntWtLatS[n] = intWt;
+            n++;
+        }
+    }
+    *jms = n;
+    return DCCM_OK;
+}
+
+extern "C" int dccm_table_gen_jones99(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                                      int nxd, const double *x_LonD, int nyd, const double *y_LatD,
+                                      const double *y_LatIntWtS, const double *y_LatIntWtD,
+                                      int accuracy_order, int lon_mode, dccm_table **out)
+{
+    (void)y_LatD;
+    *out = nullptr;
+    if (nxs < 1 || nys < 1 || nxd < 1 || nyd < 1) return fail(DCCM_ERR_ARG, "jones99: bad grid sizes");
+    std::vector<double> uS = lon_edges(nxs, x_LonS), uD = lon_edges(nxd, x_LonD);
+    std::vector<double> vS = lat_edges(nys, y_LatIntWtS), vD = lat_edges(nyd, y_LatIntWtD);
+
+    // ---- longitude: per destination column (ref :402-419) ----
+    bool general = false;
+    std::vector<int> lx1(nxd + 1), lxn(nxd + 1);          // reference mode: first source column, count
+    std::vector<int> gptr, gidx; std::vector<double> gw;  // general mode: CSR of (source column, fraction)
+    if (nxs == 1 && nxd != 1) {
+        for (int i = 1; i <= nxd; i++) { lx1[i] = 1; lxn[i] = 1; }
+    } else if (nxs != 1 && nxd == 1) {
+        lx1[1] = 1; lxn[1] = nxs;
+    } else {
+        bool same = (nxs == nxd);
+        if (same) for (int i = 0; i < nxs; i++) if (x_LonS[i] != x_LonD[i]) { same = false; break; }
+        if (lon_mode == 1 && !same) {
+            if (accuracy_order > 1)
+                return fail(DCCM_ERR_UNSUPPORTED, "jones99: 2nd order needs equal longitudes or nx==1");
+            general = true;
+            gptr.assign(nxd + 1, 0);
+            for (int id = 1; id <= nxd; id++) {
+                double a = uD[id - 1], b = uD[id];
+                gptr[id - 1] = (int)gidx.size();
+                for (int shift = -1; shift <= 1; shift++) {
+                    double off = 2.0 * kPi * shift;
+                    // source columns whose shifted cell can touch [a,b]
+                    for (int m = 1; m <= nxs; m++) {
+                        double lo = uS[m - 1] + off, hi = uS[m] + off;
+                        double l = lo > a ? lo : a, h = hi < b ? hi : b;
+                        double ov = h - l;
+                        if (ov > 0.0) { gidx.push_back(m); gw.push_back(ov / (b - a)); }
+                    }
+                }
+            }
+            gptr[nxd] = (int)gidx.size();
+        } else {
+            for (int id = 1; id <= nxd; id++) {
+                int r1, r2;
+                if (!overlap_range(uS, nxs, uD[id - 1], uD[id], r1, r2))
+                    return fail(DCCM_ERR_UNSUPPORTED,
+                                "jones99: longitude overlap search failed at iD=%d; the reference generator "
+                                "needs equal longitudes or nx==1 (use lon_mode=1)", id);
+                lx1[id] = r1; lxn[id] = r2 - r1 + 1;
+            }
+        }
+    }
+
+    // ---- latitude: per destination row (ref :421-438, :314-365) ----
+    const double DLon_k = 2.0 * kPi / (double)nxd;
+    double DLon_nk, DLon_n;
+    if (nxd == 1) { DLon_nk = 2.0 * kPi / (double)nxs; DLon_n = DLon_nk; }
+    else          { DLon_nk = 2.0 * kPi / (double)nxd; DLon_n = 2.0 * kPi; }
+    std::vector<LatRow> rows(nyd + 1);
+    std::vector<double> seg(nys + 2);
+    for (int jD = 1; jD <= nyd; jD++) {
+        int r1, r2;
+        if (!overlap_range(vS, nys, vD[jD - 1], vD[jD], r1, r2))
+            return fail(DCCM_ERR_SEARCH, "jones99: latitude overlap search failed at jD=%d", jD);
+        LatRow &R = rows[jD];
+        R.ry1 = r1; R.nyr = r2 - r1 + 1;
+        R.w1.assign(R.nyr + 1, 0.0);
+        seg[0] = vD[jD - 1];
+        for (int j = 1; j <= R.nyr - 1; j++) seg[j] = vS[r1 + j - 1];
+        seg[R.nyr] = vD[jD];
+        double lat1_k = vD[jD - 1], lat2_k = vD[jD];
+        double Ak = (std::sin(lat2_k) - std::sin(lat1_k)) * DLon_k;
+        for (int j = 1; j <= R.nyr; j++) {
+            double a = seg[j - 1], b = seg[j];
+            if (general) R.w1[j] = (std::sin(b) - std::sin(a)) / (std::sin(lat2_k) - std::sin(lat1_k));
+            else         R.w1[j] = DLon_nk * (std::sin(b) - std::sin(a)) / Ak;
+        }
+        if (accuracy_order > 1) {
+            R.w2.assign(R.nyr + 1, 0.0);
+            for (int j = 1; j <= R.nyr; j++) {
+                double a = seg[j - 1], b = seg[j];
+                double na = vS[r1 + j - 2], nb = vS[r1 + j - 1];
+                double An = (std::sin(nb) - std::sin(na)) * DLon_n;
+                R.w2[j] = ((std::cos(b) + b * std::sin(b)) - (std::cos(a) + a * std::sin(a))) * DLon_nk / Ak
+                        - ((std::cos(nb) + nb * std::sin(nb)) - (std::cos(na) + na * std::sin(na))) * DLon_n * R.w1[j] / An;
+            }
+        }
+    }
+
+    // ---- emit in table-file order (ref :230-275) ----
+    dccm_table *t = new dccm_table();
+    for (int jD = 1; jD <= nyd; jD++) {
+        const LatRow &R = rows[jD];
+        for (int iD = 1; iD <= nxd; iD++) {
+            int nxr = general ? gptr[iD] - gptr[iD - 1] : lxn[iD];
+            for (int m = 1; m <= nxr; m++) {
+                int iS = general ? gidx[gptr[iD - 1] + m - 1] : lx1[iD] + m - 1;
+                for (int n = 1; n <= R.nyr; n++) {
+                    int jS = R.ry1 + n - 1;
+                    double w = general ? gw[gptr[iD - 1] + m - 1] * R.w1[n] : R.w1[n];
+                    if (std::fabs(w) > 1e-14) t->push(iD, jD, iS, jS, w);
+                    if (accuracy_order > 1) {
+                        int j1, j2;
+                        if (jS == 1)        { j1 = jS;     j2 = jS + 1; }
+                        else if (jS == nys) { j1 = jS - 1; j2 = jS; }
+                        else                { j1 = jS - 1; j2 = jS + 1; }
+                        double DLat = y_LatS[j2 - 1] - y_LatS[j1 - 1];
+                        if (std::fabs(R.w2[n]) > 1e-14) {
+                            t->push(iD, jD, iS, j1, -R.w2[n] / DLat);
+                            t->push(iD, jD, iS, j2, +R.w2[n] / DLat);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    *out = t;
+    return DCCM_OK;
+}
+
+extern "C" int dccm_table_gen_bilinear(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                                       int nxr, const double *x_LonR, int nyr, const double *y_LatR,
+                                       int lon_mode, dccm_table **out)
+{
+    *out = nullptr;
+    if (nxs < 1 || nys < 2 || nxr < 1 || nyr < 1) return fail(DCCM_ERR_ARG, "bilinear: bad grid sizes");
+    const double dlon_r = 360.0 / (double)nxr, dlon_s = 360.0 / (double)nxs;   // ref :78-79
+    dccm_table *t = new dccm_table();
+    t->reserve((size_t)nxr * nyr * ((nxr == 1) ? 2 * nxs : (nxs == 1 ? 2 : 4)));
+    // longitude part is the same for every row: hoist (ref :116-119, cal_coef :154-165)
+    std::vector<int> is1(nxr), is2(nxr);
+    std::vector<double> a1(nxr), a2(nxr);
+    if (nxr != 1 && nxs != 1) {
+        for (int ir = 1; ir <= nxr; ir++) {
+            int is = (int)(dlon_r * (ir - 1) / dlon_s) + 1;
+            int ie = is % nxs + 1;
+            double x1 = x_LonS[is - 1], x3 = x_LonS[ie - 1], xc = x_LonR[ir - 1];
+            if (lon_mode == 1 && x3 <= x1) x3 += 2.0 * kPi;
+            is1[ir - 1] = is; is2[ir - 1] = ie;
+            a1[ir - 1] = (xc - x1) / (x3 - x1);
+            a2[ir - 1] = 1.0 - a1[ir - 1];
+        }
+    }
+    for (int jr = 1; jr <= nyr; jr++) {
+        double latR = y_LatR[jr - 1];
+        int js = -1; bool extp = true;                                   // get_correspondID_latS :130-152
+        for (int j = 1; j <= nys - 1; j++)
+            if (y_LatS[j - 1] < latR && latR <= y_LatS[j]) { js = j; extp = false; break; }
+        if (extp) {
+            if (latR <= y_LatS[0]) js = 1;
+            if (latR > y_LatS[nys - 1]) js = nys;
+            if (js < 0) { delete t; return fail(DCCM_ERR_SEARCH, "bilinear: NaN latitude at row %d", jr); }
+        }
+        if (nxr == 1) {
+            if (!extp) {
+                double b1 = (latR - y_LatS[js - 1]) / (y_LatS[js] - y_LatS[js - 1]);
+                double c1 = (1.0 - b1) / nxs, c2 = b1 / nxs;
+                for (int is = 1; is <= nxs; is++) { t->push(1, jr, is, js, c1); t->push(1, jr, is, js % nys + 1, c2); }
+            } else {
+                for (int is = 1; is <= nxs; is++) t->push(1, jr, is, js, 1.0 / nxs);
+            }
+        } else if (nxs == 1) {
+            if (!extp) {
+                double b1 = (latR - y_LatS[js - 1]) / (y_LatS[js] - y_LatS[js - 1]);
+                double c1 = 1.0 - b1, c2 = b1;
+                for (int ir = 1; ir <= nxr; ir++) { t->push(ir, jr, 1, js, c1); t->push(ir, jr, 1, js % nys + 1, c2); }
+            } else {
+                for (int ir = 1; ir <= nxr; ir++) t->push(ir, jr, 1, js, 1.0);
+            }
+        } else {
+            // The reference does not test extp_flag here; js = nys would read y_LatS(nys+1).
+            // Mirror the southern edge: extrapolate from the last two rows.
+            int jlo = js, jhi = js + 1;
+            if (js == nys) { jlo = nys - 1; jhi = nys; }
+            int jhi_out = (js == nys) ? jhi : (js % nys + 1);
+            double y1 = y_LatS[jlo - 1], y3 = y_LatS[jhi - 1];
+            double b1 = (latR - y1) / (y3 - y1), b2 = 1.0 - b1;
+            for (int ir = 0; ir < nxr; ir++) {
+                t->push(ir + 1, jr, is1[ir], jlo,     a2[ir] * b2);
+                t->push(ir + 1, jr, is2[ir], jlo,     a1[ir] * b2);
+                t->push(ir + 1, jr, is2[ir], jhi_out, a1[ir] * b1);
+                t->push(ir + 1, jr, is1[ir], jhi_out, a2[ir] * b1);
+            }
+        }
+    }
+    *out = t;
+    return DCCM_OK;
+}
+
+extern "C" int dccm_table_write_text(const dccm_table *t, const char *filename)
+{
+    FILE *f = fopen(filename, "w");
+    if (!f) return fail(DCCM_ERR_IO, "cannot open %s for writing", filename);
+    std::vector<char> buf(1 << 20);
+    setvbuf(f, buf.data(), _IOFBF, buf.size());
+    for (size_t k = 0; k < t->coef.size(); k++)
+        fprintf(f, "%12d%12d%12d%12d  %24.16E\n", t->iD[k], t->jD[k], t->iS[k], t->jS[k], t->coef[k]);
+    fclose(f);
+    return DCCM_OK;
+}
+
+// list-directed read of "ir jr is js coef" (ref common/grid_mapping_util_jones99.f90:479-504);
+// blanks or commas separate, D exponents accepted, short/garbled lines end the read silently
+// like the reference's end=200.
+extern "C" int dccm_table_read_text(const char *filename, dccm_table **out)
+{
+    *out = nullptr;
+    FILE *f = fopen(filename, "r");
+    if (!f) return fail(DCCM_ERR_IO, "cannot open %s", filename);
+    dccm_table *t = new dccm_table();
+    char line[512];
+    while (fgets(line, sizeof line, f)) {
+        for (char *p = line; *p; p++) {
+            if (*p == ',') *p = ' ';
+            if (*p == 'D' || *p == 'd') *p = 'E';
+        }
+        char *p = line, *e;
+        long v[4];
+        bool ok = true;
+        for (int k = 0; k < 4; k++) {
+            v[k] = strtol(p, &e, 10);
+            if (e == p) { ok = false; break; }
+            p = e;
+        }
+        if (!ok) continue;
+        double c = strtod(p, &e);
+        if (e == p) continue;
+        t->push((int)v[0], (int)v[1], (int)v[2], (int)v[3], c);
+    }
+    fclose(f);
+    *out = t;
+    return DCCM_OK;
+}
+
+static const char kMagic[8] = {'D', 'C', 'C', 'M', 'T', 'B', 'L', '1'};
+
+extern "C" int dccm_table_write_bin(const dccm_table *t, const char *filename)
+{
+    FILE *f = fopen(filename, "wb");
+    if (!f) return fail(DCCM_ERR_IO, "cannot open %s for writing", filename);
+    int64_t n = (int64_t)t->coef.size();
+    bool ok = fwrite(kMagic, 1, 8, f) == 8 && fwrite(&n, 8, 1, f) == 1;
+    ok = ok && fwrite(t->iD.data(), 4, n, f) == (size_t)n && fwrite(t->jD.data(), 4, n, f) == (size_t)n;
+    ok = ok && fwrite(t->iS.data(), 4, n, f) == (size_t)n && fwrite(t->jS.data(), 4, n, f) == (size_t)n;
+    ok = ok && fwrite(t->coef.data(), 8, n, f) == (size_t)n;
+    fclose(f);
+    return ok ? DCCM_OK : fail(DCCM_ERR_IO, "short write to %s", filename);
+}
+
+extern "C" int dccm_table_read_bin(const char *filename, dccm_table **out)
+{
+    *out = nullptr;
+    FILE *f = fopen(filename, "rb");
+    if (!f) return fail(DCCM_ERR_IO, "cannot open %s", filename);
+    char magic[8];
+    int64_t n = 0;
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, kMagic, 8) != 0 || fread(&n, 8, 1, f) != 1 || n < 0) {
+        fclose(f);
+        return fail(DCCM_ERR_IO, "%s is not a dccm binary table", filename);
+    }
+    dccm_table *t = new dccm_table();
+    t->iD.resize(n); t->jD.resize(n); t->iS.resize(n); t->jS.resize(n); t->coef.resize(n);
+    bool ok = fread(t->iD.data(), 4, n, f) == (size_t)n && fread(t->jD.data(), 4, n, f) == (size_t)n
+           && fread(t->iS.data(), 4, n, f) == (size_t)n && fread(t->jS.data(), 4, n, f) == (size_t)n
+           && fread(t->coef.data(), 8, n, f) == (size_t)n;
+    fclose(f);
+    if (!ok) { delete t; return fail(DCCM_ERR_IO, "short read from %s", filename); }
+    *out = t;
+    return DCCM_OK;
+}
+
+extern "C" int64_t dccm_table_size(const dccm_table *t) { return t ? (int64_t)t->coef.size() : -1; }
+
+extern "C" int dccm_table_get(const dccm_table *t, int32_t *iD, int32_t *jD, int32_t *iS, int32_t *jS, double *coef)
+{
+    size_t n = t->coef.size();
+    if (iD) memcpy(iD, t->iD.data(), 4 * n);
+    if (jD) memcpy(jD, t->jD.data(), 4 * n);
+    if (iS) memcpy(iS, t->iS.data(), 4 * n);
+    if (jS) memcpy(jS, t->jS.data(), 4 * n);
+    if (coef) memcpy(coef, t->coef.data(), 8 * n);
+    return DCCM_OK;
+}
+
+extern "C" int dccm_table_index(const dccm_table *t, int gnxs, int gnxr,
+                                int32_t *send_index, int32_t *recv_index, double *coef_s)
+{
+    size_t n = t->coef.size();
+    for (size_t k = 0; k < n; k++) {
+        int64_t r = (int64_t)t->iD[k] + (int64_t)gnxr * (t->jD[k] - 1);
+        int64_t s = (int64_t)t->iS[k] + (int64_t)gnxs * (t->jS[k] - 1);
+        if (r > INT32_MAX || s > INT32_MAX) return fail(DCCM_ERR_ARG, "table index overflows default INTEGER");
+        recv_index[k] = (int32_t)r;
+        send_index[k] = (int32_t)s;
+        coef_s[k] = t->coef[k];
+    }
+    return DCCM_OK;
+}
+
+extern "C" void dccm_table_free(dccm_table *t) { delete t; }

@@ -1,0 +1,430 @@
+// dccm_vdiff.cu -- K3/K4: column-wise implicit vertical-diffusion / surface coupling solve.
+//
+// Replaces dcpam_sfc_implicit_coupling_mod (ref atm/dcpam_sfc_implicit_coupling_mod.f90):
+//   K3 = SfcImplicitCoupling_VDiffForward (:72-378) + Solve_TriDiagSystem_Forward (:380-402)
+//   K4 = SfcImplicitCoupling_VDiffBackward (:25-70) + Solve_TriDiagSystem_Backward (:404-418)
+//
+// One thread per column; arrays are (column, level) with the column index fastest, so every
+// per-level access of a warp is one coalesced 256-byte request.  The reference builds three
+// full tridiagonal matrices, copies two of them, and sweeps each system separately with
+// whole-array statements (every 3-D array is streamed several times).  Here the transfer
+// coefficients, the three matrix rows, the right-hand sides and the top-down elimination of
+// one level are all evaluated in registers while the column is walked ONCE from k = kmax
+// down to 2: each input is read exactly once and only what the backward pass needs is
+// written -- the swept diagonal b'(k) of the three systems (a' == 1 and c' == 0 are implied)
+// and the swept right-hand sides r'(k).
+//
+// Elimination stops at k = 2: the reference divides by Mtx(k=1,-1) = 0 at k = 1 (defect C-1,
+// see DESIGN.md); row 1 is never read again, so RHS(1) is returned un-swept.
+//
+// FAST = false keeps the reference's operation order with IEEE divisions (the library is
+// built with -fmad=false), which makes K3/K4 bit-identical to the reference loops.
+// FAST = true shares reciprocals between the systems of one level (fewer fp64 divisions,
+// <= a few ulp per level from the reference; verified to the 1e-12 tolerance).
+#include <cuda_runtime.h>
+
+#include "dccm_common.h"
+
+using namespace dccm;
+
+struct dccm_vdiff {
+    int imax = 0, jmax = 0, kmax = 0, ncmax = 0, iq = 0;   // iq: 0-based water-vapour tracer
+    double Grav = 0, CpDry = 0, GasRDry = 0, DelTime = 0;
+    int fast = 0;
+    int64_t NC = 0;
+    double *bUV = nullptr, *bT = nullptr, *bQ = nullptr;   // swept diagonals, (NC, kmax)
+    DevBuf in_buf, out_buf;                                 // scratch of the host entry points
+};
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kMaxTracer = 4;
+
+struct FwdArgs {
+    const double *FX, *FY, *FH, *FQ;
+    const double *Press, *zExner, *rExner, *VirTemp, *Height, *DiffV, *DiffT, *DiffQ;
+    double *DU, *DV, *DT, *DQ, *Coef1, *Coef2;
+    double *bUV, *bT, *bQ;
+    int64_t NC;
+    int K, iq;
+    double Grav, CpDry, GasRDry, DelTime;
+};
+
+template <int NQ, bool FAST>
+__global__ void __launch_bounds__(kThreads) vdiff_forward_kernel(const FwdArgs a)
+{
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t NC = a.NC;
+    if (c >= NC) return;
+    const int K = a.K;
+    const double Grav = a.Grav, CpDry = a.CpDry, GasRDry = a.GasRDry;
+    const double twodt = 2.0 * a.DelTime;
+#define HL(p, l) __ldg(&(p)[c + NC * (int64_t)(l)])          /* half level l = 0..K */
+#define FL(p, k) __ldg(&(p)[c + NC * (int64_t)((k) - 1)])    /* full level k = 1..K */
+#define QH(n, l) __ldg(&a.FQ[c + NC * ((int64_t)(l) + (int64_t)(K + 1) * (n))])
+
+    // state carried down the column (index "hi" = level k, "lo" = level k-1)
+    double P_hi = HL(a.Press, K), H_hi = FL(a.Height, K);
+    double zE_hi = FL(a.zExner, K), zE_hi2 = 0.0, rE_hi = 0.0;
+    double TV_hi = 0.0, TT_hi = 0.0, TQ_hi = 0.0;              // transfer coefficients are 0 at k = kmax (:189-194)
+    double FX_hi = HL(a.FX, K), FY_hi = HL(a.FY, K), FH_hi = HL(a.FH, K);
+    double FQ_hi[NQ];
+#pragma unroll
+    for (int n = 0; n < NQ; n++) FQ_hi[n] = QH(n, K);
+    double bUVn = 0.0, bTn = 0.0, bQn = 0.0, rUn = 0.0, rVn = 0.0, rTn = 0.0;
+    double rQn[NQ];
+#pragma unroll
+    for (int n = 0; n < NQ; n++) rQn[n] = 0.0;
+    double rU2 = 0.0, rV2 = 0.0, rT2 = 0.0, rQ2 = 0.0;
+
+    for (int k = K; k >= 2; --k) {
+        const int l = k - 1;
+        const double P_lo = HL(a.Press, l), Tv = HL(a.VirTemp, l), H_lo = FL(a.Height, l);
+        const double dV = HL(a.DiffV, l), dT = HL(a.DiffT, l), dQ = HL(a.DiffQ, l);
+        const double rE_lo = HL(a.rExner, l), zE_lo = FL(a.zExner, l);
+        const double FX_lo = HL(a.FX, l), FY_lo = HL(a.FY, l), FH_lo = HL(a.FH, l);
+        double FQ_lo[NQ];
+#pragma unroll
+        for (int n = 0; n < NQ; n++) FQ_lo[n] = QH(n, l);
+
+        // transfer coefficients at half level l (:196-203)
+        double tmp;
+        if (FAST) tmp = P_lo / (GasRDry * Tv * (H_hi - H_lo));
+        else      tmp = P_lo / (GasRDry * Tv) / (H_hi - H_lo);
+        const double TV_lo = dV * tmp, TT_lo = dT * tmp, TQ_lo = dQ * tmp;
+
+        // matrix rows k (:207-293) and right-hand sides (:297-311)
+        double mass, aT, bT, cT;
+        if (FAST) {
+            mass = -(P_hi - P_lo) * (1.0 / (Grav * twodt));
+            const double izhi = 1.0 / zE_hi;
+            aT = -CpDry * rE_lo * TT_lo / zE_lo;
+            bT = CpDry * mass + CpDry * rE_lo * TT_lo * izhi;
+            if (k < K) bT += CpDry * rE_hi * TT_hi * izhi;
+            cT = (k < K) ? -CpDry * rE_hi * TT_hi / zE_hi2 : 0.0;
+        } else {
+            mass = -(P_hi - P_lo) / Grav / twodt;
+            aT = -CpDry * rE_lo / zE_lo * TT_lo;
+            bT = -CpDry * (P_hi - P_lo) / Grav / twodt + CpDry * rE_lo / zE_hi * TT_lo;
+            if (k < K) bT = bT + CpDry * rE_hi / zE_hi * TT_hi;
+            cT = (k < K) ? -CpDry * rE_hi / zE_hi2 * TT_hi : 0.0;
+        }
+        const double aUV = -TV_lo, cUV = -TV_hi;
+        double bUV = mass + TV_lo;
+        if (k < K) bUV = bUV + TV_hi;
+        const double aQ = -TQ_lo, cQ = -TQ_hi;
+        double bQ = mass + TQ_lo;
+        if (k < K) bQ = bQ + TQ_hi;
+        const double rU = -(FX_hi - FX_lo), rV = -(FY_hi - FY_lo), rT = -(FH_hi - FH_lo);
+        double rQ[NQ];
+#pragma unroll
+        for (int n = 0; n < NQ; n++) rQ[n] = -(FQ_hi[n] - FQ_lo[n]);
+
+        // top-down elimination of level k (:388-400)
+        double bUVp, bTp, bQp, rUp, rVp, rTp, rQp[NQ];
+        if (k == K) {
+            if (FAST) {
+                const double iu = 1.0 / aUV, it = 1.0 / aT, iq = 1.0 / aQ;
+                bUVp = bUV * iu; rUp = rU * iu; rVp = rV * iu;
+                bTp = bT * it; rTp = rT * it;
+                bQp = bQ * iq;
+#pragma unroll
+                for (int n = 0; n < NQ; n++) rQp[n] = rQ[n] * iq;
+            } else {
+                bUVp = bUV / aUV; rUp = rU / aUV; rVp = rV / aUV;
+                bTp = bT / aT; rTp = rT / aT;
+                bQp = bQ / aQ;
+#pragma unroll
+                for (int n = 0; n < NQ; n++) rQp[n] = rQ[n] / aQ;
+            }
+        } else {
+            const double dUV = aUV * bUVn, dT_ = aT * bTn, dQ_ = aQ * bQn;
+            if (FAST) {
+                const double iu = 1.0 / dUV, it = 1.0 / dT_, iq = 1.0 / dQ_;
+                bUVp = (bUV * bUVn - cUV) * iu;
+                rUp = (rU * bUVn - cUV * rUn) * iu;
+                rVp = (rV * bUVn - cUV * rVn) * iu;
+                bTp = (bT * bTn - cT) * it;
+                rTp = (rT * bTn - cT * rTn) * it;
+                bQp = (bQ * bQn - cQ) * iq;
+#pragma unroll
+                for (int n = 0; n < NQ; n++) rQp[n] = (rQ[n] * bQn - cQ * rQn[n]) * iq;
+            } else {
+                bUVp = (bUV * bUVn - cUV) / dUV;
+                rUp = (rU * bUVn - cUV * rUn) / dUV;
+                rVp = (rV * bUVn - cUV * rVn) / dUV;
+                bTp = (bT * bTn - cT) / dT_;
+                rTp = (rT * bTn - cT * rTn) / dT_;
+                bQp = (bQ * bQn - cQ) / dQ_;
+#pragma unroll
+                for (int n = 0; n < NQ; n++) rQp[n] = (rQ[n] * bQn - cQ * rQn[n]) / dQ_;
+            }
+        }
+        const int64_t o = c + NC * (int64_t)(k - 1);
+        a.bUV[o] = bUVp; a.bT[o] = bTp; a.bQ[o] = bQp;
+        a.DU[o] = rUp; a.DV[o] = rVp; a.DT[o] = rTp;
+#pragma unroll
+        for (int n = 0; n < NQ; n++) a.DQ[o + NC * (int64_t)K * n] = rQp[n];
+
+        // shift down one level
+        P_hi = P_lo; H_hi = H_lo; zE_hi2 = zE_hi; zE_hi = zE_lo; rE_hi = rE_lo;
+        TV_hi = TV_lo; TT_hi = TT_lo; TQ_hi = TQ_lo;
+        FX_hi = FX_lo; FY_hi = FY_lo; FH_hi = FH_lo;
+        bUVn = bUVp; bTn = bTp; bQn = bQp; rUn = rUp; rVn = rVp; rTn = rTp;
+#pragma unroll
+        for (int n = 0; n < NQ; n++) { FQ_hi[n] = FQ_lo[n]; rQn[n] = rQp[n]; }
+        if (k == 2) {
+            rU2 = rUp; rV2 = rVp; rT2 = rTp;
+#pragma unroll
+            for (int n = 0; n < NQ; n++) if (n == a.iq) rQ2 = rQp[n];
+        }
+    }
+
+    // level 1: un-swept RHS (= Coef2 before the correction, :313-316) and the coupling
+    // coefficients (:344-376).  Now "hi" = level 1.
+    {
+        const double P0 = HL(a.Press, 0);
+        const double rU1 = -(FX_hi - HL(a.FX, 0)), rV1 = -(FY_hi - HL(a.FY, 0)), rT1 = -(FH_hi - HL(a.FH, 0));
+        double rQ1v = 0.0;
+#pragma unroll
+        for (int n = 0; n < NQ; n++) {
+            const double r = -(FQ_hi[n] - QH(n, 0));
+            a.DQ[c + NC * (int64_t)K * n] = r;
+            if (n == a.iq) rQ1v = r;
+        }
+        a.DU[c] = rU1; a.DV[c] = rV1; a.DT[c] = rT1;
+
+        const double tmp1 = -(P_hi - P0) / Grav / twodt;
+        const double DFADUV1 = TV_hi, DFADUV2 = -TV_hi;
+        const double c1uv = tmp1 + DFADUV1 - DFADUV2 / bUVn;
+        a.Coef1[c] = c1uv;
+        a.Coef2[c] = rU1 - DFADUV2 * rU2 / bUVn;
+        a.Coef1[c + NC] = c1uv;
+        a.Coef2[c + NC] = rV1 - DFADUV2 * rV2 / bUVn;
+        const double DFADT1 = CpDry * rE_hi * TT_hi / zE_hi;
+        const double DFADT2 = -CpDry * rE_hi * TT_hi / zE_hi2;
+        a.Coef1[c + 2 * NC] = CpDry * tmp1 + DFADT1 - DFADT2 / bTn;
+        a.Coef2[c + 2 * NC] = rT1 - DFADT2 * rT2 / bTn;
+        const double DFADQ1 = TQ_hi, DFADQ2 = -TQ_hi;
+        a.Coef1[c + 3 * NC] = tmp1 + DFADQ1 - DFADQ2 / bQn;
+        a.Coef2[c + 3 * NC] = rQ1v - DFADQ2 * rQ2 / bQn;
+    }
+#undef HL
+#undef FL
+#undef QH
+}
+
+struct BwdArgs {
+    double *DU, *DV, *DT, *DQ;
+    const double *bUV, *bT, *bQ;
+    const double *level1;
+    int64_t NC;
+    int K, iq;
+    double DelTime;
+};
+
+template <int NQ>
+__global__ void __launch_bounds__(kThreads) vdiff_backward_kernel(const BwdArgs a)
+{
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t NC = a.NC;
+    if (c >= NC) return;
+    const int K = a.K;
+    const double twodt = 2.0 * a.DelTime;
+    // level 1: the surface-layer increment delivered by the surface component
+    // (ref atm/dccm_atm_mod.f90:832-835)
+    double xU, xV, xT, xQ[NQ];
+    if (a.level1) {
+        xU = a.level1[c]; xV = a.level1[c + NC]; xT = a.level1[c + 2 * NC];
+    } else {
+        xU = a.DU[c]; xV = a.DV[c]; xT = a.DT[c];
+    }
+#pragma unroll
+    for (int n = 0; n < NQ; n++) {
+        xQ[n] = a.DQ[c + NC * (int64_t)K * n];
+        if (a.level1 && n == a.iq) xQ[n] = a.level1[c + 3 * NC];
+    }
+    a.DU[c] = xU / twodt; a.DV[c] = xV / twodt; a.DT[c] = xT / twodt;           // :54-63
+#pragma unroll
+    for (int n = 0; n < NQ; n++) a.DQ[c + NC * (int64_t)K * n] = xQ[n] / twodt;
+    for (int k = 2; k <= K; k++) {                                              // :414-416
+        const int64_t o = c + NC * (int64_t)(k - 1);
+        const double bUV = __ldg(&a.bUV[o]), bT = __ldg(&a.bT[o]), bQ = __ldg(&a.bQ[o]);
+        xU = (a.DU[o] - xU) / bUV;
+        xV = (a.DV[o] - xV) / bUV;
+        xT = (a.DT[o] - xT) / bT;
+        a.DU[o] = xU / twodt; a.DV[o] = xV / twodt; a.DT[o] = xT / twodt;
+#pragma unroll
+        for (int n = 0; n < NQ; n++) {
+            const int64_t oq = o + NC * (int64_t)K * n;
+            xQ[n] = (a.DQ[oq] - xQ[n]) / bQ;
+            a.DQ[oq] = xQ[n] / twodt;
+        }
+    }
+}
+
+template <bool FAST>
+void launch_forward(int nq, const FwdArgs &a, unsigned grid, cudaStream_t st)
+{
+    switch (nq) {
+    case 1: vdiff_forward_kernel<1, FAST><<<grid, kThreads, 0, st>>>(a); break;
+    case 2: vdiff_forward_kernel<2, FAST><<<grid, kThreads, 0, st>>>(a); break;
+    case 3: vdiff_forward_kernel<3, FAST><<<grid, kThreads, 0, st>>>(a); break;
+    default: vdiff_forward_kernel<4, FAST><<<grid, kThreads, 0, st>>>(a); break;
+    }
+}
+
+}  // namespace
+
+extern "C" int dccm_vdiff_create(int imax, int jmax, int kmax, int ncmax, int index_h2ovap,
+                                 double Grav, double CpDry, double GasRDry, double DelTime, dccm_vdiff **out)
+{
+    *out = nullptr;
+    if (imax < 1 || jmax < 1) return fail(DCCM_ERR_ARG, "dccm_vdiff_create: bad horizontal size");
+    if (kmax < 2) return fail(DCCM_ERR_ARG, "dccm_vdiff_create: kmax must be >= 2 (the coupling coefficients use level 2)");
+    if (ncmax < 1 || ncmax > kMaxTracer)
+        return fail(DCCM_ERR_ARG, "dccm_vdiff_create: ncmax=%d outside 1..%d", ncmax, kMaxTracer);
+    if (index_h2ovap < 1 || index_h2ovap > ncmax) return fail(DCCM_ERR_ARG, "dccm_vdiff_create: IndexH2OVap out of range");
+    if (!(DelTime > 0.0) || !(Grav > 0.0)) return fail(DCCM_ERR_ARG, "dccm_vdiff_create: DelTime and Grav must be positive");
+    int rc = ensure_device();
+    if (rc) return rc;
+    dccm_vdiff *h = new dccm_vdiff();
+    h->imax = imax; h->jmax = jmax; h->kmax = kmax; h->ncmax = ncmax; h->iq = index_h2ovap - 1;
+    h->Grav = Grav; h->CpDry = CpDry; h->GasRDry = GasRDry; h->DelTime = DelTime;
+    h->NC = (int64_t)imax * jmax;
+    size_t bytes = sizeof(double) * (size_t)h->NC * kmax;
+    cudaError_t e = cudaMalloc(&h->bUV, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&h->bT, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&h->bQ, bytes);
+    if (e != cudaSuccess) {
+        dccm_vdiff_destroy(h);
+        return fail(DCCM_ERR_CUDA, "dccm_vdiff_create: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return DCCM_OK;
+}
+
+extern "C" void dccm_vdiff_destroy(dccm_vdiff *h)
+{
+    if (!h) return;
+    cudaFree(h->bUV); cudaFree(h->bT); cudaFree(h->bQ);
+    h->in_buf.release(); h->out_buf.release();
+    delete h;
+}
+
+extern "C" int dccm_vdiff_set_mode(dccm_vdiff *h, int fast)
+{
+    if (!h) return fail(DCCM_ERR_ARG, "dccm_vdiff_set_mode: null handle");
+    h->fast = fast ? 1 : 0;
+    return DCCM_OK;
+}
+
+extern "C" int dccm_vdiff_forward_device(dccm_vdiff *h,
+    const double *FX, const double *FY, const double *FH, const double *FQ,
+    const double *Press, const double *zExner, const double *rExner,
+    const double *VirTemp, const double *Height,
+    const double *DiffV, const double *DiffT, const double *DiffQ,
+    double *DU, double *DV, double *DT, double *DQ, double *Coef1, double *Coef2, void *stream)
+{
+    if (!h) return fail(DCCM_ERR_ARG, "dccm_vdiff_forward: null handle");
+    FwdArgs a;
+    a.FX = FX; a.FY = FY; a.FH = FH; a.FQ = FQ; a.Press = Press; a.zExner = zExner; a.rExner = rExner;
+    a.VirTemp = VirTemp; a.Height = Height; a.DiffV = DiffV; a.DiffT = DiffT; a.DiffQ = DiffQ;
+    a.DU = DU; a.DV = DV; a.DT = DT; a.DQ = DQ; a.Coef1 = Coef1; a.Coef2 = Coef2;
+    a.bUV = h->bUV; a.bT = h->bT; a.bQ = h->bQ;
+    a.NC = h->NC; a.K = h->kmax; a.iq = h->iq;
+    a.Grav = h->Grav; a.CpDry = h->CpDry; a.GasRDry = h->GasRDry; a.DelTime = h->DelTime;
+    const unsigned grid = (unsigned)((h->NC + kThreads - 1) / kThreads);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (h->fast) launch_forward<true>(h->ncmax, a, grid, st);
+    else         launch_forward<false>(h->ncmax, a, grid, st);
+    DCCM_CUDA_TRY(cudaGetLastError());
+    return DCCM_OK;
+}
+
+extern "C" int dccm_vdiff_backward_device(dccm_vdiff *h, double *DU, double *DV, double *DT, double *DQ,
+                                          const double *level1, void *stream)
+{
+    if (!h) return fail(DCCM_ERR_ARG, "dccm_vdiff_backward: null handle");
+    BwdArgs a;
+    a.DU = DU; a.DV = DV; a.DT = DT; a.DQ = DQ;
+    a.bUV = h->bUV; a.bT = h->bT; a.bQ = h->bQ; a.level1 = level1;
+    a.NC = h->NC; a.K = h->kmax; a.iq = h->iq; a.DelTime = h->DelTime;
+    const unsigned grid = (unsigned)((h->NC + kThreads - 1) / kThreads);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (h->ncmax) {
+    case 1: vdiff_backward_kernel<1><<<grid, kThreads, 0, st>>>(a); break;
+    case 2: vdiff_backward_kernel<2><<<grid, kThreads, 0, st>>>(a); break;
+    case 3: vdiff_backward_kernel<3><<<grid, kThreads, 0, st>>>(a); break;
+    default: vdiff_backward_kernel<4><<<grid, kThreads, 0, st>>>(a); break;
+    }
+    DCCM_CUDA_TRY(cudaGetLastError());
+    return DCCM_OK;
+}
+
+extern "C" int dccm_vdiff_forward_host(dccm_vdiff *h,
+    const double *FX, const double *FY, const double *FH, const double *FQ,
+    const double *Press, const double *zExner, const double *rExner,
+    const double *VirTemp, const double *Height,
+    const double *DiffV, const double *DiffT, const double *DiffQ,
+    double *DU, double *DV, double *DT, double *DQ, double *Coef1, double *Coef2)
+{
+    if (!h) return fail(DCCM_ERR_ARG, "dccm_vdiff_forward: null handle");
+    const size_t NC = (size_t)h->NC, K = h->kmax, nc = h->ncmax;
+    const size_t half = NC * (K + 1), full = NC * K;
+    // inputs: 8 half-level + 2 full-level + nc half-level tracer fluxes
+    int rc = h->in_buf.reserve(sizeof(double) * (half * (8 + nc) + full * 2));
+    if (rc) return rc;
+    rc = h->out_buf.reserve(sizeof(double) * (full * (3 + nc) + NC * 8));
+    if (rc) return rc;
+    double *p = h->in_buf.as<double>();
+    auto take = [&](size_t n) { double *q = p; p += n; return q; };
+    double *dFX = take(half), *dFY = take(half), *dFH = take(half), *dFQ = take(half * nc);
+    double *dP = take(half), *dzE = take(full), *drE = take(half), *dTv = take(half), *dH = take(full);
+    double *dDV = take(half), *dDT = take(half), *dDQ = take(half);
+    p = h->out_buf.as<double>();
+    double *oDU = take(full), *oDV = take(full), *oDT = take(full), *oDQ = take(full * nc);
+    double *oC1 = take(NC * 4), *oC2 = take(NC * 4);
+    cudaStream_t st = 0;
+    auto h2d = [&](double *d, const double *s, size_t n) {
+        return cudaMemcpyAsync(d, s, sizeof(double) * n, cudaMemcpyHostToDevice, st);
+    };
+    DCCM_CUDA_TRY(h2d(dFX, FX, half)); DCCM_CUDA_TRY(h2d(dFY, FY, half)); DCCM_CUDA_TRY(h2d(dFH, FH, half));
+    DCCM_CUDA_TRY(h2d(dFQ, FQ, half * nc)); DCCM_CUDA_TRY(h2d(dP, Press, half)); DCCM_CUDA_TRY(h2d(dzE, zExner, full));
+    DCCM_CUDA_TRY(h2d(drE, rExner, half)); DCCM_CUDA_TRY(h2d(dTv, VirTemp, half)); DCCM_CUDA_TRY(h2d(dH, Height, full));
+    DCCM_CUDA_TRY(h2d(dDV, DiffV, half)); DCCM_CUDA_TRY(h2d(dDT, DiffT, half)); DCCM_CUDA_TRY(h2d(dDQ, DiffQ, half));
+    rc = dccm_vdiff_forward_device(h, dFX, dFY, dFH, dFQ, dP, dzE, drE, dTv, dH, dDV, dDT, dDQ,
+                                   oDU, oDV, oDT, oDQ, oC1, oC2, st);
+    if (rc) return rc;
+    auto d2h = [&](double *d, const double *s, size_t n) {
+        return cudaMemcpyAsync(d, s, sizeof(double) * n, cudaMemcpyDeviceToHost, st);
+    };
+    DCCM_CUDA_TRY(d2h(DU, oDU, full)); DCCM_CUDA_TRY(d2h(DV, oDV, full)); DCCM_CUDA_TRY(d2h(DT, oDT, full));
+    DCCM_CUDA_TRY(d2h(DQ, oDQ, full * nc)); DCCM_CUDA_TRY(d2h(Coef1, oC1, NC * 4)); DCCM_CUDA_TRY(d2h(Coef2, oC2, NC * 4));
+    DCCM_CUDA_TRY(cudaStreamSynchronize(st));
+    return DCCM_OK;
+}
+
+extern "C" int dccm_vdiff_backward_host(dccm_vdiff *h, double *DU, double *DV, double *DT, double *DQ)
+{
+    if (!h) return fail(DCCM_ERR_ARG, "dccm_vdiff_backward: null handle");
+    const size_t NC = (size_t)h->NC, K = h->kmax, nc = h->ncmax, full = NC * K;
+    int rc = h->out_buf.reserve(sizeof(double) * (full * (3 + nc) + NC * 8));
+    if (rc) return rc;
+    double *p = h->out_buf.as<double>();
+    double *oDU = p, *oDV = p + full, *oDT = p + 2 * full, *oDQ = p + 3 * full;
+    cudaStream_t st = 0;
+    DCCM_CUDA_TRY(cudaMemcpyAsync(oDU, DU, sizeof(double) * full, cudaMemcpyHostToDevice, st));
+    DCCM_CUDA_TRY(cudaMemcpyAsync(oDV, DV, sizeof(double) * full, cudaMemcpyHostToDevice, st));
+    DCCM_CUDA_TRY(cudaMemcpyAsync(oDT, DT, sizeof(double) * full, cudaMemcpyHostToDevice, st));
+    DCCM_CUDA_TRY(cudaMemcpyAsync(oDQ, DQ, sizeof(double) * full * nc, cudaMemcpyHostToDevice, st));
+    rc = dccm_vdiff_backward_device(h, oDU, oDV, oDT, oDQ, nullptr, st);
+    if (rc) return rc;
+    DCCM_CUDA_TRY(cudaMemcpyAsync(DU, oDU, sizeof(double) * full, cudaMemcpyDeviceToHost, st));
+    DCCM_CUDA_TRY(cudaMemcpyAsync(DV, oDV, sizeof(double) * full, cudaMemcpyDeviceToHost, st));
+    DCCM_CUDA_TRY(cudaMemcpyAsync(DT, oDT, sizeof(double) * full, cudaMemcpyDeviceToHost, st));
+    DCCM_CUDA_TRY(cudaMemcpyAsync(DQ, oDQ, sizeof(double) * full * nc, cudaMemcpyDeviceToHost, st));
+    DCCM_CUDA_TRY(cudaStreamSynchronize(st));
+    return DCCM_OK;
+}

@@ -1,0 +1,188 @@
+/*
+ * dccm_b200.h -- C ABI of the B200-native surface-exchange path of Dennou-CCM.
+ *
+ * This is the drop-in boundary: every entry point is what an ISO_C_BINDING shim with the
+ * reference's UNCHANGED Fortran interface binds to (shims: fortran/, wiring: INTEGRATION.md).
+ * Plain pointers and sizes only; default Fortran INTEGER = int32_t, REAL(DP) = double;
+ * all arrays are Fortran column-major; indices stored in tables are 1-based as in the
+ * reference.  `ref:` citations are file:line under the reference tree.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; dccm_last_error() gives the
+ *     message (thread-local).  There is NO CPU fallback: a call that needs the GPU fails
+ *     with DCCM_ERR_CUDA when no sm_100 device is usable.
+ *   - *_host entry points take HOST buffers and are synchronous (results are in the host
+ *     arrays on return), i.e. exactly the reference semantics.
+ *   - *_device entry points take DEVICE pointers and a cudaStream_t (as void*) and are
+ *     asynchronous on that stream; they are what the resident exchange step is built from.
+ */
+#ifndef DCCM_B200_H
+#define DCCM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCCM_OK            0
+#define DCCM_ERR_ARG       1
+#define DCCM_ERR_CUDA      2
+#define DCCM_ERR_IO        3
+#define DCCM_ERR_UNSUPPORTED 4   /* grid pair the reference generator cannot handle (lon_mode 0) */
+#define DCCM_ERR_SEARCH    5     /* "Exception.." stop of search_OverwrapRange */
+
+/* ------------------------------------------------------------------ runtime */
+const char *dccm_last_error(void);
+const char *dccm_build_info(void);
+int dccm_init(int device);                 /* cudaSetDevice + capability check (sm_100) */
+int dccm_device_count(int *count);
+int dccm_sync(void *stream);               /* cudaStreamSynchronize */
+
+/* ------------------------------------------------------------------ grids
+ * Stand-ins for the SPML w_module axes gmapgen uses (ref tool/gmapgen/gmapgen_main.f90:256-307). */
+int dccm_grid_gauss(int im, int jm, double *x_Lon, double *y_Lat, double *x_LonWt, double *y_LatWt);
+int dccm_grid_regular(int im, int jm, double *x_Lon, double *y_Lat, double *x_LonWt, double *y_LatWt);
+/* generate_surface_exchage_grid, ref tool/gmapgen/gmapgen_main.f90:336-405.
+ * y_LatS / y_IntWtLatS need room for jma+jmo-1 values; longitudes are the atmosphere's. */
+int dccm_grid_exchange(int jma, const double *y_LatA, const double *y_IntWtLatA,
+                       int jmo, const double *y_IntWtLatO,
+                       int *jms, double *y_LatS, double *y_IntWtLatS);
+
+/* ------------------------------------------------------------------ mapping tables */
+typedef struct dccm_table dccm_table;
+
+/* gen_gridmapfile_lonlat2lonlat (Jones 1999), ref common/grid_mapping_util_jones99.f90:35-442.
+ * lon_mode 0: reference behaviour (equal longitudes or nx==1 on one side; anything else ->
+ * DCCM_ERR_UNSUPPORTED).  lon_mode 1: generalised longitude overlap for mismatched longitudes
+ * (first order only); identical to mode 0 on the grid pairs the reference supports. */
+int dccm_table_gen_jones99(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                           int nxd, const double *x_LonD, int nyd, const double *y_LatD,
+                           const double *y_LatIntWtS, const double *y_LatIntWtD,
+                           int accuracy_order, int lon_mode, dccm_table **out);
+/* gen_gridmapfile_lonlat2lonlat (bilinear), ref common/grid_mapping_util.f90:32-177.
+ * lon_mode 1 unwraps the east neighbour by 2*pi at the wrap column (ref :117-119 does not). */
+int dccm_table_gen_bilinear(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                            int nxr, const double *x_LonR, int nyr, const double *y_LatR,
+                            int lon_mode, dccm_table **out);
+/* The reference's on-disk format: one entry per line "iD jD iS jS coef", list-directed
+ * (ref common/grid_mapping_util_jones99.f90:246-247, :479-504). */
+int dccm_table_write_text(const dccm_table *t, const char *filename);
+int dccm_table_read_text(const char *filename, dccm_table **out);
+/* compact binary form of the same entries */
+int dccm_table_write_bin(const dccm_table *t, const char *filename);
+int dccm_table_read_bin(const char *filename, dccm_table **out);
+int64_t dccm_table_size(const dccm_table *t);
+int dccm_table_get(const dccm_table *t, int32_t *iD, int32_t *jD, int32_t *iS, int32_t *jS, double *coef);
+/* set_mappingTable_interpCoef, ref common/grid_mapping_util_jones99.f90:446-506
+ * (recv_index = iD + GNXR*(jD-1), send_index = iS + GNXS*(jS-1)). */
+int dccm_table_index(const dccm_table *t, int gnxs, int gnxr,
+                     int32_t *send_index, int32_t *recv_index, double *coef_s);
+void dccm_table_free(dccm_table *t);
+
+/* ------------------------------------------------------------------ remap apply (K1)
+ * Replaces interpolate_data / interpolate_data_latlon,
+ * ref common/interpolate_data.f90:1-17, common/interpolation_data_latlon_mod.f90:274-306. */
+typedef struct dccm_remap dccm_remap;
+
+/* Built once where the reference calls set_operation_index + set_interpolate_coef
+ * (ref common/interpolation_data_latlon_mod.f90:116-154, :219-270): local 1-based
+ * send/recv indices and coefS in operation (= table) order. */
+int dccm_remap_create(int64_t nops, const int32_t *send_index, const int32_t *recv_index,
+                      const double *coef, int n_send, int n_recv, dccm_remap **out);
+void dccm_remap_destroy(dccm_remap *h);
+int64_t dccm_remap_nnz(const dccm_remap *h);
+/* 0 = general CSR, 1 = separable lat x lon stencil (tables compressed to O(I+J)) */
+int dccm_remap_kind(const dccm_remap *h);
+/* recv_data(:,:) = 0 ; recv(r_i,d) += send(s_i,d)*coef(i), d = 1..num_of_data  (ref :293-302) */
+int dccm_remap_apply_host(dccm_remap *h, const double *send, int sn1, int sn2,
+                          double *recv, int rn1, int rn2, int num_of_data);
+int dccm_remap_apply_device(dccm_remap *h, const double *d_send, int sn1,
+                            double *d_recv, int rn1, int rn2, int num_of_data, void *stream);
+/* registry keyed like the reference's operation_index(recv_model, send_model, mapping_tag)
+ * (ref :88, :289); ids are Jcup component numbers (1-based), tags as in
+ * common/dccm_common_params_mod.f90:64-69. */
+int dccm_interp_register(int recv_model, int send_model, int mapping_tag, dccm_remap *h);
+int dccm_interpolate_data(int recv_model, int send_model, int mapping_tag,
+                          int sn1, int sn2, const double *send_data,
+                          int rn1, int rn2, double *recv_data, int num_of_data);
+
+/* ------------------------------------------------------------------ bulk flux (K2)
+ * Replaces DSFCM_Util_SfcBulkFlux_Get, ref sfc/DSFCM_Util_SfcBulkFlux_mod.f90:108-439
+ * (+ BulkCoefL82 :443-572, limits :574-591).  Argument order = the Fortran dummy order. */
+int dccm_bulkflux_get_host(int IA, int JA,
+    double *xya_WindStressX, double *xya_WindStressY,
+    double *xya_SenHFlx, double *xya_QVapMFlx, double *xya_LatHFlx,
+    double *xya_SfcVelTransCoef, double *xya_SfcTempTransCoef, double *xya_SfcQVapTransCoef,
+    double *xya_DelVarImplCPL,
+    double *xya_SUwRFlx, double *xya_LUwRFlx,
+    double *xya_SfcHFlx_ns, double *xya_SfcHFlx_sr, double *xya_DSfcHFlxDTs,
+    const double *xy_WindU, const double *xy_WindV, const double *xy_SfcAirTemp, const double *xy_QVap1,
+    const double *xy_SDwRFlx, const double *xy_LDwRFlx,
+    const double *xya_ImplCplCoef1, const double *xya_ImplCplCoef2,
+    double *xya_SfcTemp, double *xya_SfcAlbedo, const double *xy_SIceCon,
+    const double *a_Sig1Info, const double *xy_SfcHeight, const double *xy_SfcPress);
+
+/* Device form.  Columns are addressed as col(i,j) = off + i + ld*j, i<nx, j<ny; the n-th
+ * slot of a 3-D array is at + n*slot_stride.  (IA,JA)-haloed arrays: nx=IA-2, ny=JA-2,
+ * ld=IA, off=IA+1, slot_stride=IA*JA.  Output pointers may be NULL (not stored). */
+typedef struct dccm_sfc_fields {
+    /* out (3 slots each; DelVarImplCPL 4) */
+    double *WindStressX, *WindStressY, *SenHFlx, *QVapMFlx, *LatHFlx;
+    double *SfcVelTransCoef, *SfcTempTransCoef, *SfcQVapTransCoef;
+    double *DelVarImplCPL;
+    double *SUwRFlx, *LUwRFlx;
+    double *SfcHFlx_ns, *SfcHFlx_sr, *DSfcHFlxDTs;
+    /* in */
+    const double *WindU, *WindV, *SfcAirTemp, *QVap1, *SDwRFlx, *LDwRFlx;
+    const double *ImplCplCoef1, *ImplCplCoef2;   /* 4 slots */
+    double *SfcTemp, *SfcAlbedo;                 /* inout: slots 1,2 in, slot 3 out */
+    const double *SIceCon;
+    const double *SfcHeight;                     /* NULL = 0 everywhere (sfc/dccm_sfc_mod.f90:885) */
+    const double *SfcPress;
+} dccm_sfc_fields;
+int dccm_bulkflux_device(int nx, int ny, int ld, int64_t off, int64_t slot_stride,
+                         const dccm_sfc_fields *f, double sig1, void *stream);
+
+/* ------------------------------------------------------------------ implicit coupling (K3/K4)
+ * Replaces dcpam_sfc_implicit_coupling_mod, ref atm/dcpam_sfc_implicit_coupling_mod.f90. */
+typedef struct dccm_vdiff dccm_vdiff;
+
+/* dcpam_sfc_implicit_coupling_Init (ref :420-426); sizes/constants come from DCPAM's
+ * gridset / composition / constants / timeset modules (ref :3-7, :85-108).
+ * index_h2ovap is 1-based.  The swept matrices live in the handle (ref :16-18 `save`). */
+int dccm_vdiff_create(int imax, int jmax, int kmax, int ncmax, int index_h2ovap,
+                      double Grav, double CpDry, double GasRDry, double DelTime, dccm_vdiff **out);
+void dccm_vdiff_destroy(dccm_vdiff *h);
+/* 0 = operation order of the reference (bit-exact vs the oracle), 1 = shared reciprocals */
+int dccm_vdiff_set_mode(dccm_vdiff *h, int fast);
+/* SfcImplicitCoupling_VDiffForward (ref :72-378), Fortran dummy order. */
+int dccm_vdiff_forward_host(dccm_vdiff *h,
+    const double *xyr_MomFluxX, const double *xyr_MomFluxY, const double *xyr_HeatFlux,
+    const double *xyrf_QMixFlux,
+    const double *xyr_Press, const double *xyz_Exner, const double *xyr_Exner,
+    const double *xyr_VirTemp, const double *xyz_Height,
+    const double *xyr_VelDiffCoef, const double *xyr_TempDiffCoef, const double *xyr_QMixDiffCoef,
+    double *xyz_DUDt, double *xyz_DVDt, double *xyz_DTempDt, double *xyzf_DQMixDt,
+    double *xya_ImplCplCoef1, double *xya_ImplCplCoef2);
+/* SfcImplicitCoupling_VDiffBackward (ref :25-70) */
+int dccm_vdiff_backward_host(dccm_vdiff *h,
+    double *xyz_DUDt, double *xyz_DVDt, double *xyz_DTempDt, double *xyzf_DQMixDt);
+int dccm_vdiff_forward_device(dccm_vdiff *h,
+    const double *xyr_MomFluxX, const double *xyr_MomFluxY, const double *xyr_HeatFlux,
+    const double *xyrf_QMixFlux,
+    const double *xyr_Press, const double *xyz_Exner, const double *xyr_Exner,
+    const double *xyr_VirTemp, const double *xyz_Height,
+    const double *xyr_VelDiffCoef, const double *xyr_TempDiffCoef, const double *xyr_QMixDiffCoef,
+    double *xyz_DUDt, double *xyz_DVDt, double *xyz_DTempDt, double *xyzf_DQMixDt,
+    double *xya_ImplCplCoef1, double *xya_ImplCplCoef2, void *stream);
+/* level1 (4 slots of imax*jmax: U,V,T,q_vap increments = DelVarImplCPL remapped to the ATM
+ * grid) replaces level 1 of the tendencies first, as atm/dccm_atm_mod.f90:832-835 does; NULL
+ * = the caller already wrote level 1. */
+int dccm_vdiff_backward_device(dccm_vdiff *h,
+    double *xyz_DUDt, double *xyz_DVDt, double *xyz_DTempDt, double *xyzf_DQMixDt,
+    const double *level1, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,110 @@
+/*
+ * dccm_oracle.h -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * Plain-C restatement of the Dennou-CCM surface-exchange hot path, following the
+ * reference Fortran loop nests line by line (citations are relative to
+ * /root/reference and given on every function in dccm_oracle.c).
+ *
+ * PARITY UNPINNED: the reference ships no tests, no golden vectors and no mapping
+ * tables, and it is Fortran-only (no Fortran compiler in this image; the hot-path
+ * modules also `use` the un-vendored gtool5 / Jcup / DCPAM modules), so neither
+ * golden fixtures nor an `oracle/_ref` build of the real reference exist.  The
+ * oracle is pinned instead by self-derived known-answer tests (tests/test_oracle_kat.py,
+ * SURVEY.md section 4 KAT-1..5).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library, and only as the checker / the timed CPU baseline.
+ */
+#ifndef DCCM_ORACLE_H
+#define DCCM_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- mapping-table container (one entry = one text line "iD jD iS jS coef") ---- */
+typedef struct orc_table {
+    int64_t n, cap;
+    int32_t *iD, *jD, *iS, *jS;   /* 1-based, as written to the table file */
+    double  *coef;
+} orc_table;
+
+orc_table *orc_table_new(void);
+void       orc_table_free(orc_table *t);
+int64_t    orc_table_n(const orc_table *t);
+void       orc_table_copy(const orc_table *t, int32_t *iD, int32_t *jD, int32_t *iS,
+                          int32_t *jS, double *coef);
+
+/* ---- grids (stand-in for SPML w_module) ---- */
+int orc_gauss_legendre(int n, double *mu, double *w);
+int orc_gauss_grid(int im, int jm, double *x_Lon, double *y_Lat, double *x_LonWt, double *y_LatWt);
+int orc_regular_grid(int im, int jm, double *x_Lon, double *y_Lat, double *x_LonWt, double *y_LatWt);
+
+/* ---- table generators ---- */
+/* lon_mode 0 = reference-faithful; 1 = generalised longitude overlap (extension, no parity claim) */
+int orc_gen_jones99(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                    int nxd, const double *x_LonD, int nyd, const double *y_LatD,
+                    const double *y_LatIntWtS, const double *y_LatIntWtD,
+                    int accuracy_order, int lon_mode, orc_table *out);
+int orc_gen_bilinear(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                     int nxr, const double *x_LonR, int nyr, const double *y_LatR,
+                     int lon_mode, orc_table *out);
+int orc_exchange_grid(int jma, const double *y_LatA, const double *y_IntWtLatA,
+                      int jmo, const double *y_IntWtLatO,
+                      int *jms, double *y_LatS, double *y_IntWtLatS);
+
+/* ---- table file I/O ---- */
+int orc_table_write_text(const orc_table *t, const char *filename);
+int orc_table_read_text(const char *filename, orc_table *out);
+void orc_table_to_index(const orc_table *t, int gnxs, int gnxr,
+                        int32_t *send_index, int32_t *recv_index, double *coef_s);
+
+/* ---- remap apply ---- */
+void orc_remap_apply(int64_t nops, const int32_t *send_index, const int32_t *recv_index,
+                     const double *coef, const double *send, int sn1, int sn2,
+                     double *recv, int rn1, int rn2, int num_of_data);
+
+/* ---- bulk flux ---- */
+void orc_bulkflux(int IA, int JA,
+    double *xya_WindStressX, double *xya_WindStressY,
+    double *xya_SenHFlx, double *xya_QVapMFlx, double *xya_LatHFlx,
+    double *xya_SfcVelTransCoef, double *xya_SfcTempTransCoef, double *xya_SfcQVapTransCoef,
+    double *xya_DelVarImplCPL,
+    double *xya_SUwRFlx, double *xya_LUwRFlx,
+    double *xya_SfcHFlx_ns, double *xya_SfcHFlx_sr, double *xya_DSfcHFlxDTs,
+    const double *xy_WindU, const double *xy_WindV, const double *xy_SfcAirTemp, const double *xy_QVap1,
+    const double *xy_SDwRFlx, const double *xy_LDwRFlx,
+    const double *xya_ImplCplCoef1, const double *xya_ImplCplCoef2,
+    double *xya_SfcTemp, double *xya_SfcAlbedo, const double *xy_SIceCon,
+    const double *a_Sig1Info, const double *xy_SfcHeight, const double *xy_SfcPress);
+
+/* ---- implicit coupling (column tridiagonal) ---- */
+typedef struct orc_vdiff {
+    int imax, jmax, kmax, ncmax, index_h2ovap; /* index_h2ovap 1-based */
+    double Grav, CpDry, GasRDry, DelTime;
+    double *UVMtx, *TempMtx, *QMixMtx;         /* (imax*jmax, kmax, 3) */
+} orc_vdiff;
+
+orc_vdiff *orc_vdiff_new(int imax, int jmax, int kmax, int ncmax, int index_h2ovap,
+                         double Grav, double CpDry, double GasRDry, double DelTime);
+void orc_vdiff_free(orc_vdiff *h);
+void orc_vdiff_forward(orc_vdiff *h,
+    const double *xyr_MomFluxX, const double *xyr_MomFluxY, const double *xyr_HeatFlux,
+    const double *xyrf_QMixFlux,
+    const double *xyr_Press, const double *xyz_Exner, const double *xyr_Exner,
+    const double *xyr_VirTemp, const double *xyz_Height,
+    const double *xyr_VelDiffCoef, const double *xyr_TempDiffCoef, const double *xyr_QMixDiffCoef,
+    double *xyz_DUDt, double *xyz_DVDt, double *xyz_DTempDt, double *xyzf_DQMixDt,
+    double *xya_ImplCplCoef1, double *xya_ImplCplCoef2);
+void orc_vdiff_backward(orc_vdiff *h,
+    double *xyz_DUDt, double *xyz_DVDt, double *xyz_DTempDt, double *xyzf_DQMixDt);
+/* copy of the swept diagonal b'(k) (k = 1..kmax; k=1 unspecified, see defect C-1) */
+void orc_vdiff_get_diag(const orc_vdiff *h, int which, double *out);
+
+int orc_num_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
