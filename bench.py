@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- coupling exchanges/s of the surface-exchange step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+One "step" = one full exchange (K3 forward -> remap A->S + O/I->S -> K2 bulk flux -> remap
+S->A + S->O/I -> K4 backward, 43 remapped layers) over one batch of synthetic input.
+Default workload: BASELINE config 5, T1279 atmosphere <-> 0.1 deg ocean -- the configuration the
+north_star's targets are quoted on; it fits one B200 (~45 GB).  For N > 1 the SAME grids are split
+into N latitude bands (strong scaling) with a halo exchange of source rows per remap.
+
+`--impl reference` times the CPU restatement of the reference loops (oracle/, the reference
+itself is Fortran and cannot be built here) on the host cores, on a bounded latitude-band sample.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (IMA, JMA, IMO, JMO, ocean regular?, K, ncmax, members)
+    "T1279_0p1deg": (3840, 1920, 3600, 1800, True, 26, 1, 1),      # BASELINE config 5
+    "T341_0p25deg": (1024, 512, 1440, 720, True, 26, 1, 1),        # config 4
+    "T106_1deg": (320, 160, 360, 180, True, 26, 1, 1),             # config 3
+    "T42x64": (128, 64, 128, 64, False, 26, 1, 64),                # config 2: 64-member ensemble
+    "T42": (128, 64, 128, 64, False, 26, 1, 1),                    # config 1 (b)
+}
+DESCR = {
+    "T1279_0p1deg": "T1279 (3840x1920, L26) atm <-> 0.1deg (3600x1800) ocean via 3840x3718 exchange grid",
+    "T341_0p25deg": "T341 (1024x512, L26) atm <-> 0.25deg (1440x720) ocean",
+    "T106_1deg": "T106 (320x160, L26) atm <-> 1deg (360x180) ocean",
+    "T42x64": "64 batched T42L26 members (APESpinUpSolarDepExp ensemble), shared tables",
+    "T42": "APEI07Couple T42L26 atm <-> T42 ocean",
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 8 for k in range(4) if r[4 + k] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_grids(dccm, wl):
+    T = dccm.tables
+    ima, jma, imo, jmo, reg, K, nc, M = WORKLOADS[wl]
+    A = T.get_LonLatGrid(ima, jma)
+    O = T.regular_LonLatGrid(imo, jmo) if reg else T.get_LonLatGrid(imo, jmo)
+    S = T.generate_surface_exchange_grid(A, O)
+    return A, O, S, K, nc, M
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle on the host cores, bounded latitude-band sample
+# ------------------------------------------------------------------------------------------
+
+class CpuSample:
+    """A latitude band holding ~1/frac_inv of every grid; one call = the whole exchange on it."""
+
+    def __init__(self, dccm, wl, target_cols=150_000):
+        import oracle
+        oracle.build()
+        self.orc = oracle
+        syn = importlib.import_module("dennou-ccm_b200.synthetic")
+        self.syn = syn
+        A, O, S, K, nc, M = make_grids(dccm, wl)
+        self.K, self.nc, self.M = K, nc, M
+        rows = max(2, min(A.jm, int(round(target_cols / (A.im * M)))))
+        self.frac = rows / A.jm
+        ja0 = (A.jm - rows) // 2
+        lat0, lat1 = (A.y_Lat[ja0] + (A.y_Lat[ja0 - 1] if ja0 else -np.pi / 2)) / 2, \
+                     (A.y_Lat[ja0 + rows - 1] + (A.y_Lat[ja0 + rows] if ja0 + rows < A.jm else np.pi / 2)) / 2
+        band = lambda g: (int(np.searchsorted(g.y_Lat, lat0)), int(np.searchsorted(g.y_Lat, lat1)))
+        self.bA, self.bS, self.bO = (ja0, ja0 + rows), band(S), band(O)
+        self.grids = (A, O, S)
+        # column-solve inputs of the band (members = extra columns)
+        self.vin = syn.column_inputs(np, A, K, nc, *self.bA)
+        if M > 1:
+            self.vin = {k: np.concatenate([v] * M, axis=-1) for k, v in self.vin.items()}
+        ncolA = (self.bA[1] - self.bA[0]) * A.im * M
+        self.vd = oracle.VDiff(ncolA, 1, K, nc, 1, syn.GRAV, syn.CPDRY, syn.GASRDRY, syn.DELTIME)
+        # remap: tables restricted to the destination rows of the band; sources full size
+        T = dccm.tables
+        self.remaps = []
+        spec = [("as", A, S, self.bS, 13, 4), ("os", O, S, self.bS, 2, 3), ("sa", S, A, self.bA, 5, 4), ("so", S, O, self.bO, 2, 10)]
+        rng = np.random.default_rng(1)
+        for key, s, d, (j0, j1), dbil, dcons in spec:
+            for kind, D in (("bil", dbil), ("cons", dcons)):
+                tab = T.gen_table_bilinear(s, d, 1) if kind == "bil" else T.gen_table_jones99(s, d, 1, 1)
+                send_i, recv_i, coef = tab.index(s.im, d.im)
+                del tab
+                lo, hi = j0 * d.im, j1 * d.im
+                m = (recv_i > lo) & (recv_i <= hi)
+                send_i, recv_i, coef = send_i[m], (recv_i[m] - lo).astype(np.int32), coef[m]
+                smin = int(send_i.min()) - 1
+                send_i = (send_i - smin).astype(np.int32)
+                nsrc = int(send_i.max())
+                x = rng.standard_normal((D * M, nsrc))
+                self.remaps.append((send_i, recv_i, coef, x, hi - lo))
+        # bulk flux on the S band (halo'd arrays as the reference passes them)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from test_oracle_kat import _bulk_inputs
+
+        class G:
+            pass
+        g = G()
+        g.im, g.jm = S.im * M, self.bS[1] - self.bS[0]
+        g.x_Lon = np.tile(S.x_Lon, M); g.y_Lat = S.y_Lat[self.bS[0]:self.bS[1]]
+        g.n = g.im * g.jm
+        self.bulk = _bulk_inputs(syn, g)
+
+    def run_once(self):
+        o = self.orc
+        t0 = time.perf_counter()
+        f = o.VDiff.forward(self.vd, self.vin)
+        t1 = time.perf_counter()
+        for send_i, recv_i, coef, x, nd in self.remaps[:4]:
+            o.remap_apply(send_i, recv_i, coef, x, nd)
+        t2 = time.perf_counter()
+        IA, JA, inp = self.bulk
+        o.bulkflux(IA, JA, inp)
+        t3 = time.perf_counter()
+        for send_i, recv_i, coef, x, nd in self.remaps[4:]:
+            o.remap_apply(send_i, recv_i, coef, x, nd)
+        t4 = time.perf_counter()
+        self.vd.backward(f["DUDt"], f["DVDt"], f["DTempDt"], f["DQMixDt"])
+        t5 = time.perf_counter()
+        return t5 - t0, {"fwd": t1 - t0, "remap_to_sfc": t2 - t1, "bulk": t3 - t2, "remap_from_sfc": t4 - t3, "bwd": t5 - t4}
+
+    def describe(self):
+        A, O, S = self.grids
+        return (f"latitude band = {self.frac:.4f} of every grid (ATM rows {self.bA[0]}:{self.bA[1]} of {A.jm}, "
+                f"SFC rows {self.bS[0]}:{self.bS[1]} of {S.jm}); time scaled by 1/{self.frac:.4f}")
+
+
+def cpu_baseline(dccm, wl, reps=3):
+    cs = CpuSample(dccm, wl)
+    cs.run_once()
+    ts = [cs.run_once() for _ in range(reps)]
+    t = float(np.median([x[0] for x in ts]))
+    parts = {k: float(np.median([x[1][k] for x in ts])) for k in ts[0][1]}
+    return {"value": cs.frac / t, "unit": "exchanges/s", "cores": cs.orc.num_threads(), "kind": "port",
+            "sample": cs.describe(), "sample_seconds": t, "parts_s": parts,
+            "note": "C restatement of the reference loops (oracle/); remap and the tridiagonal sweeps are "
+                    "serial as in the reference, OpenMP only where the reference has !$omp"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    dccm = importlib.import_module("dennou-ccm_b200")
+    cs = CpuSample(dccm, args.workload)
+    for _ in range(args.warmup):
+        cs.run_once()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cs.run_once()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = cs.frac / dt
+    line = {"impl": "reference", "metric": "coupling exchanges/sec", "value": v, "unit": "exchanges/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / cs.frac,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "description": DESCR[args.workload]},
+            "cpu_baseline": {"value": v, "unit": "exchanges/s", "cores": cs.orc.num_threads(), "kind": "port",
+                             "sample": cs.describe()},
+            "e2e": {"value": v, "unit": "exchanges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+
+def run_ours(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dccm = importlib.import_module("dennou-ccm_b200")
+    dccm._lib.check(dccm.lib().dccm_init(local))
+    syn = importlib.import_module("dennou-ccm_b200.synthetic")
+    exch_mod = importlib.import_module("dennou-ccm_b200.exchange")
+    wl = args.workload
+    A, O, S, K, nc, M = make_grids(dccm, wl)
+    if world > 1:
+        raise SystemExit("multi-GPU sharding is wired in dennou-ccm_b200/sharding.py (see bench --gpus)")
+
+    t_setup = time.time()
+    ex = exch_mod.SurfaceExchange(A, O, S, K, nc, 1, members=M, fast=not args.reference_order, device=dev)
+    # synthetic inputs, generated on the device
+    col = [syn.column_inputs(torch, A, K, nc, dev=dev, member=m) for m in range(M)]
+    col_in = {k: torch.cat([c[k] for c in col], dim=-1).contiguous() for k in col[0]}
+    del col
+    atm = [syn.atm_surface_fields(torch, A, dev=dev, member=m) for m in range(M)]
+    ocn = [syn.ocn_surface_fields(torch, O, dev=dev, member=m) for m in range(M)]
+    atm_sfc = {k: torch.stack([a[k] for a in atm]) for k in atm[0]}
+    ocn_sfc = {k: torch.stack([o[k] for o in ocn]) for k in ocn[0]}
+    ex.set_inputs(col_in, atm_sfc, ocn_sfc)
+    torch.cuda.synchronize()
+    t_setup = time.time() - t_setup
+
+    bytes_alg = ex.algorithmic_bytes()
+    peak, peak_src = load_peaks()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for _ in range(max(3, args.warmup)):
+        ex.step()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ex.launches = 0
+    marks = []
+    torch.cuda.synchronize()
+    e0 = ev(); e0.record()
+    for _ in range(args.steps):
+        m = [ev() for _ in range(7)]
+        m[0].record(); ex.forward()
+        m[1].record(); ex.remap_to_sfc()
+        m[2].record(); ex.bulk()
+        m[3].record(); ex.pack_sfc()
+        m[4].record(); ex.remap_from_sfc()
+        m[5].record(); ex.backward()
+        m[6].record()
+        marks.append(m)
+    e1 = ev(); e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = ex.launches
+    names = ["fwd", "remap_to_sfc", "bulk", "pack", "remap_from_sfc", "bwd"]
+    part_ms = {n: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in marks])) for i, n in enumerate(names)}
+
+    value = 1e3 / ms
+    fwd_gbs = bytes_alg["fwd"] / (part_ms["fwd"] * 1e-3) / 1e9
+    line = {
+        "metric": "coupling exchanges/sec", "value": value, "unit": "exchanges/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl, "description": DESCR[wl], "columns_atm": A.n * M, "cells_sfc": S.n * M,
+                   "cells_ocn": O.n * M, "kmax": K, "ncmax": nc, "remapped_layers": 43,
+                   "l2": "inputs larger than L2 (working set %.1f GB)" % (bytes_alg["total"] / 1e9),
+                   "mode": "reference-order" if args.reference_order else "fast (shared reciprocals)",
+                   "setup_s": round(t_setup, 1)},
+        "remapped_cell_fields_per_s": ex.remapped_cell_fields() * value,
+        "exchange_algorithmic_gbytes": bytes_alg["total"] / 1e9,
+        "exchange_hbm_gbs": bytes_alg["total"] / (ms * 1e-3) / 1e9,
+        "exchange_frac_of_peak": bytes_alg["total"] / (ms * 1e-3) / 1e9 / peak,
+        "part_ms": part_ms,
+        "part_gbs": {n: bytes_alg[n] / (part_ms[n] * 1e-3) / 1e9 for n in bytes_alg if n in part_ms},
+        "roofline": {"bound": "hbm", "kernel": "vdiff_forward_kernel", "achieved": fwd_gbs, "peak": peak,
+                     "unit": "GB/s", "frac": fwd_gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": bytes_alg["fwd"]},
+        "clocks": clocks, "gpu_launches": launches,
+    }
+
+    if not args.no_e2e:
+        line["e2e"] = run_e2e(torch, ex, col_in, atm_sfc, ocn_sfc, args)
+    if not args.no_cpu and rank == 0:
+        try:
+            line["cpu_baseline"] = cpu_baseline(dccm, wl)
+        except Exception as e:           # the baseline must never take the GPU number down
+            line["cpu_baseline"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def run_e2e(torch, ex, col_in, atm_sfc, ocn_sfc, args):
+    """Same exchange, HOST buffers: every step copies the step's inputs from pinned host memory,
+    runs the exchange and reads the results (tendencies + fields for ATM and OCN) back."""
+    steps = max(1, min(args.steps, 3))
+    host_in = {}
+    pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
+    for k, t in list(col_in.items()) + [("a:" + k, v) for k, v in atm_sfc.items()] + [("o:" + k, v) for k, v in ocn_sfc.items()]:
+        host_in[k] = pin(t)
+    outs = [ex.tend["DUDt"], ex.tend["DVDt"], ex.tend["DTempDt"], ex.tend["DQMixDt"], ex.a_recv, ex.o_recv]
+    host_out = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs]
+    h2d = sum(t.numel() * 8 for t in host_in.values())
+    d2h = sum(t.numel() * 8 for t in host_out)
+
+    def one():
+        for k, t in host_in.items():
+            if k.startswith("a:"):
+                atm_sfc[k[2:]].copy_(t, non_blocking=True)
+            elif k.startswith("o:"):
+                ocn_sfc[k[2:]].copy_(t, non_blocking=True)
+            else:
+                col_in[k].copy_(t, non_blocking=True)
+        ex.set_inputs(col_in, atm_sfc, ocn_sfc)
+        ex.step()
+        for h, d in zip(host_out, outs):
+            h.copy_(d, non_blocking=True)
+
+    one()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": 1.0 / dt, "unit": "exchanges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": 1e3 * dt, "steps": steps,
+            "note": "pinned host buffers, H2D of all column/surface inputs and D2H of tendencies + remapped fields inside the timed region"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="T1279_0p1deg", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--reference-order", action="store_true", help="bit-exact column solves (IEEE divisions)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,205 @@
+"""One atmosphere <-> surface <-> ocean coupling exchange, device resident (SURVEY.md 8d metric 1):
+
+    K3 forward (ATM)  ->  remap A->S (17 layers) + O/I->S (5)  ->  K2 bulk flux (SFC)
+                      ->  remap S->A (9) + S->O/S->I (12)       ->  K4 backward (ATM)
+
+The field lists, their grouping by mapping table and their order follow the reference glue
+(ref sfc/dccm_sfc_mod.f90:449-466 get-vars, :764-784 put-vars; atm/dccm_atm_mod.f90:697-712,
+:817-835; ocn/dccm_ocn_mod.f90:625-645; Appendix A of SURVEY.md): 43 remapped layers per exchange.
+Everything between the forward inputs and the backward outputs stays in HBM; the host-side
+pack/unpack/put/get staging of the reference glue disappears.
+
+torch owns the device buffers and the stream; every kernel is the library's own
+(libdccm_b200.so) launched through the C ABI on torch's current stream.
+"""
+import numpy as np
+
+from . import _lib as L
+from . import dsfcm, tables
+from .dcpam_sfc_implicit_coupling_mod import SfcImplicitCoupling, IN_ORDER
+from .interpolation_data_latlon_mod import RemapOperator
+
+# layer lists; mapping tag 1 = bilinear, 2 = conservative
+A2S_BIL = ["WindU", "WindV", "SfcAirTemp", "QVap1", "SfcPress"] + ["ImplCplCoef1"] * 4 + ["ImplCplCoef2"] * 4   # 13
+A2S_CONS = ["LDwRFlx", "SDwRFlx", "RainFall", "SnowFall"]                                                      # 4
+O2S_BIL = ["SfcTempO", "SfcTempI"]                                                                             # 2
+O2S_CONS = ["SIceCon", "SfcAlbedoO", "SfcAlbedoI"]                                                             # 3
+S2A_CONS = ["LUwRFlx3", "SUwRFlx3", "SenHFlx3", "QVapMFlx3"]                                                   # 4
+S2A_BIL = ["SfcAlbedo3"] + ["DelVarImplCPL"] * 4                                                               # 5
+S2O_CONS = ["SfcHFlx_ns1", "SfcHFlx_sr1", "SnowFall", "RainFall", "Evap1", "-WindStressX3", "-WindStressY3",
+            "SfcHFlx_ns2", "SfcHFlx_sr2", "Evap2"]                                                             # 10
+S2O_BIL = ["DSfcHFlxDTs1", "DSfcHFlxDTs2"]                                                                     # 2
+N_LAYERS = len(A2S_BIL) + len(A2S_CONS) + len(O2S_BIL) + len(O2S_CONS) + len(S2A_CONS) + len(S2A_BIL) \
+    + len(S2O_CONS) + len(S2O_BIL)
+assert N_LAYERS == 43
+
+
+def build_tables(A, O, S, order_as=1, lon_mode=1):
+    """The 8 tables gmapgen writes for the 3-component mode (ref tool/gmapgen/gmapgen_main.f90:100-149),
+    as (send_index, recv_index, coef) triples keyed by direction and kind."""
+    t = {}
+    for key, s, d in (("as", A, S), ("sa", S, A), ("os", O, S), ("so", S, O)):
+        order = order_as if key == "as" else 1
+        t[key + "_cons"] = tables.gen_table_jones99(s, d, order, lon_mode).index(s.im, d.im)
+        t[key + "_bil"] = tables.gen_table_bilinear(s, d, lon_mode).index(s.im, d.im)
+    return t
+
+
+class SurfaceExchange:
+    """Device-resident exchange step for one rank's share of the grids (whole grids on 1 GPU).
+
+    members > 1 batches an ensemble that shares the tables (BASELINE config 2): every 2-D field
+    gets `members` copies stacked along the layer axis; columns are members*n.
+    """
+
+    def __init__(self, A, O, S, kmax, ncmax=1, index_h2ovap=1, tabs=None, consts=None, members=1,
+                 fast=True, device=None, api_complete=True):
+        import torch
+        self.torch = torch
+        self.dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.A, self.O, self.S = A, O, S
+        self.K, self.nc, self.iq, self.M = kmax, ncmax, index_h2ovap, members
+        from . import synthetic as syn
+        c = consts or {}
+        self.Grav = c.get("Grav", syn.GRAV); self.CpDry = c.get("CpDry", syn.CPDRY)
+        self.GasRDry = c.get("GasRDry", syn.GASRDRY); self.DelTime = c.get("DelTime", syn.DELTIME)
+        self.sig1 = c.get("Sig1", syn.SIG1)
+        tabs = tabs or build_tables(A, O, S)
+        self.ops = {}
+        self.nnz = {}
+        for key, (send_i, recv_i, coef) in tabs.items():
+            s, d = {"a": A, "s": S, "o": O}[key[0]], {"a": A, "s": S, "o": O}[key[1]]
+            self.ops[key] = RemapOperator(send_i, recv_i, coef, s.n, d.n)
+            self.nnz[key] = len(coef)
+        nA, nS, nO, M = A.n, S.n, O.n, members
+        # ensemble members are extra columns for the column solve: imax*jmax = M*nA
+        self.vdiff = SfcImplicitCoupling(M * A.im, A.jm, kmax, ncmax, index_h2ovap,
+                                         self.Grav, self.CpDry, self.GasRDry, self.DelTime, fast=fast)
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=self.dev)
+        # ATM side
+        self.col_in = {k: None for k in IN_ORDER}
+        self.tend = {"DUDt": z(kmax, M * nA), "DVDt": z(kmax, M * nA), "DTempDt": z(kmax, M * nA),
+                     "DQMixDt": z(ncmax, kmax, M * nA)}
+        # layer-major send/recv buffers; member m of layer l is row l*M + m
+        self.a2s_bil = z(13 * M, nA); self.a2s_cons = z(4 * M, nA)
+        self.o2s_bil = z(2 * M, nO); self.o2s_cons = z(3 * M, nO)
+        self.s_bil = z(13 * M, nS); self.s_cons = z(4 * M, nS)
+        self.s_obil = z(3 * M, nS)        # SfcTemp slots 1,2 (in) + slot 3 (out)
+        self.s_ocons = z(4 * M, nS)       # SIceCon, SfcAlbedo slots 1,2 (in) + slot 3 (out)
+        self.sfc_out = {k: z(3 * M, nS) for k in dsfcm.OUT3}
+        self.sfc_out["DelVarImplCPL"] = z(4 * M, nS)
+        self.s2a = z(9 * M, nS); self.s2o = z(12 * M, nS)
+        self.a_recv = z(9 * M, nA); self.o_recv = z(12 * M, nO)
+        self.launches = 0
+
+    # -- inputs -----------------------------------------------------------------------------
+    def set_inputs(self, col_in, atm_sfc, ocn_sfc):
+        """col_in: dict IN_ORDER -> tensors with M*nA columns; atm_sfc/ocn_sfc: dicts of (M, n) tensors."""
+        M = self.M
+        self.col_in = col_in
+        for l, name in enumerate(("WindU", "WindV", "SfcAirTemp", "QVap1", "SfcPress")):
+            self.a2s_bil[l * M:(l + 1) * M] = atm_sfc[name]
+        for l, name in enumerate(A2S_CONS):
+            self.a2s_cons[l * M:(l + 1) * M] = atm_sfc[name]
+        for l, name in enumerate(O2S_BIL):
+            self.o2s_bil[l * M:(l + 1) * M] = ocn_sfc[name]
+        for l, name in enumerate(O2S_CONS):
+            self.o2s_cons[l * M:(l + 1) * M] = ocn_sfc[name]
+
+    # -- the step ---------------------------------------------------------------------------
+    def forward(self):
+        M, nA = self.M, self.A.n
+        out = dict(self.tend)
+        # Coef1/Coef2 go straight into the A->S send buffer (layers 5..8 and 9..12); for M > 1 the
+        # solver's (4, M*nA) slot-major layout is exactly rows [5M, 9M) of the (13M, nA) buffer.
+        out["ImplCplCoef1"] = self.a2s_bil[5 * M:9 * M].view(4, M * nA)
+        out["ImplCplCoef2"] = self.a2s_bil[9 * M:13 * M].view(4, M * nA)
+        self.vdiff.forward_device(self.col_in, out)
+        self.launches += 1
+
+    def remap_to_sfc(self):
+        M = self.M
+        self.ops["as_bil"].apply(self.a2s_bil, self.s_bil)
+        self.ops["as_cons"].apply(self.a2s_cons, self.s_cons)
+        self.ops["os_bil"].apply(self.o2s_bil, self.s_obil[:2 * M])
+        self.ops["os_cons"].apply(self.o2s_cons, self.s_ocons[:3 * M])
+        self.launches += 4
+
+    def bulk(self):
+        M, nS = self.M, self.S.n
+        # with M members the 3-slot arrays are (3M, nS): slot stride = M*nS, columns = M*nS
+        v = lambda t, lo, hi: t[lo * M:hi * M].view(-1)
+        f = dict(self.sfc_out)
+        f = {k: t.view(-1) for k, t in f.items()}
+        f.update(WindU=v(self.s_bil, 0, 1), WindV=v(self.s_bil, 1, 2), SfcAirTemp=v(self.s_bil, 2, 3),
+                 QVap1=v(self.s_bil, 3, 4), SfcPress=v(self.s_bil, 4, 5),
+                 ImplCplCoef1=v(self.s_bil, 5, 9), ImplCplCoef2=v(self.s_bil, 9, 13),
+                 LDwRFlx=v(self.s_cons, 0, 1), SDwRFlx=v(self.s_cons, 1, 2),
+                 SfcTemp=v(self.s_obil, 0, 3), SIceCon=v(self.s_ocons, 0, 1), SfcAlbedo=v(self.s_ocons, 1, 4),
+                 SfcHeight=None)
+        dsfcm.bulkflux_device(M * nS, 1, f, self.sig1, slot_stride=M * nS)
+        self.launches += 1
+
+    def pack_sfc(self):
+        """put-side selection of the reference glue (ref sfc/dccm_sfc_mod.f90:764-784)."""
+        M = self.M
+        o = self.sfc_out
+        sl = lambda t, n: t[(n - 1) * M:n * M]
+        a = self.s2a
+        a[0 * M:1 * M] = sl(o["LUwRFlx"], 3); a[1 * M:2 * M] = sl(o["SUwRFlx"], 3)
+        a[2 * M:3 * M] = sl(o["SenHFlx"], 3); a[3 * M:4 * M] = sl(o["QVapMFlx"], 3)
+        a[4 * M:5 * M] = self.s_ocons[3 * M:4 * M]
+        a[5 * M:9 * M] = o["DelVarImplCPL"]
+        b = self.s2o
+        b[0 * M:1 * M] = sl(o["SfcHFlx_ns"], 1); b[1 * M:2 * M] = sl(o["SfcHFlx_sr"], 1)
+        b[2 * M:3 * M] = self.s_cons[3 * M:4 * M]; b[3 * M:4 * M] = self.s_cons[2 * M:3 * M]
+        b[4 * M:5 * M] = sl(o["QVapMFlx"], 1)
+        self.torch.neg(sl(o["WindStressX"], 3), out=b[5 * M:6 * M])
+        self.torch.neg(sl(o["WindStressY"], 3), out=b[6 * M:7 * M])
+        b[7 * M:8 * M] = sl(o["SfcHFlx_ns"], 2); b[8 * M:9 * M] = sl(o["SfcHFlx_sr"], 2)
+        b[9 * M:10 * M] = sl(o["QVapMFlx"], 2)
+        b[10 * M:11 * M] = sl(o["DSfcHFlxDTs"], 1); b[11 * M:12 * M] = sl(o["DSfcHFlxDTs"], 2)
+
+    def remap_from_sfc(self):
+        M = self.M
+        self.ops["sa_cons"].apply(self.s2a[:4 * M], self.a_recv[:4 * M])
+        self.ops["sa_bil"].apply(self.s2a[4 * M:], self.a_recv[4 * M:])
+        self.ops["so_cons"].apply(self.s2o[:10 * M], self.o_recv[:10 * M])
+        self.ops["so_bil"].apply(self.s2o[10 * M:], self.o_recv[10 * M:])
+        self.launches += 4
+
+    def backward(self):
+        M, nA = self.M, self.A.n
+        lvl1 = self.a_recv[5 * M:9 * M].view(4, M * nA)
+        self.vdiff.backward_device(self.tend, lvl1)
+        self.launches += 1
+
+    def step(self):
+        self.forward()
+        self.remap_to_sfc()
+        self.bulk()
+        self.pack_sfc()
+        self.remap_from_sfc()
+        self.backward()
+
+    # -- accounting (SURVEY.md 8d / BASELINE.md section 4) --------------------------------------
+    def algorithmic_bytes(self, n_out=42):
+        nA, nS, nO, K, nc, M = self.A.n, self.S.n, self.O.n, self.K, self.nc, self.M
+
+        def remap(key, D, nsrc, ndst):
+            return 12 * self.nnz[key] + 4 * (ndst + 1) + 8 * D * M * (nsrc + ndst)
+
+        b = {}
+        b["fwd"] = 8 * M * nA * ((9 + nc) * (K + 1) + 2 * K + 3 * K + (3 + nc) * K + 8)
+        b["bwd"] = 8 * M * nA * (3 * K + (3 + nc) * K + 4 + (3 + nc) * K)
+        b["remap_to_sfc"] = (remap("as_bil", 13, nA, nS) + remap("as_cons", 4, nA, nS)
+                             + remap("os_bil", 2, nO, nS) + remap("os_cons", 3, nO, nS))
+        b["bulk"] = 8 * (20 + n_out) * M * nS
+        b["remap_from_sfc"] = (remap("sa_cons", 4, nS, nA) + remap("sa_bil", 5, nS, nA)
+                               + remap("so_cons", 10, nS, nO) + remap("so_bil", 2, nS, nO))
+        b["total"] = sum(b.values())
+        return b
+
+    def remapped_cell_fields(self):
+        nA, nS, nO, M = self.A.n, self.S.n, self.O.n, self.M
+        return M * (22 * nS + 9 * nA + 12 * nO)

@@ -1,0 +1,133 @@
+"""CPU-side tests of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/dccm_b200.h declares, the host-side table code agrees index-for-index with the oracle,
+and the product never routes through the oracle or a CPU fallback.  No compute calls here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from util import as_orc_grid, pair
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "dennou-ccm_b200")
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "dccm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dccm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(dccm):
+    lib = ctypes.CDLL(dccm._lib.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 35
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/dccm_b200.h but not exported"
+    assert sorted(dccm._lib.declared_symbols()) == syms, "ctypes binding and header disagree"
+    assert b"sm_100a" in dccm.lib().dccm_build_info()
+
+
+def test_library_is_sm100a_only(dccm):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", dccm._lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_product_does_not_touch_the_oracle():
+    for dp, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
+                text = open(os.path.join(dp, f)).read()
+                assert "oracle" not in text.lower().replace("bit-exact vs the oracle", "").replace(
+                    "bit-identical to the reference", ""), f"{f} mentions the oracle"
+
+
+@pytest.mark.parametrize("name", ["T21_Pl42", "T42_T42", "T21_1deg", "T106_1deg"])
+def test_generators_match_oracle_index_for_index(orc, dccm, name):
+    """'identical remap indices': same entries, same order, bit-identical weights."""
+    T = dccm.tables
+    A, O, S = pair(orc, dccm, name)
+    oA, oO, oS = [as_orc_grid(orc, g) for g in (A, O, S)]
+    for (s, d, os_, od) in [(A, S, oA, oS), (S, A, oS, oA), (S, O, oS, oO), (O, S, oO, oS)]:
+        for order in (1, 2):
+            try:
+                t = T.gen_table_jones99(s, d, order, 1).entries()
+            except dccm.DccmError:
+                with pytest.raises(RuntimeError):
+                    orc.gen_jones99(os_, od, order, 1)
+                continue
+            o = orc.gen_jones99(os_, od, order, 1)
+            for x, y in zip(t, (o.iD, o.jD, o.iS, o.jS, o.coef)):
+                assert np.array_equal(x, y)
+        for lm in (0, 1):
+            t = T.gen_table_bilinear(s, d, lm).entries()
+            o = orc.gen_bilinear(os_, od, lm)
+            for x, y in zip(t, (o.iD, o.jD, o.iS, o.jS, o.coef)):
+                assert np.array_equal(x, y)
+
+
+def test_unsupported_grid_pair_fails_like_the_reference(dccm, orc):
+    A, O, S = pair(orc, dccm, "T21_1deg")
+    with pytest.raises(dccm.DccmError, match="lon_mode=1"):
+        dccm.tables.gen_table_jones99(O, S, 1, 0)
+    with pytest.raises(dccm.DccmError, match="2nd order"):
+        dccm.tables.gen_table_jones99(O, S, 2, 1)
+
+
+def test_reference_named_table_interfaces(dccm, orc, tmp_path):
+    """gen_gridmapfile_lonlat2lonlat + set_mappingTable_interpCoef with the reference's argument
+    lists (ref common/grid_mapping_util_jones99.f90:35-54,446-462; common/grid_mapping_util.f90:32-48)."""
+    A, O, S = pair(orc, dccm, "T21_Pl42")
+    fn = str(tmp_path / "gmap-ATM_T21-SFC_conserve.dat")
+    dccm.grid_mapping_util_jones99.gen_gridmapfile_lonlat2lonlat(
+        fn, A.x_Lon, A.y_Lat, S.x_Lon, S.y_Lat, A.x_LonWt, A.y_LatWt, S.x_LonWt, S.y_LatWt, 2)
+    send, recv, coef = dccm.grid_mapping_util_jones99.set_mappingTable_interpCoef(fn, A.im, S.im)
+    o = orc.gen_jones99(as_orc_grid(orc, A), as_orc_grid(orc, S), 2)
+    os_, or_, oc = o.to_index(A.im, S.im)
+    assert np.array_equal(send, os_) and np.array_equal(recv, or_) and np.array_equal(coef, oc)
+    # the oracle reads the product's file and vice versa (same on-disk format)
+    r = orc.read_table(fn)
+    assert np.array_equal(r.coef, o.coef) and np.array_equal(r.jS, o.jS)
+    fn2 = str(tmp_path / "gmap-bilinear.dat")
+    dccm.grid_mapping_util.gen_gridmapfile_lonlat2lonlat(fn2, S.x_Lon, S.y_Lat, O.x_Lon, O.y_Lat)
+    send, recv, coef = dccm.grid_mapping_util.set_mappingTable_interpCoef(fn2, S.im, O.im)
+    ob = orc.gen_bilinear(as_orc_grid(orc, S), as_orc_grid(orc, O))
+    os_, or_, oc = ob.to_index(S.im, O.im)
+    assert np.array_equal(send, os_) and np.array_equal(recv, or_) and np.array_equal(coef, oc)
+    # binary table form round-trips exactly
+    t = dccm.tables.gen_table_jones99(A, S, 2)
+    t.write(str(tmp_path / "t.bin"), binary=True)
+    u = dccm.tables.MappingTable.read(str(tmp_path / "t.bin"), binary=True)
+    for x, y in zip(t.entries(), u.entries()):
+        assert np.array_equal(x, y)
+    with pytest.raises(dccm.DccmError):
+        dccm.tables.MappingTable.read(str(tmp_path / "missing.dat"))
+
+
+def test_dsfcm_admin_grid_layout(dccm):
+    """ref sfc/DSFCM_Admin_Grid_mod.f90:35-52 and sfc/DSFCM_Admin_Variable_mod.f90:57-80"""
+    g = dccm.dsfcm.DSFCM_Admin_Grid(128, 64)
+    assert (g.IS, g.IE, g.IA, g.JS, g.JE, g.JA) == (2, 129, 130, 2, 65, 66)
+    v = dccm.dsfcm.DSFCM_Admin_Variable(g)
+    assert v.xya_SenHFlx.shape == (3, 66, 130) and v.xya_DelVarImplCPL.shape == (4, 66, 130)
+    assert v.xy_SIceCon.shape == (66, 130)
+
+
+def test_no_cpu_fallback_without_gpu(dccm):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(dccm.DccmError, match="no CPU fallback"):
+        dccm.RemapOperator([1], [1], [1.0], 1, 1)
+    with pytest.raises(dccm.DccmError, match="no CPU fallback"):
+        dccm.SfcImplicitCoupling(4, 2, 5, 1, 1, 9.8, 1004.6, 287.04, 1200.0)
+    z = np.zeros((3, 5, 6))
+    with pytest.raises(dccm.DccmError, match="no CPU fallback"):
+        dccm.DSFCM_Util_SfcBulkFlux_Get(6, 5, *[z.copy() for _ in range(8)], np.zeros((4, 5, 6)),
+                                        *[z.copy() for _ in range(5)], *[np.zeros((5, 6)) for _ in range(6)],
+                                        np.zeros((4, 5, 6)), np.zeros((4, 5, 6)), z.copy(), z.copy(),
+                                        np.zeros((5, 6)), np.array([0.995, 0.01]), np.zeros((5, 6)), np.zeros((5, 6)))
