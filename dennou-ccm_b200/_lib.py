@@ -81,6 +81,8 @@ _SIGS = {
     "dccm_bulkflux_get_host": (C.c_int, [C.c_int, C.c_int] + [f64p] * 28),
     "dccm_bulkflux_device": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
                                        C.POINTER(SfcFields), C.c_double, vp]),
+    "dccm_sfc_exchange_device": (C.c_int, [vp] * 4 + [vp] * 4 + [C.c_int, C.c_double, vp, vp,
+                                           C.POINTER(SfcFields), vp]),
     "dccm_vdiff_create": (C.c_int, [C.c_int] * 5 + [C.c_double] * 4 + [C.POINTER(vp)]),
     "dccm_vdiff_destroy": (None, [vp]),
     "dccm_vdiff_set_mode": (C.c_int, [vp, C.c_int]),

@@ -22,16 +22,7 @@
 
 using namespace dccm;
 
-struct dccm_remap {
-    int n_send = 0, n_recv = 0;
-    int64_t nnz = 0;
-    int max_row_nnz = 0;
-    int kind = 0;
-    int32_t *d_rowptr = nullptr;
-    int32_t *d_col = nullptr;
-    double *d_w = nullptr;
-    DevBuf send_buf, recv_buf;
-};
+#include "dccm_remap_internal.h"
 
 namespace {
 

@@ -373,8 +373,8 @@ extern "C" int dccm_vdiff_forward_host(dccm_vdiff *h,
     if (!h) return fail(DCCM_ERR_ARG, "dccm_vdiff_forward: null handle");
     const size_t NC = (size_t)h->NC, K = h->kmax, nc = h->ncmax;
     const size_t half = NC * (K + 1), full = NC * K;
-    // inputs: 8 half-level + 2 full-level + nc half-level tracer fluxes
-    int rc = h->in_buf.reserve(sizeof(double) * (half * (8 + nc) + full * 2));
+    // inputs: 9 half-level + 2 full-level + nc half-level tracer fluxes
+    int rc = h->in_buf.reserve(sizeof(double) * (half * (9 + nc) + full * 2));
     if (rc) return rc;
     rc = h->out_buf.reserve(sizeof(double) * (full * (3 + nc) + NC * 8));
     if (rc) return rc;

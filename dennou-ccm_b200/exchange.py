@@ -160,6 +160,27 @@ class SurfaceExchange:
         b[9 * M:10 * M] = sl(o["QVapMFlx"], 2)
         b[10 * M:11 * M] = sl(o["DSfcHFlxDTs"], 1); b[11 * M:12 * M] = sl(o["DSfcHFlxDTs"], 2)
 
+    def sfc_fused(self, store_full=False):
+        """remap_to_sfc + bulk + pack_sfc in ONE kernel (dccm_sfc_exchange_device): the 22 remapped
+        input layers stay in registers; only the 21 put-side layers are stored."""
+        import ctypes as C
+        full = None
+        if store_full:
+            f = L.SfcFields()
+            for n in L.SfcFields._names:
+                setattr(f, n, None)
+            for k, t in self.sfc_out.items():
+                setattr(f, k, t.data_ptr())
+            f.SfcTemp = self.s_obil.data_ptr()
+            f.SfcAlbedo = self.s_ocons[self.M:].data_ptr()
+            full = C.byref(f)
+        o = self.ops
+        L.check(L.lib().dccm_sfc_exchange_device(
+            o["as_bil"]._h, o["as_cons"]._h, o["os_bil"]._h, o["os_cons"]._h,
+            L.tptr(self.a2s_bil), L.tptr(self.a2s_cons), L.tptr(self.o2s_bil), L.tptr(self.o2s_cons),
+            self.M, float(self.sig1), L.tptr(self.s2a), L.tptr(self.s2o), full, L.current_stream()))
+        self.launches += 1
+
     def remap_from_sfc(self):
         M = self.M
         self.ops["sa_cons"].apply(self.s2a[:4 * M], self.a_recv[:4 * M])
@@ -174,11 +195,14 @@ class SurfaceExchange:
         self.vdiff.backward_device(self.tend, lvl1)
         self.launches += 1
 
-    def step(self):
+    def step(self, fused=True):
         self.forward()
-        self.remap_to_sfc()
-        self.bulk()
-        self.pack_sfc()
+        if fused:
+            self.sfc_fused()
+        else:
+            self.remap_to_sfc()
+            self.bulk()
+            self.pack_sfc()
         self.remap_from_sfc()
         self.backward()
 
@@ -197,7 +221,11 @@ class SurfaceExchange:
         b["bulk"] = 8 * (20 + n_out) * M * nS
         b["remap_from_sfc"] = (remap("sa_cons", 4, nS, nA) + remap("sa_bil", 5, nS, nA)
                                + remap("so_cons", 10, nS, nO) + remap("so_bil", 2, nS, nO))
-        b["total"] = sum(b.values())
+        # fused surface step: tables + source layers in, the 21 put-side layers out
+        b["sfc_fused"] = (12 * (self.nnz["as_bil"] + self.nnz["as_cons"] + self.nnz["os_bil"] + self.nnz["os_cons"])
+                          + 4 * 4 * (nS + 1) + 8 * M * (17 * nA + 5 * nO) + 8 * 21 * M * nS)
+        b["total"] = b["fwd"] + b["bwd"] + b["remap_to_sfc"] + b["bulk"] + b["remap_from_sfc"]
+        b["total_fused"] = b["fwd"] + b["bwd"] + b["sfc_fused"] + b["remap_from_sfc"]
         return b
 
     def remapped_cell_fields(self):

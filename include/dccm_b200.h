@@ -143,6 +143,25 @@ typedef struct dccm_sfc_fields {
 int dccm_bulkflux_device(int nx, int ny, int ld, int64_t off, int64_t slot_stride,
                          const dccm_sfc_fields *f, double sig1, void *stream);
 
+/* ------------------------------------------------------------------ fused surface step (K1+K2)
+ * The surface component's whole coupling step, get -> bulk flux -> put, in one kernel:
+ * replaces jcup_get_data x16 -> interpolate_data -> unpack (ref sfc/dccm_sfc_mod.f90:865-881,
+ * :900-951), DSFCM_Util_SfcBulkFlux_Get (:886-897) and the put-side selection/pack (:764-809).
+ * Buffers are layer-major with `members` ensemble members per layer (row = layer*members+m):
+ *   a2s_bil (13 layers, nA): WindU WindV SfcAirTemp QVap1 SfcPress ImplCplCoef1(4) ImplCplCoef2(4)
+ *   a2s_cons (4, nA): LDwRFlx SDwRFlx RainFall SnowFall
+ *   o2s_bil (2, nO): SfcTemp(ocean) SfcTemp(ice)   o2s_cons (3, nO): SIceCon SfcAlbedo(ocean) SfcAlbedo(ice)
+ *   s2a (9, nS): LUwRFlx SUwRFlx SenHFlx QVapMFlx [composite] | SfcAlbedo(3) DelVarImplCPL(4)
+ *   s2o (12, nS): SfcHFlx_ns SfcHFlx_sr [ocean] SnowFall RainFall Evap -WindStressX -WindStressY |
+ *                 SfcHFlx_ns SfcHFlx_sr Evap [ice] | DSfcHFlxDTs(ocean) DSfcHFlxDTs(ice)
+ * `full` (optional) receives the API-complete DSFCM arrays, slot stride members*nS. */
+int dccm_sfc_exchange_device(const dccm_remap *as_bil, const dccm_remap *as_cons,
+                             const dccm_remap *os_bil, const dccm_remap *os_cons,
+                             const double *a2s_bil, const double *a2s_cons,
+                             const double *o2s_bil, const double *o2s_cons,
+                             int members, double sig1, double *s2a, double *s2o,
+                             const dccm_sfc_fields *full, void *stream);
+
 /* ------------------------------------------------------------------ implicit coupling (K3/K4)
  * Replaces dcpam_sfc_implicit_coupling_mod, ref atm/dcpam_sfc_implicit_coupling_mod.f90. */
 typedef struct dccm_vdiff dccm_vdiff;

@@ -8,6 +8,7 @@ nproc > $OUT/host.txt; free -g >> $OUT/host.txt
 ( time timeout 900 python -m pytest tests -m gpu -x -q ) > $OUT/pytest.log 2>&1
 echo "pytest exit $?" >> $OUT/pytest.log
 ( time timeout 900 python bench.py --steps 10 --warmup 3 ) > $OUT/bench.json 2> $OUT/bench.err
+( timeout 600 python bench.py --steps 10 --warmup 3 --unfused --no-e2e --no-cpu ) > $OUT/bench_unfused.json 2>> $OUT/bench.err
 echo "bench exit $?" >> $OUT/bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'remap_csr|bulkflux|vdiff|exchange' -c 60 \
     --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_bench.log 2>&1

@@ -328,12 +328,22 @@ def test_exchange_step_vs_oracle(gpu, orc, dccm, S, name, K, fast):
     col, atm, ocn = S.column_inputs(np, A, K, 1), S.atm_surface_fields(np, A), S.ocn_surface_fields(np, O)
     tt = lambda d: {k: torch.as_tensor(v, device=gpu).contiguous() for k, v in d.items()}
     ex.set_inputs(tt(col), {k: v[None] for k, v in tt(atm).items()}, {k: v[None] for k, v in tt(ocn).items()})
-    ex.step()
+    ex.step(fused=False)
     torch.cuda.synchronize()
     ref = oracle_exchange(orc, S, A, O, Sx, K, 1, 1, tabs, col, atm, ocn)
     detail = {}
     worst = compare_exchange(ex, ref, detail=detail)
     assert worst <= RTOL, detail
+    # the fused surface kernel (remap + bulk flux + pack in registers) gives the same bits
+    keep = {k: getattr(ex, k).clone() for k in ("s2a", "s2o", "a_recv", "o_recv")}
+    keep.update({k: v.clone() for k, v in ex.tend.items()})
+    ex.s2a.zero_(); ex.s2o.zero_()
+    ex.step(fused=True)
+    torch.cuda.synchronize()
+    for k in ("s2a", "s2o", "a_recv", "o_recv"):
+        assert torch.equal(getattr(ex, k), keep[k]), k
+    for k in ex.tend:
+        assert torch.equal(ex.tend[k], keep[k]), k
     if not fast:
         # reference-order mode: everything up to the bulk flux is bit-exact
         assert detail["Coef1"] == 0.0 and detail["Coef2"] == 0.0 and detail["s_bil"] == 0.0
@@ -360,6 +370,10 @@ def test_exchange_ensemble_members_match_single_runs(gpu, orc, dccm, S):
                    {k: torch.stack([a[k] for a in atms]) for k in atms[0]},
                    {k: torch.stack([o[k] for o in ocns]) for k in ocns[0]})
     exM.step()
+    unf = X.SurfaceExchange(A, O, Sx, K, 1, 1, tabs=tabs, members=M, device=gpu)
+    unf.col_in, unf.a2s_bil, unf.a2s_cons, unf.o2s_bil, unf.o2s_cons = exM.col_in, exM.a2s_bil.clone(), exM.a2s_cons, exM.o2s_bil, exM.o2s_cons
+    unf.step(fused=False)
+    assert torch.equal(unf.o_recv, exM.o_recv) and torch.equal(unf.a_recv, exM.a_recv)
     for m in range(M):
         ex1 = X.SurfaceExchange(A, O, Sx, K, 1, 1, tabs=tabs, members=1, device=gpu)
         ex1.set_inputs(cols[m], {k: v[None] for k, v in atms[m].items()}, {k: v[None] for k, v in ocns[m].items()})
