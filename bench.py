@@ -233,17 +233,24 @@ def run_ours(args, rank, world):
     exch_mod = importlib.import_module("dennou-ccm_b200.exchange")
     wl = args.workload
     A, O, S, K, nc, M = make_grids(dccm, wl)
-    if world > 1:
-        raise SystemExit("multi-GPU sharding is wired in dennou-ccm_b200/sharding.py (see bench --gpus)")
 
     t_setup = time.time()
-    ex = exch_mod.SurfaceExchange(A, O, S, K, nc, 1, members=M, fast=not args.reference_order, device=dev)
-    # synthetic inputs, generated on the device
-    col = [syn.column_inputs(torch, A, K, nc, dev=dev, member=m) for m in range(M)]
+    if world > 1:
+        if M > 1:
+            raise SystemExit("ensemble workloads shard by member (replicas): run them with --gpus 1 per member block")
+        sh = importlib.import_module("dennou-ccm_b200.sharding")
+        ex = sh.ShardedExchange(A, O, S, K, nc, 1, rank=rank, world=world, dist=dist,
+                                fast=not args.reference_order, device=dev)
+        (ja0, ja1), (jo0, jo1) = ex.plan.bands["A"][rank], ex.plan.bands["O"][rank]
+    else:
+        ex = exch_mod.SurfaceExchange(A, O, S, K, nc, 1, members=M, fast=not args.reference_order, device=dev)
+        (ja0, ja1), (jo0, jo1) = (0, A.jm), (0, O.jm)
+    # synthetic inputs, generated on the device (pure functions of the global cell index)
+    col = [syn.column_inputs(torch, A, K, nc, ja0, ja1, dev=dev, member=m) for m in range(M)]
     col_in = {k: torch.cat([c[k] for c in col], dim=-1).contiguous() for k in col[0]}
     del col
-    atm = [syn.atm_surface_fields(torch, A, dev=dev, member=m) for m in range(M)]
-    ocn = [syn.ocn_surface_fields(torch, O, dev=dev, member=m) for m in range(M)]
+    atm = [syn.atm_surface_fields(torch, A, ja0, ja1, dev=dev, member=m) for m in range(M)]
+    ocn = [syn.ocn_surface_fields(torch, O, jo0, jo1, dev=dev, member=m) for m in range(M)]
     atm_sfc = {k: torch.stack([a[k] for a in atm]) for k in atm[0]}
     ocn_sfc = {k: torch.stack([o[k] for o in ocn]) for k in ocn[0]}
     ex.set_inputs(col_in, atm_sfc, ocn_sfc)
@@ -251,6 +258,11 @@ def run_ours(args, rank, world):
     t_setup = time.time() - t_setup
 
     bytes_alg = ex.algorithmic_bytes()
+    if world > 1:                                  # whole-job bytes: sum over ranks
+        keys = sorted(bytes_alg)
+        t = torch.tensor([float(bytes_alg[k]) for k in keys], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        bytes_alg = {k: float(v) for k, v in zip(keys, t.tolist())}
     peak, peak_src = load_peaks()
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -262,25 +274,33 @@ def run_ours(args, rank, world):
     sampler.start()
     ex.launches = 0
     marks = []
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     e0 = ev(); e0.record()
     for _ in range(args.steps):
         m = [ev() for _ in range(7)]
-        m[0].record(); ex.forward()
+        m[0].record(); ex.forward(); ex.halo_to_sfc()
         if args.unfused:
             m[1].record(); ex.remap_to_sfc()
             m[2].record(); ex.bulk()
             m[3].record(); ex.pack_sfc()
         else:
             m[1].record(); m[2].record(); m[3].record(); ex.sfc_fused()
-        m[4].record(); ex.remap_from_sfc()
+        m[4].record(); ex.halo_from_sfc(); ex.remap_from_sfc()
         m[5].record(); ex.backward()
         m[6].record()
         marks.append(m)
     e1 = ev(); e1.record()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:                                  # device time, max over ranks
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     launches = ex.launches
     names = (["fwd", "remap_to_sfc", "bulk", "pack", "remap_from_sfc", "bwd"] if args.unfused
              else ["fwd", "_a", "_b", "sfc_fused", "remap_from_sfc", "bwd"])
@@ -312,16 +332,25 @@ def run_ours(args, rank, world):
                      "algorithmic_bytes_per_launch": bytes_alg["fwd"]},
         "clocks": clocks, "gpu_launches": launches,
     }
+    if world > 1:
+        line["config"]["sharding"] = (f"{world} latitude bands (row blocks), halo rows via NCCL send/recv: "
+                                      f"{ex.plan.halo_bytes(rank, {'A': 17, 'O': 5, 'S': 21})} B received on rank {rank} per exchange")
+        line["roofline"]["note"] = "per-rank kernel on rank 0's band; achieved = rank-0 bytes / rank-0 time"
+        line["roofline"]["achieved"] = ex.algorithmic_bytes()["fwd"] / (part_ms["fwd"] * 1e-3) / 1e9
+        line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
+        line["roofline"]["algorithmic_bytes_per_launch"] = ex.algorithmic_bytes()["fwd"]
 
     if not args.no_e2e:
         line["e2e"] = run_e2e(torch, ex, col_in, atm_sfc, ocn_sfc, args)
-    if not args.no_cpu and rank == 0:
+    if not args.no_cpu and rank == 0 and world == 1:
         try:
             line["cpu_baseline"] = cpu_baseline(dccm, wl)
         except Exception as e:           # the baseline must never take the GPU number down
             line["cpu_baseline"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_e2e(torch, ex, col_in, atm_sfc, ocn_sfc, args):
@@ -350,13 +379,23 @@ def run_e2e(torch, ex, col_in, atm_sfc, ocn_sfc, args):
         for h, d in zip(host_out, outs):
             h.copy_(d, non_blocking=True)
 
+    import torch.distributed as dist
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     one()
     torch.cuda.synchronize()
+    if multi:
+        dist.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
         one()
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / steps
+    if multi:
+        t = torch.tensor([dt, float(h2d), float(d2h)], dtype=torch.float64, device=ex.dev)
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t)
+        dt, h2d, d2h = float(tm[0]), int(t[1]), int(t[2])
     return {"value": 1.0 / dt, "unit": "exchanges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "ms_per_step": 1e3 * dt, "steps": steps,
             "note": "pinned host buffers, H2D of all column/surface inputs and D2H of tendencies + remapped fields inside the timed region"}

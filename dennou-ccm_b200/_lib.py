@@ -61,6 +61,10 @@ _SIGS = {
                                          f64p, f64p, C.c_int, C.c_int, C.POINTER(vp)]),
     "dccm_table_gen_bilinear": (C.c_int, [C.c_int, f64p, C.c_int, f64p, C.c_int, f64p, C.c_int, f64p,
                                           C.c_int, C.POINTER(vp)]),
+    "dccm_table_gen_jones99_rows": (C.c_int, [C.c_int, f64p, C.c_int, f64p, C.c_int, f64p, C.c_int, f64p,
+                                              f64p, f64p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "dccm_table_gen_bilinear_rows": (C.c_int, [C.c_int, f64p, C.c_int, f64p, C.c_int, f64p, C.c_int, f64p,
+                                               C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
     "dccm_table_write_text": (C.c_int, [vp, C.c_char_p]),
     "dccm_table_read_text": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
     "dccm_table_write_bin": (C.c_int, [vp, C.c_char_p]),
@@ -81,11 +85,12 @@ _SIGS = {
     "dccm_bulkflux_get_host": (C.c_int, [C.c_int, C.c_int] + [f64p] * 28),
     "dccm_bulkflux_device": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
                                        C.POINTER(SfcFields), C.c_double, vp]),
-    "dccm_sfc_exchange_device": (C.c_int, [vp] * 4 + [vp] * 4 + [C.c_int, C.c_double, vp, vp,
+    "dccm_sfc_exchange_device": (C.c_int, [vp] * 4 + [vp] * 4 + [C.c_int, C.c_double, vp, vp, C.c_int64,
                                            C.POINTER(SfcFields), vp]),
     "dccm_vdiff_create": (C.c_int, [C.c_int] * 5 + [C.c_double] * 4 + [C.POINTER(vp)]),
     "dccm_vdiff_destroy": (None, [vp]),
     "dccm_vdiff_set_mode": (C.c_int, [vp, C.c_int]),
+    "dccm_vdiff_set_coef_stride": (C.c_int, [vp, C.c_int64]),
     "dccm_vdiff_forward_host": (C.c_int, [vp] + [f64p] * 18),
     "dccm_vdiff_backward_host": (C.c_int, [vp] + [f64p] * 4),
     "dccm_vdiff_forward_device": (C.c_int, [vp] + [vp] * 18 + [vp]),

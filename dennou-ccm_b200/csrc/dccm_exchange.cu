@@ -37,7 +37,7 @@ struct SfcArgs {
     double *s2a, *s2o;                                        // (9M, nS) (12M, nS)
     dccm_sfc_fields full;                                     // optional API-complete outputs, slot stride M*nS
     int has_full;
-    int64_t nA, nO, nS;
+    int64_t nA, nO, nS, sld;      // sld: cells per (layer, member) row of s2a / s2o (>= nS)
     int M;
     double sig1;
 };
@@ -88,13 +88,13 @@ __global__ void __launch_bounds__(kThreads) sfc_exchange_kernel(const SfcArgs a)
     bulk_column(in, a.sig1, o);
 
     // packed put-side layers, row = layer * M + member
-    const int64_t ld = (int64_t)M * nS;                   // one layer of all members
-    double *pa = a.s2a + (int64_t)m * nS + r;
+    const int64_t ld = (int64_t)M * a.sld;                // one layer of all members
+    double *pa = a.s2a + (int64_t)m * a.sld + r;
     pa[0 * ld] = o.LUwRFlx[2]; pa[1 * ld] = o.SUwRFlx[2]; pa[2 * ld] = o.SenHFlx[2]; pa[3 * ld] = o.QVapMFlx[2];
     pa[4 * ld] = o.SfcAlbedo3;
 #pragma unroll
     for (int k = 0; k < 4; k++) pa[(5 + k) * ld] = o.Del[k];
-    double *po = a.s2o + (int64_t)m * nS + r;
+    double *po = a.s2o + (int64_t)m * a.sld + r;
     po[0 * ld] = o.HFlx_ns[0]; po[1 * ld] = o.HFlx_sr[0]; po[2 * ld] = snow; po[3 * ld] = rain;
     po[4 * ld] = o.QVapMFlx[0]; po[5 * ld] = -o.WindStressX[2]; po[6 * ld] = -o.WindStressY[2];
     po[7 * ld] = o.HFlx_ns[1]; po[8 * ld] = o.HFlx_sr[1]; po[9 * ld] = o.QVapMFlx[1];
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kThreads) sfc_exchange_kernel(const SfcArgs a)
 
     if (a.has_full) {
         const dccm_sfc_fields &f = a.full;
-        const int64_t c = (int64_t)m * nS + r, ss = ld;
+        const int64_t c = (int64_t)m * nS + r, ss = (int64_t)M * nS;
 #define ST3(ptr, v) if (f.ptr) { f.ptr[c] = o.v[0]; f.ptr[c + ss] = o.v[1]; f.ptr[c + 2 * ss] = o.v[2]; }
 #define ST2(ptr, v) if (f.ptr) { f.ptr[c] = o.v[0]; f.ptr[c + ss] = o.v[1]; }
         ST3(WindStressX, WindStressX) ST3(WindStressY, WindStressY) ST3(SenHFlx, SenHFlx)
@@ -129,7 +129,7 @@ extern "C" int dccm_sfc_exchange_device(const dccm_remap *as_bil, const dccm_rem
                                         const dccm_remap *os_bil, const dccm_remap *os_cons,
                                         const double *a2s_bil, const double *a2s_cons,
                                         const double *o2s_bil, const double *o2s_cons,
-                                        int members, double sig1, double *s2a, double *s2o,
+                                        int members, double sig1, double *s2a, double *s2o, int64_t s_ld,
                                         const dccm_sfc_fields *full, void *stream)
 {
     if (!as_bil || !as_cons || !os_bil || !os_cons) return fail(DCCM_ERR_ARG, "dccm_sfc_exchange: null table handle");
@@ -146,7 +146,8 @@ extern "C" int dccm_sfc_exchange_device(const dccm_remap *as_bil, const dccm_rem
     a.s2a = s2a; a.s2o = s2o;
     a.has_full = full ? 1 : 0;
     if (full) a.full = *full; else memset(&a.full, 0, sizeof a.full);
-    a.nA = nA; a.nO = nO; a.nS = nS; a.M = members; a.sig1 = sig1;
+    if (s_ld != 0 && s_ld < nS) return fail(DCCM_ERR_ARG, "dccm_sfc_exchange: s_ld < surface cells");
+    a.nA = nA; a.nO = nO; a.nS = nS; a.sld = s_ld ? s_ld : nS; a.M = members; a.sig1 = sig1;
     const int64_t n = (int64_t)nS * members;
     const unsigned grid = (unsigned)((n + kThreads - 1) / kThreads);
     sfc_exchange_kernel<<<grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);

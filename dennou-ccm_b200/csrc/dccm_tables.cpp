@@ -163,9 +163,20 @@ extern "C" int dccm_table_gen_jones99(int nxs, const double *x_LonS, int nys, co
                                       const double *y_LatIntWtS, const double *y_LatIntWtD,
                                       int accuracy_order, int lon_mode, dccm_table **out)
 {
+    return dccm_table_gen_jones99_rows(nxs, x_LonS, nys, y_LatS, nxd, x_LonD, nyd, y_LatD, y_LatIntWtS, y_LatIntWtD,
+                                       accuracy_order, lon_mode, 1, nyd, out);
+}
+
+extern "C" int dccm_table_gen_jones99_rows(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                                           int nxd, const double *x_LonD, int nyd, const double *y_LatD,
+                                           const double *y_LatIntWtS, const double *y_LatIntWtD,
+                                           int accuracy_order, int lon_mode, int jd_first, int jd_last,
+                                           dccm_table **out)
+{
     (void)y_LatD;
     *out = nullptr;
     if (nxs < 1 || nys < 1 || nxd < 1 || nyd < 1) return fail(DCCM_ERR_ARG, "jones99: bad grid sizes");
+    if (jd_first < 1 || jd_last > nyd || jd_first > jd_last + 1) return fail(DCCM_ERR_ARG, "jones99: bad destination row range");
     std::vector<double> uS = lon_edges(nxs, x_LonS), uD = lon_edges(nxd, x_LonD);
     std::vector<double> vS = lat_edges(nys, y_LatIntWtS), vD = lat_edges(nyd, y_LatIntWtD);
 
@@ -219,7 +230,7 @@ extern "C" int dccm_table_gen_jones99(int nxs, const double *x_LonS, int nys, co
     else          { DLon_nk = 2.0 * kPi / (double)nxd; DLon_n = 2.0 * kPi; }
     std::vector<LatRow> rows(nyd + 1);
     std::vector<double> seg(nys + 2);
-    for (int jD = 1; jD <= nyd; jD++) {
+    for (int jD = jd_first; jD <= jd_last; jD++) {
         int r1, r2;
         if (!overlap_range(vS, nys, vD[jD - 1], vD[jD], r1, r2))
             return fail(DCCM_ERR_SEARCH, "jones99: latitude overlap search failed at jD=%d", jD);
@@ -250,7 +261,7 @@ extern "C" int dccm_table_gen_jones99(int nxs, const double *x_LonS, int nys, co
 
     // ---- emit in table-file order (ref :230-275) ----
     dccm_table *t = new dccm_table();
-    for (int jD = 1; jD <= nyd; jD++) {
+    for (int jD = jd_first; jD <= jd_last; jD++) {
         const LatRow &R = rows[jD];
         for (int iD = 1; iD <= nxd; iD++) {
             int nxr = general ? gptr[iD] - gptr[iD - 1] : lxn[iD];
@@ -283,11 +294,19 @@ extern "C" int dccm_table_gen_bilinear(int nxs, const double *x_LonS, int nys, c
                                        int nxr, const double *x_LonR, int nyr, const double *y_LatR,
                                        int lon_mode, dccm_table **out)
 {
+    return dccm_table_gen_bilinear_rows(nxs, x_LonS, nys, y_LatS, nxr, x_LonR, nyr, y_LatR, lon_mode, 1, nyr, out);
+}
+
+extern "C" int dccm_table_gen_bilinear_rows(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                                            int nxr, const double *x_LonR, int nyr, const double *y_LatR,
+                                            int lon_mode, int jr_first, int jr_last, dccm_table **out)
+{
     *out = nullptr;
     if (nxs < 1 || nys < 2 || nxr < 1 || nyr < 1) return fail(DCCM_ERR_ARG, "bilinear: bad grid sizes");
+    if (jr_first < 1 || jr_last > nyr || jr_first > jr_last + 1) return fail(DCCM_ERR_ARG, "bilinear: bad destination row range");
     const double dlon_r = 360.0 / (double)nxr, dlon_s = 360.0 / (double)nxs;   // ref :78-79
     dccm_table *t = new dccm_table();
-    t->reserve((size_t)nxr * nyr * ((nxr == 1) ? 2 * nxs : (nxs == 1 ? 2 : 4)));
+    t->reserve((size_t)nxr * (jr_last - jr_first + 1) * ((nxr == 1) ? 2 * nxs : (nxs == 1 ? 2 : 4)));
     // longitude part is the same for every row: hoist (ref :116-119, cal_coef :154-165)
     std::vector<int> is1(nxr), is2(nxr);
     std::vector<double> a1(nxr), a2(nxr);
@@ -302,7 +321,7 @@ extern "C" int dccm_table_gen_bilinear(int nxs, const double *x_LonS, int nys, c
             a2[ir - 1] = 1.0 - a1[ir - 1];
         }
     }
-    for (int jr = 1; jr <= nyr; jr++) {
+    for (int jr = jr_first; jr <= jr_last; jr++) {
         double latR = y_LatR[jr - 1];
         int js = -1; bool extp = true;                                   // get_correspondID_latS :130-152
         for (int j = 1; j <= nys - 1; j++)

@@ -32,6 +32,7 @@ struct dccm_vdiff {
     double Grav = 0, CpDry = 0, GasRDry = 0, DelTime = 0;
     int fast = 0;
     int64_t NC = 0;
+    int64_t coef_stride = 0;                                // 0 = NC
     double *bUV = nullptr, *bT = nullptr, *bQ = nullptr;   // swept diagonals, (NC, kmax)
     DevBuf in_buf, out_buf;                                 // scratch of the host entry points
 };
@@ -46,7 +47,7 @@ struct FwdArgs {
     const double *Press, *zExner, *rExner, *VirTemp, *Height, *DiffV, *DiffT, *DiffQ;
     double *DU, *DV, *DT, *DQ, *Coef1, *Coef2;
     double *bUV, *bT, *bQ;
-    int64_t NC;
+    int64_t NC, cstride;          // cstride: slot stride of Coef1/Coef2 (>= NC)
     int K, iq;
     double Grav, CpDry, GasRDry, DelTime;
 };
@@ -200,15 +201,16 @@ __global__ void __launch_bounds__(kThreads) vdiff_forward_kernel(const FwdArgs a
         const double c1uv = tmp1 + DFADUV1 - DFADUV2 / bUVn;
         a.Coef1[c] = c1uv;
         a.Coef2[c] = rU1 - DFADUV2 * rU2 / bUVn;
-        a.Coef1[c + NC] = c1uv;
-        a.Coef2[c + NC] = rV1 - DFADUV2 * rV2 / bUVn;
+        const int64_t CS = a.cstride;
+        a.Coef1[c + CS] = c1uv;
+        a.Coef2[c + CS] = rV1 - DFADUV2 * rV2 / bUVn;
         const double DFADT1 = CpDry * rE_hi * TT_hi / zE_hi;
         const double DFADT2 = -CpDry * rE_hi * TT_hi / zE_hi2;
-        a.Coef1[c + 2 * NC] = CpDry * tmp1 + DFADT1 - DFADT2 / bTn;
-        a.Coef2[c + 2 * NC] = rT1 - DFADT2 * rT2 / bTn;
+        a.Coef1[c + 2 * CS] = CpDry * tmp1 + DFADT1 - DFADT2 / bTn;
+        a.Coef2[c + 2 * CS] = rT1 - DFADT2 * rT2 / bTn;
         const double DFADQ1 = TQ_hi, DFADQ2 = -TQ_hi;
-        a.Coef1[c + 3 * NC] = tmp1 + DFADQ1 - DFADQ2 / bQn;
-        a.Coef2[c + 3 * NC] = rQ1v - DFADQ2 * rQ2 / bQn;
+        a.Coef1[c + 3 * CS] = tmp1 + DFADQ1 - DFADQ2 / bQn;
+        a.Coef2[c + 3 * CS] = rQ1v - DFADQ2 * rQ2 / bQn;
     }
 #undef HL
 #undef FL
@@ -248,18 +250,40 @@ __global__ void __launch_bounds__(kThreads) vdiff_backward_kernel(const BwdArgs 
     a.DU[c] = xU / twodt; a.DV[c] = xV / twodt; a.DT[c] = xT / twodt;           // :54-63
 #pragma unroll
     for (int n = 0; n < NQ; n++) a.DQ[c + NC * (int64_t)K * n] = xQ[n] / twodt;
-    for (int k = 2; k <= K; k++) {                                              // :414-416
+    // Bottom-up substitution (:414-416).  The recurrence x_k = (r'_k - x_{k-1}) / b'_k is a serial
+    // chain of divisions, but its operands are not: the loads of level k+2 are issued before level k
+    // is consumed (two register sets, loop unrolled by two), so memory latency overlaps the chain.
+    struct Lvl { double bUV, bT, bQ, rU, rV, rT, rQ[NQ]; };
+    auto load = [&](int k, Lvl &v) {
         const int64_t o = c + NC * (int64_t)(k - 1);
-        const double bUV = __ldg(&a.bUV[o]), bT = __ldg(&a.bT[o]), bQ = __ldg(&a.bQ[o]);
-        xU = (a.DU[o] - xU) / bUV;
-        xV = (a.DV[o] - xV) / bUV;
-        xT = (a.DT[o] - xT) / bT;
+        v.bUV = __ldg(&a.bUV[o]); v.bT = __ldg(&a.bT[o]); v.bQ = __ldg(&a.bQ[o]);
+        v.rU = a.DU[o]; v.rV = a.DV[o]; v.rT = a.DT[o];
+#pragma unroll
+        for (int n = 0; n < NQ; n++) v.rQ[n] = a.DQ[o + NC * (int64_t)K * n];
+    };
+    auto solve = [&](int k, const Lvl &v) {
+        const int64_t o = c + NC * (int64_t)(k - 1);
+        xU = (v.rU - xU) / v.bUV;
+        xV = (v.rV - xV) / v.bUV;
+        xT = (v.rT - xT) / v.bT;
         a.DU[o] = xU / twodt; a.DV[o] = xV / twodt; a.DT[o] = xT / twodt;
 #pragma unroll
         for (int n = 0; n < NQ; n++) {
-            const int64_t oq = o + NC * (int64_t)K * n;
-            xQ[n] = (a.DQ[oq] - xQ[n]) / bQ;
-            a.DQ[oq] = xQ[n] / twodt;
+            xQ[n] = (v.rQ[n] - xQ[n]) / v.bQ;
+            a.DQ[o + NC * (int64_t)K * n] = xQ[n] / twodt;
+        }
+    };
+    Lvl s0, s1;
+    load(2, s0);
+    if (K >= 3) load(3, s1);
+    for (int k = 2; k <= K; k += 2) {
+        const Lvl c0 = s0;
+        if (k + 2 <= K) load(k + 2, s0);
+        solve(k, c0);
+        if (k + 1 <= K) {
+            const Lvl c1 = s1;
+            if (k + 3 <= K) load(k + 3, s1);
+            solve(k + 1, c1);
         }
     }
 }
@@ -320,6 +344,14 @@ extern "C" int dccm_vdiff_set_mode(dccm_vdiff *h, int fast)
     return DCCM_OK;
 }
 
+extern "C" int dccm_vdiff_set_coef_stride(dccm_vdiff *h, int64_t slot_stride)
+{
+    if (!h) return fail(DCCM_ERR_ARG, "dccm_vdiff_set_coef_stride: null handle");
+    if (slot_stride != 0 && slot_stride < h->NC) return fail(DCCM_ERR_ARG, "dccm_vdiff_set_coef_stride: stride < columns");
+    h->coef_stride = slot_stride;
+    return DCCM_OK;
+}
+
 extern "C" int dccm_vdiff_forward_device(dccm_vdiff *h,
     const double *FX, const double *FY, const double *FH, const double *FQ,
     const double *Press, const double *zExner, const double *rExner,
@@ -334,6 +366,7 @@ extern "C" int dccm_vdiff_forward_device(dccm_vdiff *h,
     a.DU = DU; a.DV = DV; a.DT = DT; a.DQ = DQ; a.Coef1 = Coef1; a.Coef2 = Coef2;
     a.bUV = h->bUV; a.bT = h->bT; a.bQ = h->bQ;
     a.NC = h->NC; a.K = h->kmax; a.iq = h->iq;
+    a.cstride = h->coef_stride > 0 ? h->coef_stride : h->NC;
     a.Grav = h->Grav; a.CpDry = h->CpDry; a.GasRDry = h->GasRDry; a.DelTime = h->DelTime;
     const unsigned grid = (unsigned)((h->NC + kThreads - 1) / kThreads);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -29,6 +29,9 @@ class SfcImplicitCoupling:
     def set_fast(self, fast):
         L.check(L.lib().dccm_vdiff_set_mode(self._h, 1 if fast else 0))
 
+    def set_coef_stride(self, slot_stride):
+        L.check(L.lib().dccm_vdiff_set_coef_stride(self._h, int(slot_stride)))
+
     def __del__(self):
         if getattr(self, "_h", None):
             L.lib().dccm_vdiff_destroy(self._h)

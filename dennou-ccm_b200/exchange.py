@@ -53,7 +53,10 @@ class SurfaceExchange:
     """
 
     def __init__(self, A, O, S, kmax, ncmax=1, index_h2ovap=1, tabs=None, consts=None, members=1,
-                 fast=True, device=None, api_complete=True):
+                 fast=True, device=None, layout=None):
+        """layout (sharded runs, sharding.py): {"A"|"S"|"O": (n_own, n_ext, off)} -- cells this rank
+        owns, cells of its source buffers (own + halo rows) and where the owned cells start in them;
+        A/O/S are then objects with .im/.jm/.n of the LOCAL band."""
         import torch
         self.torch = torch
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
@@ -65,13 +68,19 @@ class SurfaceExchange:
         self.GasRDry = c.get("GasRDry", syn.GASRDRY); self.DelTime = c.get("DelTime", syn.DELTIME)
         self.sig1 = c.get("Sig1", syn.SIG1)
         tabs = tabs or build_tables(A, O, S)
+        layout = layout or {"A": (A.n, A.n, 0), "S": (S.n, S.n, 0), "O": (O.n, O.n, 0)}
+        self.layout = layout
+        self.sharded = any(ext != own for own, ext, off in layout.values())
+        assert not (self.sharded and members > 1), "ensembles shard by member, not by latitude band"
         self.ops = {}
         self.nnz = {}
         for key, (send_i, recv_i, coef) in tabs.items():
-            s, d = {"a": A, "s": S, "o": O}[key[0]], {"a": A, "s": S, "o": O}[key[1]]
-            self.ops[key] = RemapOperator(send_i, recv_i, coef, s.n, d.n)
+            s, d = key[0].upper(), key[1].upper()
+            self.ops[key] = RemapOperator(send_i, recv_i, coef, layout[s][1], layout[d][0])
             self.nnz[key] = len(coef)
         nA, nS, nO, M = A.n, S.n, O.n, members
+        nAx, nSx, nOx = layout["A"][1], layout["S"][1], layout["O"][1]
+        self.offA, self.offS, self.offO = layout["A"][2], layout["S"][2], layout["O"][2]
         # ensemble members are extra columns for the column solve: imax*jmax = M*nA
         self.vdiff = SfcImplicitCoupling(M * A.im, A.jm, kmax, ncmax, index_h2ovap,
                                          self.Grav, self.CpDry, self.GasRDry, self.DelTime, fast=fast)
@@ -81,15 +90,17 @@ class SurfaceExchange:
         self.tend = {"DUDt": z(kmax, M * nA), "DVDt": z(kmax, M * nA), "DTempDt": z(kmax, M * nA),
                      "DQMixDt": z(ncmax, kmax, M * nA)}
         # layer-major send/recv buffers; member m of layer l is row l*M + m
-        self.a2s_bil = z(13 * M, nA); self.a2s_cons = z(4 * M, nA)
-        self.o2s_bil = z(2 * M, nO); self.o2s_cons = z(3 * M, nO)
+        self.a2s_bil = z(13 * M, nAx); self.a2s_cons = z(4 * M, nAx)
+        self.o2s_bil = z(2 * M, nOx); self.o2s_cons = z(3 * M, nOx)
         self.s_bil = z(13 * M, nS); self.s_cons = z(4 * M, nS)
         self.s_obil = z(3 * M, nS)        # SfcTemp slots 1,2 (in) + slot 3 (out)
         self.s_ocons = z(4 * M, nS)       # SIceCon, SfcAlbedo slots 1,2 (in) + slot 3 (out)
         self.sfc_out = {k: z(3 * M, nS) for k in dsfcm.OUT3}
         self.sfc_out["DelVarImplCPL"] = z(4 * M, nS)
-        self.s2a = z(9 * M, nS); self.s2o = z(12 * M, nS)
+        self.s2a = z(9 * M, nSx); self.s2o = z(12 * M, nSx)
         self.a_recv = z(9 * M, nA); self.o_recv = z(12 * M, nO)
+        if self.sharded:
+            self.vdiff.set_coef_stride(nAx)
         self.launches = 0
 
     # -- inputs -----------------------------------------------------------------------------
@@ -97,14 +108,16 @@ class SurfaceExchange:
         """col_in: dict IN_ORDER -> tensors with M*nA columns; atm_sfc/ocn_sfc: dicts of (M, n) tensors."""
         M = self.M
         self.col_in = col_in
+        a0, a1 = self.offA, self.offA + self.A.n
+        o0, o1 = self.offO, self.offO + self.O.n
         for l, name in enumerate(("WindU", "WindV", "SfcAirTemp", "QVap1", "SfcPress")):
-            self.a2s_bil[l * M:(l + 1) * M] = atm_sfc[name]
+            self.a2s_bil[l * M:(l + 1) * M, a0:a1] = atm_sfc[name]
         for l, name in enumerate(A2S_CONS):
-            self.a2s_cons[l * M:(l + 1) * M] = atm_sfc[name]
+            self.a2s_cons[l * M:(l + 1) * M, a0:a1] = atm_sfc[name]
         for l, name in enumerate(O2S_BIL):
-            self.o2s_bil[l * M:(l + 1) * M] = ocn_sfc[name]
+            self.o2s_bil[l * M:(l + 1) * M, o0:o1] = ocn_sfc[name]
         for l, name in enumerate(O2S_CONS):
-            self.o2s_cons[l * M:(l + 1) * M] = ocn_sfc[name]
+            self.o2s_cons[l * M:(l + 1) * M, o0:o1] = ocn_sfc[name]
 
     # -- the step ---------------------------------------------------------------------------
     def forward(self):
@@ -112,12 +125,17 @@ class SurfaceExchange:
         out = dict(self.tend)
         # Coef1/Coef2 go straight into the A->S send buffer (layers 5..8 and 9..12); for M > 1 the
         # solver's (4, M*nA) slot-major layout is exactly rows [5M, 9M) of the (13M, nA) buffer.
-        out["ImplCplCoef1"] = self.a2s_bil[5 * M:9 * M].view(4, M * nA)
-        out["ImplCplCoef2"] = self.a2s_bil[9 * M:13 * M].view(4, M * nA)
+        if self.sharded:      # strided slots inside the wider send buffer (dccm_vdiff_set_coef_stride)
+            out["ImplCplCoef1"] = self.a2s_bil[5:9].view(-1)[self.offA:]
+            out["ImplCplCoef2"] = self.a2s_bil[9:13].view(-1)[self.offA:]
+        else:
+            out["ImplCplCoef1"] = self.a2s_bil[5 * M:9 * M].view(4, M * nA)
+            out["ImplCplCoef2"] = self.a2s_bil[9 * M:13 * M].view(4, M * nA)
         self.vdiff.forward_device(self.col_in, out)
         self.launches += 1
 
     def remap_to_sfc(self):
+        assert not self.sharded, "the unfused surface step is single-GPU only"
         M = self.M
         self.ops["as_bil"].apply(self.a2s_bil, self.s_bil)
         self.ops["as_cons"].apply(self.a2s_cons, self.s_cons)
@@ -178,7 +196,8 @@ class SurfaceExchange:
         L.check(L.lib().dccm_sfc_exchange_device(
             o["as_bil"]._h, o["as_cons"]._h, o["os_bil"]._h, o["os_cons"]._h,
             L.tptr(self.a2s_bil), L.tptr(self.a2s_cons), L.tptr(self.o2s_bil), L.tptr(self.o2s_cons),
-            self.M, float(self.sig1), L.tptr(self.s2a), L.tptr(self.s2o), full, L.current_stream()))
+            self.M, float(self.sig1), C.c_void_p(self.s2a.data_ptr() + 8 * self.offS),
+            C.c_void_p(self.s2o.data_ptr() + 8 * self.offS), self.s2a.shape[1], full, L.current_stream()))
         self.launches += 1
 
     def remap_from_sfc(self):
@@ -195,14 +214,22 @@ class SurfaceExchange:
         self.vdiff.backward_device(self.tend, lvl1)
         self.launches += 1
 
+    def halo_to_sfc(self):
+        """hook: sharded runs exchange the halo rows of the ATM/OCN send buffers here"""
+
+    def halo_from_sfc(self):
+        """hook: sharded runs exchange the halo rows of the SFC send buffers here"""
+
     def step(self, fused=True):
         self.forward()
+        self.halo_to_sfc()
         if fused:
             self.sfc_fused()
         else:
             self.remap_to_sfc()
             self.bulk()
             self.pack_sfc()
+        self.halo_from_sfc()
         self.remap_from_sfc()
         self.backward()
 

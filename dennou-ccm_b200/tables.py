@@ -86,18 +86,21 @@ class MappingTable:
         return MappingTable(h)
 
 
-def gen_table_jones99(src, dst, accuracy_order=1, lon_mode=0):
+def gen_table_jones99(src, dst, accuracy_order=1, lon_mode=0, rows=None):
+    """rows = (j0, j1): only destination rows j0 <= j < j1 (0-based) -- a rank's latitude band."""
     h = C.c_void_p()
-    L.check(L.lib().dccm_table_gen_jones99(src.im, L.dp(src.x_Lon), src.jm, L.dp(src.y_Lat),
-                                           dst.im, L.dp(dst.x_Lon), dst.jm, L.dp(dst.y_Lat),
-                                           L.dp(src.y_LatWt), L.dp(dst.y_LatWt),
-                                           accuracy_order, lon_mode, C.byref(h)))
+    j0, j1 = (0, dst.jm) if rows is None else rows
+    L.check(L.lib().dccm_table_gen_jones99_rows(src.im, L.dp(src.x_Lon), src.jm, L.dp(src.y_Lat),
+                                                dst.im, L.dp(dst.x_Lon), dst.jm, L.dp(dst.y_Lat),
+                                                L.dp(src.y_LatWt), L.dp(dst.y_LatWt),
+                                                accuracy_order, lon_mode, j0 + 1, j1, C.byref(h)))
     return MappingTable(h)
 
 
-def gen_table_bilinear(src, dst, lon_mode=0):
+def gen_table_bilinear(src, dst, lon_mode=0, rows=None):
     h = C.c_void_p()
-    L.check(L.lib().dccm_table_gen_bilinear(src.im, L.dp(src.x_Lon), src.jm, L.dp(src.y_Lat),
-                                            dst.im, L.dp(dst.x_Lon), dst.jm, L.dp(dst.y_Lat),
-                                            lon_mode, C.byref(h)))
+    j0, j1 = (0, dst.jm) if rows is None else rows
+    L.check(L.lib().dccm_table_gen_bilinear_rows(src.im, L.dp(src.x_Lon), src.jm, L.dp(src.y_Lat),
+                                                 dst.im, L.dp(dst.x_Lon), dst.jm, L.dp(dst.y_Lat),
+                                                 lon_mode, j0 + 1, j1, C.byref(h)))
     return MappingTable(h)

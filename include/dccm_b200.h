@@ -64,6 +64,17 @@ int dccm_table_gen_jones99(int nxs, const double *x_LonS, int nys, const double 
 int dccm_table_gen_bilinear(int nxs, const double *x_LonS, int nys, const double *y_LatS,
                             int nxr, const double *x_LonR, int nyr, const double *y_LatR,
                             int lon_mode, dccm_table **out);
+/* Same generators restricted to destination rows jd_first..jd_last (1-based, inclusive): the
+ * entries a rank owning that latitude band needs (row-block sharding).  Entries are
+ * identical to the corresponding slice of the full table. */
+int dccm_table_gen_jones99_rows(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                                int nxd, const double *x_LonD, int nyd, const double *y_LatD,
+                                const double *y_LatIntWtS, const double *y_LatIntWtD,
+                                int accuracy_order, int lon_mode, int jd_first, int jd_last,
+                                dccm_table **out);
+int dccm_table_gen_bilinear_rows(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                                 int nxr, const double *x_LonR, int nyr, const double *y_LatR,
+                                 int lon_mode, int jr_first, int jr_last, dccm_table **out);
 /* The reference's on-disk format: one entry per line "iD jD iS jS coef", list-directed
  * (ref common/grid_mapping_util_jones99.f90:246-247, :479-504). */
 int dccm_table_write_text(const dccm_table *t, const char *filename);
@@ -154,12 +165,14 @@ int dccm_bulkflux_device(int nx, int ny, int ld, int64_t off, int64_t slot_strid
  *   s2a (9, nS): LUwRFlx SUwRFlx SenHFlx QVapMFlx [composite] | SfcAlbedo(3) DelVarImplCPL(4)
  *   s2o (12, nS): SfcHFlx_ns SfcHFlx_sr [ocean] SnowFall RainFall Evap -WindStressX -WindStressY |
  *                 SfcHFlx_ns SfcHFlx_sr Evap [ice] | DSfcHFlxDTs(ocean) DSfcHFlxDTs(ice)
+ * s_ld = cells per row of s2a / s2o (0 = nS; larger when the rows also hold halo cells of a
+ * sharded run, with s2a / s2o pointing at the first owned cell).
  * `full` (optional) receives the API-complete DSFCM arrays, slot stride members*nS. */
 int dccm_sfc_exchange_device(const dccm_remap *as_bil, const dccm_remap *as_cons,
                              const dccm_remap *os_bil, const dccm_remap *os_cons,
                              const double *a2s_bil, const double *a2s_cons,
                              const double *o2s_bil, const double *o2s_cons,
-                             int members, double sig1, double *s2a, double *s2o,
+                             int members, double sig1, double *s2a, double *s2o, int64_t s_ld,
                              const dccm_sfc_fields *full, void *stream);
 
 /* ------------------------------------------------------------------ implicit coupling (K3/K4)
@@ -174,6 +187,9 @@ int dccm_vdiff_create(int imax, int jmax, int kmax, int ncmax, int index_h2ovap,
 void dccm_vdiff_destroy(dccm_vdiff *h);
 /* 0 = operation order of the reference (bit-exact vs the oracle), 1 = shared reciprocals */
 int dccm_vdiff_set_mode(dccm_vdiff *h, int fast);
+/* slot stride of xya_ImplCplCoef1/2 in the *_device form (0 = imax*jmax): lets the forward
+ * solve write the coefficients straight into a wider A->S send buffer (sharded runs). */
+int dccm_vdiff_set_coef_stride(dccm_vdiff *h, int64_t slot_stride);
 /* SfcImplicitCoupling_VDiffForward (ref :72-378), Fortran dummy order. */
 int dccm_vdiff_forward_host(dccm_vdiff *h,
     const double *xyr_MomFluxX, const double *xyr_MomFluxY, const double *xyr_HeatFlux,

@@ -315,7 +315,8 @@ def test_full_size_properties_T1279(gpu, dccm, S):
 
 # ------------------------------------------------------------------ whole exchange step
 
-@pytest.mark.parametrize("name,K,fast", [("T21_Pl42", 16, False), ("T42_T42", 26, True), ("T21_1deg", 26, True)])
+@pytest.mark.parametrize("name,K,fast", [("T21_Pl42", 16, False), ("T42_T42", 26, False), ("T21_1deg", 26, False),
+                                         ("T21_1deg", 26, True)])
 def test_exchange_step_vs_oracle(gpu, orc, dccm, S, name, K, fast):
     import torch
     from exchange_ref import compare_exchange, oracle_exchange
@@ -333,7 +334,10 @@ def test_exchange_step_vs_oracle(gpu, orc, dccm, S, name, K, fast):
     ref = oracle_exchange(orc, S, A, O, Sx, K, 1, 1, tabs, col, atm, ocn)
     detail = {}
     worst = compare_exchange(ex, ref, detail=detail)
-    assert worst <= RTOL, detail
+    print(name, "fast" if fast else "reference-order", {k: float("%.2e" % v) for k, v in detail.items()})
+    # shared-reciprocal mode trades <= 3 ulp per operation; the coupling coefficients are
+    # differences of nearly equal terms, which amplifies that to a few 1e-12 downstream
+    assert worst <= (5e-12 if fast else RTOL), detail
     # the fused surface kernel (remap + bulk flux + pack in registers) gives the same bits
     keep = {k: getattr(ex, k).clone() for k in ("s2a", "s2o", "a_recv", "o_recv")}
     keep.update({k: v.clone() for k, v in ex.tend.items()})
@@ -382,3 +386,17 @@ def test_exchange_ensemble_members_match_single_runs(gpu, orc, dccm, S):
         assert torch.equal(exM.o_recv[m::M], ex1.o_recv)
         assert torch.equal(exM.a_recv[m::M], ex1.a_recv)
         assert torch.equal(exM.tend["DTempDt"][:, m * A.n:(m + 1) * A.n], ex1.tend["DTempDt"])
+
+
+def test_sharded_exchange_two_gpus_bit_exact(gpu):
+    """2 ranks over NCCL: each band of the sharded run equals the unsharded run (tests/sharded_gpu_check.py)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29631",
+                        os.path.join(here, "sharded_gpu_check.py"), "T106_1deg"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
