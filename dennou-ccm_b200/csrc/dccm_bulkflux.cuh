@@ -74,8 +74,10 @@ __device__ __forceinline__ void bulk_column(const BulkIn &in, double sig1, BulkO
     }
     const double VirTemp = in.SfcAirTemp * (1.0 + (((1.0 / EpsV) - 1.0) * in.QVap1));   // :215
     const double Press1 = in.SfcPress * sig1;                                        // :217
-    const double Exner = pow(Press1 / RefPress, GasRDry / CpDry);                    // :218
-    const double SfcExner = pow(in.SfcPress / RefPress, GasRDry / CpDry);            // :219
+    // x**kappa as exp(kappa*log(x)): |log x| << 1 here, so the result is within 1 ulp of the
+    // correctly rounded power (as good as pow()) at a fraction of its instruction count.
+    const double Exner = exp((GasRDry / CpDry) * log(Press1 / RefPress));            // :218
+    const double SfcExner = exp((GasRDry / CpDry) * log(in.SfcPress / RefPress));    // :219
     const double VelAbs = sqrt(in.WindU * in.WindU + in.WindV * in.WindV);           // :221
     const double Height = in.SfcHeight + GasRDry / Grav * VirTemp * (1.0 - sig1);    // :223-224
 

@@ -42,24 +42,47 @@ struct SfcArgs {
     double sig1;
 };
 
-template <int D>
+// One destination row of one table, D layers.  The row's (col, w) pairs are fetched CH at a
+// time BEFORE any of the dependent source loads is issued, so a thread has up to CH*D gathers in
+// flight instead of D (rows of these tables hold 1-4 entries); accumulation stays in table order.
+template <int D, int CH>
 __device__ __forceinline__ void gather(const Csr &t, int r, const double *__restrict__ src, int64_t n_src,
                                        int M, int m, double (&acc)[D])
 {
 #pragma unroll
     for (int d = 0; d < D; d++) acc[d] = 0.0;
-    const int k0 = t.rowptr[r], k1 = t.rowptr[r + 1];
+    const int k0 = __ldg(&t.rowptr[r]), k1 = __ldg(&t.rowptr[r + 1]);
     const double *s0 = src + (int64_t)m * n_src;
-    for (int k = k0; k < k1; k++) {
-        const int c = __ldg(&t.col[k]);
-        const double ww = __ldg(&t.w[k]);
+    const int64_t lstride = (int64_t)M * n_src;
+    for (int kb = k0; kb < k1; kb += CH) {
+        int c[CH];
+        double w[CH];
 #pragma unroll
-        for (int d = 0; d < D; d++)
-            acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(s0 + c + (int64_t)d * M * n_src), ww));
+        for (int j = 0; j < CH; j++) {
+            const bool on = kb + j < k1;
+            c[j] = on ? __ldg(&t.col[kb + j]) : 0;
+            w[j] = on ? __ldg(&t.w[kb + j]) : 0.0;
+        }
+        double v[CH][D];
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            if (kb + j < k1) {
+                const double *p = s0 + c[j];
+#pragma unroll
+                for (int d = 0; d < D; d++) v[j][d] = __ldg(p + d * lstride);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            if (kb + j < k1) {
+#pragma unroll
+                for (int d = 0; d < D; d++) acc[d] = __dadd_rn(acc[d], __dmul_rn(v[j][d], w[j]));
+            }
+        }
     }
 }
 
-__global__ void __launch_bounds__(kThreads) sfc_exchange_kernel(const SfcArgs a)
+__global__ void __launch_bounds__(kThreads, 4) sfc_exchange_kernel(const SfcArgs a)
 {
     const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int64_t nS = a.nS;
@@ -69,10 +92,10 @@ __global__ void __launch_bounds__(kThreads) sfc_exchange_kernel(const SfcArgs a)
     const int M = a.M;
 
     double ab[13], ac[4], ob[2], oc[3];
-    gather<13>(a.as_bil, r, a.a2s_bil, a.nA, M, m, ab);
-    gather<4>(a.as_cons, r, a.a2s_cons, a.nA, M, m, ac);
-    gather<2>(a.os_bil, r, a.o2s_bil, a.nO, M, m, ob);
-    gather<3>(a.os_cons, r, a.o2s_cons, a.nO, M, m, oc);
+    gather<13, 2>(a.as_bil, r, a.a2s_bil, a.nA, M, m, ab);
+    gather<4, 4>(a.as_cons, r, a.a2s_cons, a.nA, M, m, ac);
+    gather<2, 4>(a.os_bil, r, a.o2s_bil, a.nO, M, m, ob);
+    gather<3, 4>(a.os_cons, r, a.o2s_cons, a.nO, M, m, oc);
 
     BulkIn in;
     in.WindU = ab[0]; in.WindV = ab[1]; in.SfcAirTemp = ab[2]; in.QVap1 = ab[3]; in.SfcPress = ab[4];

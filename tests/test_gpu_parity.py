@@ -319,7 +319,7 @@ def test_full_size_properties_T1279(gpu, dccm, S):
                                          ("T21_1deg", 26, True)])
 def test_exchange_step_vs_oracle(gpu, orc, dccm, S, name, K, fast):
     import torch
-    from exchange_ref import compare_exchange, oracle_exchange
+    from exchange_ref import compare_exchange, floor_rel, oracle_exchange
     X = importlib.import_module("dennou-ccm_b200.exchange")
     A, O, Sx = pair(orc, dccm, name)
     if O.im == 1:                                   # exchange needs bilinear O<->S tables too: fine for nx=1
@@ -335,9 +335,24 @@ def test_exchange_step_vs_oracle(gpu, orc, dccm, S, name, K, fast):
     detail = {}
     worst = compare_exchange(ex, ref, detail=detail)
     print(name, "fast" if fast else "reference-order", {k: float("%.2e" % v) for k, v in detail.items()})
-    # shared-reciprocal mode trades <= 3 ulp per operation; the coupling coefficients are
-    # differences of nearly equal terms, which amplifies that to a few 1e-12 downstream
-    assert worst <= (5e-12 if fast else RTOL), detail
+    # Conditioning: the Louis stability functions and the air-sea potential-temperature difference
+    # amplify a ONE-ulp change of an input to a few 1e-12 in the fluxes, so no implementation whose
+    # exp/log/pow differ from the reference's libm in the last ulp can meet 1e-12 in every cell.
+    # The bar per stage is therefore max(1e-12, 4 x the oracle's own response to 1-ulp input changes).
+    tol = {k: RTOL for k in detail}
+    for fld in ("SfcPress", "SfcAirTemp"):
+        atm2 = dict(atm)
+        atm2[fld] = atm[fld] * (1.0 + 2.0 ** -52)
+        ref2 = oracle_exchange(orc, S, A, O, Sx, K, 1, 1, tabs, col, atm2, ocn)
+        for k in ("s2a", "s2o", "a_recv", "o_recv"):
+            tol[k] = max(tol[k], 4.0 * floor_rel(ref2[k], ref[k]))
+        for k in ("DUDt", "DVDt", "DTempDt", "DQMixDt"):
+            tol["bwd_" + k] = max(tol["bwd_" + k], 4.0 * floor_rel(ref2["bwd"][k], ref["bwd"][k]))
+    for k in ("Coef1", "Coef2", "s_bil", "s_cons", "s_obil", "s_ocons"):      # no transcendental upstream
+        tol[k] = RTOL if fast else 0.0
+    over = {k: (detail[k], tol[k]) for k in detail if detail[k] > tol[k]}
+    assert not over, over
+    assert worst <= 1e-11
     # the fused surface kernel (remap + bulk flux + pack in registers) gives the same bits
     keep = {k: getattr(ex, k).clone() for k in ("s2a", "s2o", "a_recv", "o_recv")}
     keep.update({k: v.clone() for k, v in ex.tend.items()})
@@ -348,9 +363,6 @@ def test_exchange_step_vs_oracle(gpu, orc, dccm, S, name, K, fast):
         assert torch.equal(getattr(ex, k), keep[k]), k
     for k in ex.tend:
         assert torch.equal(ex.tend[k], keep[k]), k
-    if not fast:
-        # reference-order mode: everything up to the bulk flux is bit-exact
-        assert detail["Coef1"] == 0.0 and detail["Coef2"] == 0.0 and detail["s_bil"] == 0.0
     # global integrals of the conservatively remapped fluxes agree to the conservation bar
     wA = np.repeat(A.y_LatWt, A.im)
     got, want = ex.a_recv[:4].cpu().numpy(), ref["a_recv"][:4]
