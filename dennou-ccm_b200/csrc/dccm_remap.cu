@@ -37,7 +37,7 @@ remap_csr_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__
 {
     const int r = blockIdx.x * kThreads + threadIdx.x;
     if (r >= n_recv) return;
-    const int k0 = __ldg(&rowptr[r]), k1 = __ldg(&rowptr[r + 1]);
+    const int k0 = rowptr[r], k1 = rowptr[r + 1];
     const int d_begin = blockIdx.y * fields_per_y;
     const int d_end = min(nfield, d_begin + fields_per_y);
     for (int d0 = d_begin; d0 < d_end; d0 += FB) {
@@ -45,38 +45,29 @@ remap_csr_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__
 #pragma unroll
         for (int d = 0; d < FB; d++) acc[d] = 0.0;
         const double *s0 = send + (int64_t)d0 * sn1;
-        const int nf = min(FB, d_end - d0);
-        // (col, w) of CH operations are fetched before their dependent source loads are issued:
-        // CH*FB gathers in flight per thread; accumulation order stays the table order.
-        constexpr int CH = 2;
-        for (int kb = k0; kb < k1; kb += CH) {
-            int c[CH];
-            double ww[CH];
+        if (d0 + FB <= d_end) {
+            for (int k = k0; k < k1; k++) {
+                const int c = col[k];
+                const double ww = w[k];
 #pragma unroll
-            for (int j = 0; j < CH; j++) {
-                const bool on = kb + j < k1;
-                c[j] = on ? __ldg(&col[kb + j]) : 0;
-                ww[j] = on ? __ldg(&w[kb + j]) : 0.0;
+                for (int d = 0; d < FB; d++)
+                    acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(s0 + c + (int64_t)d * sn1), ww));
             }
-            double v[CH][FB];
 #pragma unroll
-            for (int j = 0; j < CH; j++)
-                if (kb + j < k1) {
+            for (int d = 0; d < FB; d++) recv[r + (int64_t)(d0 + d) * rn1] = acc[d];
+        } else {
+            const int nf = d_end - d0;
+            for (int k = k0; k < k1; k++) {
+                const int c = col[k];
+                const double ww = w[k];
 #pragma unroll
-                    for (int d = 0; d < FB; d++)
-                        if (d < nf) v[j][d] = __ldg(s0 + c[j] + (int64_t)d * sn1);
-                }
+                for (int d = 0; d < FB; d++)
+                    if (d < nf) acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(s0 + c + (int64_t)d * sn1), ww));
+            }
 #pragma unroll
-            for (int j = 0; j < CH; j++)
-                if (kb + j < k1) {
-#pragma unroll
-                    for (int d = 0; d < FB; d++)
-                        if (d < nf) acc[d] = __dadd_rn(acc[d], __dmul_rn(v[j][d], ww[j]));
-                }
+            for (int d = 0; d < FB; d++)
+                if (d < nf) recv[r + (int64_t)(d0 + d) * rn1] = acc[d];
         }
-#pragma unroll
-        for (int d = 0; d < FB; d++)
-            if (d < nf) recv[r + (int64_t)(d0 + d) * rn1] = acc[d];
     }
 }
 
