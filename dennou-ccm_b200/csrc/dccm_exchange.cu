@@ -174,14 +174,14 @@ extern "C" int dccm_sfc_exchange_device(const dccm_remap *as_bil, const dccm_rem
     a.nA = nA; a.nO = nO; a.nS = nS; a.sld = s_ld ? s_ld : nS; a.M = members; a.sig1 = sig1;
     const int64_t n = (int64_t)nS * members;
     const unsigned grid = (unsigned)((n + kThreads - 1) / kThreads);
-    static const int minb = getenv("DCCM_SFC_MINB") ? atoi(getenv("DCCM_SFC_MINB")) : 4;   // tuning knob
+    static const int minb = getenv("DCCM_SFC_MINB") ? atoi(getenv("DCCM_SFC_MINB")) : 5;   // tuning knob (5 measured best on B200, profiles/)
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (minb) {
     case 3: sfc_exchange_kernel<3><<<grid, kThreads, 0, st>>>(a); break;
-    case 5: sfc_exchange_kernel<5><<<grid, kThreads, 0, st>>>(a); break;
     case 6: sfc_exchange_kernel<6><<<grid, kThreads, 0, st>>>(a); break;
     case 8: sfc_exchange_kernel<8><<<grid, kThreads, 0, st>>>(a); break;
-    default: sfc_exchange_kernel<4><<<grid, kThreads, 0, st>>>(a); break;
+    case 4: sfc_exchange_kernel<4><<<grid, kThreads, 0, st>>>(a); break;
+    default: sfc_exchange_kernel<5><<<grid, kThreads, 0, st>>>(a); break;
     }
     DCCM_CUDA_TRY(cudaGetLastError());
     return DCCM_OK;

@@ -1,0 +1,29 @@
+#!/bin/bash
+# Multi-GPU visit: gpurun --gpus N -- bash scripts/gpu_multi.sh <tag> <N>
+TAG=${1:-multi}; N=${2:-2}
+OUT=gpurun_out/$TAG; mkdir -p $OUT
+nvidia-smi --query-gpu=index,name --format=csv > $OUT/gpus.txt 2>&1
+nvidia-smi topo -m > $OUT/topo.txt 2>&1
+( timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 \
+    tests/sharded_gpu_check.py T106_1deg ) > $OUT/check_T106.log 2>&1; echo "check T106 exit $?" | tee -a $OUT/check_T106.log
+( timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29612 \
+    tests/sharded_gpu_check.py T341_0p25deg ) > $OUT/check_T341.log 2>&1; echo "check T341 exit $?" | tee -a $OUT/check_T341.log
+grep "rank" $OUT/check_T106.log $OUT/check_T341.log | head -20
+n=1
+while [ $n -le $N ]; do
+  if [ $n -eq 1 ]; then
+    ( timeout 900 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu ) > $OUT/bench_n1.json 2> $OUT/bench_n1.err
+  else
+    ( timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29620+n)) \
+        bench.py --gpus $n --steps 10 --warmup 3 ) > $OUT/bench_n$n.json 2> $OUT/bench_n$n.err
+  fi
+  python - <<PY
+import json
+try:
+    d=[json.loads(l) for l in open('$OUT/bench_n$n.json') if l.startswith('{')][-1]
+    print('N=$n', round(d['value'],2), 'ex/s', round(d['ms_per_step'],3), 'ms', {k: round(v,3) for k,v in d['part_ms'].items()}, 'e2e', d.get('e2e',{}).get('value'))
+except Exception as e:
+    print('N=$n failed', e); print(open('$OUT/bench_n$n.err').read()[-1500:])
+PY
+  n=$((n*2))
+done
