@@ -163,24 +163,50 @@ class BandPlan:
                    for peer, kind, c0, c1 in self.halo_messages(g, rank) if kind == "recv")
 
 
-def exchange_halo(bufs_msgs, rank, dist):
-    """bufs_msgs: [(tensor (L, n_ext), msgs)].  One grouped batch of point-to-point transfers
-    (NCCL send/recv on GPUs, gloo on CPU tensors in the tests): boundary rows are packed, sent to
-    the neighbour and unpacked straight into the halo cells of the (layer-major) send buffer."""
-    ops, unpack = [], []
-    for buf, msgs in bufs_msgs:
-        for peer, kind, c0, c1 in msgs:
+class HaloExchanger:
+    """Halo rows of several layer-major send buffers, exchanged with the two neighbouring ranks.
+
+    All layers of all buffers that go to one neighbour travel in ONE message (one staging tensor
+    per peer and direction, allocated once), so a phase is at most 2 sends + 2 receives grouped in
+    a single NCCL launch (gloo on CPU tensors in the tests), however many fields are coupled."""
+
+    def __init__(self, bufs_msgs, dist):
+        self.dist = dist
+        self.items = []                      # (peer, kind, staging, [(buf, c0, c1, offset)])
+        by = {}
+        for buf, msgs in bufs_msgs:
+            for peer, kind, c0, c1 in msgs:
+                by.setdefault((peer, kind), []).append((buf, c0, c1))
+        # lower neighbour first, sends and receives in the same order on both sides
+        for (peer, kind) in sorted(by, key=lambda k: (k[0], k[1] != "send")):
+            parts, n = [], 0
+            for buf, c0, c1 in by[(peer, kind)]:
+                parts.append((buf, c0, c1, n))
+                n += buf.shape[0] * (c1 - c0)
+            stage = parts[0][0].new_empty(n)
+            self.items.append((peer, kind, stage, parts))
+        self.ops = [dist.P2POp(dist.isend if kind == "send" else dist.irecv, stage, peer)
+                    for peer, kind, stage, parts in self.items] if dist is not None else []
+        self.nbytes_recv = sum(8 * st.numel() for peer, kind, st, parts in self.items if kind == "recv")
+
+    def __call__(self):
+        if not self.items:
+            return
+        for peer, kind, stage, parts in self.items:
             if kind == "send":
-                ops.append(dist.P2POp(dist.isend, buf[:, c0:c1].contiguous(), peer))
-            else:
-                tmp = buf.new_empty((buf.shape[0], c1 - c0))
-                ops.append(dist.P2POp(dist.irecv, tmp, peer))
-                unpack.append((buf, c0, c1, tmp))
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
+                for buf, c0, c1, o in parts:
+                    stage[o:o + buf.shape[0] * (c1 - c0)].view(buf.shape[0], c1 - c0).copy_(buf[:, c0:c1])
+        for req in self.dist.batch_isend_irecv(self.ops):
             req.wait()
-    for buf, c0, c1, tmp in unpack:
-        buf[:, c0:c1] = tmp
+        for peer, kind, stage, parts in self.items:
+            if kind == "recv":
+                for buf, c0, c1, o in parts:
+                    buf[:, c0:c1] = stage[o:o + buf.shape[0] * (c1 - c0)].view(buf.shape[0], c1 - c0)
+
+
+def exchange_halo(bufs_msgs, rank, dist):
+    """one-shot form of HaloExchanger (tests)"""
+    HaloExchanger(bufs_msgs, dist)()
 
 
 class ShardedExchange(SurfaceExchange):
@@ -192,15 +218,15 @@ class ShardedExchange(SurfaceExchange):
         lA, lO, lS = self.plan.local_grids(rank)
         super().__init__(lA, lO, lS, kmax, ncmax, index_h2ovap, tabs=self.plan.local_tables(rank),
                          layout=self.plan.layout(rank), **kw)
-        self.msgA = self.plan.halo_messages("A", rank)
-        self.msgO = self.plan.halo_messages("O", rank)
-        self.msgS = self.plan.halo_messages("S", rank)
+        mA, mO, mS = (self.plan.halo_messages(g, rank) for g in ("A", "O", "S"))
+        self.halo_in = HaloExchanger([(self.a2s_bil, mA), (self.a2s_cons, mA),
+                                      (self.o2s_bil, mO), (self.o2s_cons, mO)], dist)
+        self.halo_out = HaloExchanger([(self.s2a, mS), (self.s2o, mS)], dist)
 
     def halo_to_sfc(self):
         if self.world > 1:
-            exchange_halo([(self.a2s_bil, self.msgA), (self.a2s_cons, self.msgA),
-                           (self.o2s_bil, self.msgO), (self.o2s_cons, self.msgO)], self.rank, self.dist)
+            self.halo_in()
 
     def halo_from_sfc(self):
         if self.world > 1:
-            exchange_halo([(self.s2a, self.msgS), (self.s2o, self.msgS)], self.rank, self.dist)
+            self.halo_out()
