@@ -399,9 +399,16 @@ def run_ours(args, rank, world):
         except Exception as e:           # the baseline must never take the GPU number down
             line["cpu_baseline"] = {"error": repr(e)}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear down without dist.destroy_process_group(): with NCCL work captured in a CUDA graph the
+        # communicator teardown can block forever.  Drain, meet at a barrier, then leave.
+        del graph, run_step
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def run_e2e(torch, ex, col_in, atm_sfc, ocn_sfc, args):

@@ -4,17 +4,17 @@ TAG=${1:-multi}; N=${2:-2}
 OUT=gpurun_out/$TAG; mkdir -p $OUT
 nvidia-smi --query-gpu=index,name --format=csv > $OUT/gpus.txt 2>&1
 nvidia-smi topo -m > $OUT/topo.txt 2>&1
-( timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 \
+( timeout -k 5 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 \
     tests/sharded_gpu_check.py T106_1deg ) > $OUT/check_T106.log 2>&1; echo "check T106 exit $?" | tee -a $OUT/check_T106.log
-( timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29612 \
+( timeout -k 5 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29612 \
     tests/sharded_gpu_check.py T341_0p25deg ) > $OUT/check_T341.log 2>&1; echo "check T341 exit $?" | tee -a $OUT/check_T341.log
 grep "rank" $OUT/check_T106.log $OUT/check_T341.log | head -20
-n=1
+n=${3:-1}
 while [ $n -le $N ]; do
   if [ $n -eq 1 ]; then
-    ( timeout 900 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu ) > $OUT/bench_n1.json 2> $OUT/bench_n1.err
+    ( timeout -k 5 300 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu ) > $OUT/bench_n1.json 2> $OUT/bench_n1.err
   else
-    ( timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29620+n)) \
+    ( timeout -k 5 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29620+n)) \
         bench.py --gpus $n --steps 10 --warmup 3 ) > $OUT/bench_n$n.json 2> $OUT/bench_n$n.err
   fi
   python - <<PY
