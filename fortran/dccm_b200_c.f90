@@ -1,0 +1,101 @@
+!> ISO_C_BINDING interfaces of libdccm_b200.so (include/dccm_b200.h).
+!! Source-only deliverable: there is no Fortran compiler in the build image; the C side of
+!! every entry point below is exercised by tests/ through the same ABI.
+module dccm_b200_c
+  use iso_c_binding
+  implicit none
+  public
+
+  interface
+     function dccm_init(device) bind(C, name="dccm_init") result(rc)
+       import; integer(c_int), value :: device; integer(c_int) :: rc
+     end function
+     function dccm_last_error() bind(C, name="dccm_last_error") result(msg)
+       import; type(c_ptr) :: msg
+     end function
+     function dccm_remap_create(nops, send_index, recv_index, coef, n_send, n_recv, handle) &
+          & bind(C, name="dccm_remap_create") result(rc)
+       import
+       integer(c_int64_t), value :: nops
+       integer(c_int32_t), intent(in) :: send_index(*), recv_index(*)
+       real(c_double), intent(in) :: coef(*)
+       integer(c_int), value :: n_send, n_recv
+       type(c_ptr), intent(out) :: handle
+       integer(c_int) :: rc
+     end function
+     function dccm_interp_register(recv_model, send_model, mapping_tag, handle) &
+          & bind(C, name="dccm_interp_register") result(rc)
+       import; integer(c_int), value :: recv_model, send_model, mapping_tag
+       type(c_ptr), value :: handle; integer(c_int) :: rc
+     end function
+     function dccm_interpolate_data(recv_model, send_model, mapping_tag, sn1, sn2, send_data, &
+          & rn1, rn2, recv_data, num_of_data) bind(C, name="dccm_interpolate_data") result(rc)
+       import
+       integer(c_int), value :: recv_model, send_model, mapping_tag, sn1, sn2, rn1, rn2, num_of_data
+       real(c_double), intent(in) :: send_data(sn1, *)
+       real(c_double), intent(inout) :: recv_data(rn1, *)
+       integer(c_int) :: rc
+     end function
+     function dccm_bulkflux_get_host(IA, JA, &
+          & WindStressX, WindStressY, SenHFlx, QVapMFlx, LatHFlx, &
+          & SfcVelTransCoef, SfcTempTransCoef, SfcQVapTransCoef, DelVarImplCPL, &
+          & SUwRFlx, LUwRFlx, SfcHFlx_ns, SfcHFlx_sr, DSfcHFlxDTs, &
+          & WindU, WindV, SfcAirTemp, QVap1, SDwRFlx, LDwRFlx, ImplCplCoef1, ImplCplCoef2, &
+          & SfcTemp, SfcAlbedo, SIceCon, Sig1Info, SfcHeight, SfcPress) &
+          & bind(C, name="dccm_bulkflux_get_host") result(rc)
+       import
+       integer(c_int), value :: IA, JA
+       real(c_double) :: WindStressX(*), WindStressY(*), SenHFlx(*), QVapMFlx(*), LatHFlx(*)
+       real(c_double) :: SfcVelTransCoef(*), SfcTempTransCoef(*), SfcQVapTransCoef(*), DelVarImplCPL(*)
+       real(c_double) :: SUwRFlx(*), LUwRFlx(*), SfcHFlx_ns(*), SfcHFlx_sr(*), DSfcHFlxDTs(*)
+       real(c_double), intent(in) :: WindU(*), WindV(*), SfcAirTemp(*), QVap1(*), SDwRFlx(*), LDwRFlx(*)
+       real(c_double), intent(in) :: ImplCplCoef1(*), ImplCplCoef2(*)
+       real(c_double) :: SfcTemp(*), SfcAlbedo(*)
+       real(c_double), intent(in) :: SIceCon(*), Sig1Info(2), SfcHeight(*), SfcPress(*)
+       integer(c_int) :: rc
+     end function
+     function dccm_vdiff_create(imax, jmax, kmax, ncmax, index_h2ovap, Grav, CpDry, GasRDry, DelTime, handle) &
+          & bind(C, name="dccm_vdiff_create") result(rc)
+       import
+       integer(c_int), value :: imax, jmax, kmax, ncmax, index_h2ovap
+       real(c_double), value :: Grav, CpDry, GasRDry, DelTime
+       type(c_ptr), intent(out) :: handle
+       integer(c_int) :: rc
+     end function
+     function dccm_vdiff_forward_host(handle, MomFluxX, MomFluxY, HeatFlux, QMixFlux, Press, zExner, rExner, &
+          & VirTemp, Height, VelDiffCoef, TempDiffCoef, QMixDiffCoef, DUDt, DVDt, DTempDt, DQMixDt, &
+          & ImplCplCoef1, ImplCplCoef2) bind(C, name="dccm_vdiff_forward_host") result(rc)
+       import
+       type(c_ptr), value :: handle
+       real(c_double), intent(in) :: MomFluxX(*), MomFluxY(*), HeatFlux(*), QMixFlux(*), Press(*), zExner(*), rExner(*)
+       real(c_double), intent(in) :: VirTemp(*), Height(*), VelDiffCoef(*), TempDiffCoef(*), QMixDiffCoef(*)
+       real(c_double) :: DUDt(*), DVDt(*), DTempDt(*), DQMixDt(*), ImplCplCoef1(*), ImplCplCoef2(*)
+       integer(c_int) :: rc
+     end function
+     function dccm_vdiff_backward_host(handle, DUDt, DVDt, DTempDt, DQMixDt) &
+          & bind(C, name="dccm_vdiff_backward_host") result(rc)
+       import
+       type(c_ptr), value :: handle
+       real(c_double) :: DUDt(*), DVDt(*), DTempDt(*), DQMixDt(*)
+       integer(c_int) :: rc
+     end function
+  end interface
+
+contains
+
+  !> abort through the caller's error channel with the library's message (the reference aborts
+  !! through jcup_error / MessageNotify('E', ...))
+  subroutine dccm_check(rc, where)
+    integer(c_int), intent(in) :: rc
+    character(*), intent(in) :: where
+    character(kind=c_char), pointer :: msg(:)
+    integer :: n
+    if (rc == 0) return
+    call c_f_pointer(dccm_last_error(), msg, (/ 1024 /))
+    n = 1
+    do while (n < 1024 .and. msg(n) /= c_null_char); n = n + 1; end do
+    write(0,*) trim(where), ": libdccm_b200 error ", rc, ": ", msg(1:n-1)
+    stop 1
+  end subroutine dccm_check
+
+end module dccm_b200_c
