@@ -74,6 +74,10 @@ _SIGS = {
     "dccm_table_index": (C.c_int, [vp, C.c_int, C.c_int, i32p, i32p, f64p]),
     "dccm_table_free": (None, [vp]),
     "dccm_remap_create": (C.c_int, [C.c_int64, i32p, i32p, f64p, C.c_int, C.c_int, C.POINTER(vp)]),
+    "dccm_remap_create_lonlat": (C.c_int, [C.c_int64, i32p, i32p, f64p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.POINTER(vp)]),
+    "dccm_remap_classify": (C.c_int, [C.c_int64, i32p, i32p, f64p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "dccm_remap_destroy": (None, [vp]),
     "dccm_remap_nnz": (C.c_int64, [vp]),
     "dccm_remap_kind": (C.c_int, [vp]),

@@ -26,9 +26,10 @@ namespace {
 
 constexpr int kThreads = 128;
 
-struct Csr {
+struct Csr {                       // one table: CSR (kind 0) or zonal stencil (kind 1)
     const int32_t *rowptr, *col;
     const double *w;
+    int kind, nxs, nxd;
 };
 
 struct SfcArgs {
@@ -51,9 +52,23 @@ __device__ __forceinline__ void gather(const Csr &t, int r, const double *__rest
 {
 #pragma unroll
     for (int d = 0; d < D; d++) acc[d] = 0.0;
-    const int k0 = __ldg(&t.rowptr[r]), k1 = __ldg(&t.rowptr[r + 1]);
     const double *s0 = src + (int64_t)m * n_src;
     const int64_t lstride = (int64_t)M * n_src;
+    if (t.kind == 1) {
+        // zonal stencil: rowptr = per-latitude-row pointer, col = interleaved (di, jS) pairs
+        const int jD = r / t.nxd, iD = r - jD * t.nxd;
+        const int e0 = __ldg(&t.rowptr[jD]), e1 = __ldg(&t.rowptr[jD + 1]);
+        for (int e = e0; e < e1; e++) {
+            int i = iD + __ldg(&t.col[2 * e]);
+            if (i >= t.nxs) i -= t.nxs;
+            const double *p = s0 + (int64_t)__ldg(&t.col[2 * e + 1]) * t.nxs + i;
+            const double ww = __ldg(&t.w[e]);
+#pragma unroll
+            for (int d = 0; d < D; d++) acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(p + d * lstride), ww));
+        }
+        return;
+    }
+    const int k0 = __ldg(&t.rowptr[r]), k1 = __ldg(&t.rowptr[r + 1]);
     for (int kb = k0; kb < k1; kb += CH) {
         int c[CH];
         double w[CH];
@@ -145,7 +160,11 @@ __global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_kernel(const SfcA
     }
 }
 
-Csr csr_of(const dccm_remap *h) { return Csr{h->d_rowptr, h->d_col, h->d_w}; }
+Csr csr_of(const dccm_remap *h)
+{
+    if (h->kind == 1) return Csr{h->d_zptr, h->d_zdj, h->d_zw, 1, h->nxs, h->nxd};
+    return Csr{h->d_rowptr, h->d_col, h->d_w, 0, 0, 0};
+}
 
 }  // namespace
 

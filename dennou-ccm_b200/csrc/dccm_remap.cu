@@ -71,21 +71,95 @@ remap_csr_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__
     }
 }
 
+// kind 1: zonal stencil, one thread per destination cell, no per-cell table reads.
+template <int FB>
+__global__ void __launch_bounds__(kThreads)
+remap_zonal_kernel(const int32_t *__restrict__ zptr, const int32_t *__restrict__ zdj,
+                   const double *__restrict__ zw, int nxs, int nxd,
+                   const double *__restrict__ send, int64_t sn1, double *__restrict__ recv, int64_t rn1,
+                   int n_recv, int nfield, int fields_per_y)
+{
+    const int r = blockIdx.x * kThreads + threadIdx.x;
+    if (r >= n_recv) return;
+    const int jD = r / nxd, iD = r - jD * nxd;
+    const int e0 = __ldg(&zptr[jD]), e1 = __ldg(&zptr[jD + 1]);
+    const int d_begin = blockIdx.y * fields_per_y;
+    const int d_end = min(nfield, d_begin + fields_per_y);
+    for (int d0 = d_begin; d0 < d_end; d0 += FB) {
+        double acc[FB];
+#pragma unroll
+        for (int d = 0; d < FB; d++) acc[d] = 0.0;
+        const double *s0 = send + (int64_t)d0 * sn1;
+        const int nf = min(FB, d_end - d0);
+        for (int e = e0; e < e1; e++) {
+            int i = iD + __ldg(&zdj[2 * e]);
+            if (i >= nxs) i -= nxs;
+            const int64_t c = (int64_t)__ldg(&zdj[2 * e + 1]) * nxs + i;
+            const double ww = __ldg(&zw[e]);
+            if (nf == FB) {
+#pragma unroll
+                for (int d = 0; d < FB; d++)
+                    acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(s0 + c + (int64_t)d * sn1), ww));
+            } else {
+#pragma unroll
+                for (int d = 0; d < FB; d++)
+                    if (d < nf) acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(s0 + c + (int64_t)d * sn1), ww));
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < FB; d++)
+            if (d < nf) recv[r + (int64_t)(d0 + d) * rn1] = acc[d];
+    }
+}
+
+// Is the (row-sorted) table a zonal stencil on an (nxs x .) -> (nxd x nyd) grid pair?  Exact test:
+// every row of a destination latitude must repeat row iD = 0 shifted in longitude, weights bitwise.
+bool detect_zonal(const std::vector<int32_t> &rowptr, const std::vector<int32_t> &col, const std::vector<double> &w,
+                  int nxs, int nxd, int nyd, std::vector<int32_t> &zptr, std::vector<int32_t> &zdi,
+                  std::vector<int32_t> &zjs, std::vector<double> &zw)
+{
+    if (!(nxs == nxd || nxs == 1) || nxd < 2) return false;
+    zptr.assign(nyd + 1, 0);
+    zdi.clear(); zjs.clear(); zw.clear();
+    for (int jD = 0; jD < nyd; jD++) {
+        const int r0 = jD * nxd;
+        const int k0 = rowptr[r0], n = rowptr[r0 + 1] - k0;
+        if (n > 64) return false;
+        for (int k = 0; k < n; k++) {
+            zdi.push_back(col[k0 + k] % nxs);
+            zjs.push_back(col[k0 + k] / nxs);
+            zw.push_back(w[k0 + k]);
+        }
+        zptr[jD + 1] = (int32_t)zdi.size();
+        const int32_t *di = zdi.data() + zptr[jD], *js = zjs.data() + zptr[jD];
+        const double *ww = zw.data() + zptr[jD];
+        for (int iD = 1; iD < nxd; iD++) {
+            const int k1 = rowptr[r0 + iD];
+            if (rowptr[r0 + iD + 1] - k1 != n) return false;
+            for (int k = 0; k < n; k++) {
+                int i = iD + di[k];
+                if (i >= nxs) i -= nxs;
+                if (nxs == 1) i = 0;
+                if (col[k1 + k] != js[k] * nxs + i) return false;
+                if (memcmp(&w[k1 + k], &ww[k], sizeof(double)) != 0) return false;
+            }
+        }
+    }
+    return true;
+}
+
 std::mutex g_reg_mutex;
 std::map<std::tuple<int, int, int>, dccm_remap *> g_registry;
 
 }  // namespace
 
-extern "C" int dccm_remap_create(int64_t nops, const int32_t *send_index, const int32_t *recv_index,
-                                 const double *coef, int n_send, int n_recv, dccm_remap **out)
+namespace {
+// COO (1-based, operation order) -> destination-row CSR by a stable counting sort: per-row order == table order
+int build_csr(int64_t nops, const int32_t *send_index, const int32_t *recv_index, const double *coef,
+              int n_send, int n_recv, std::vector<int32_t> &rowptr, std::vector<int32_t> &col,
+              std::vector<double> &w, int &maxnnz)
 {
-    *out = nullptr;
-    if (nops < 0 || n_send < 1 || n_recv < 1) return fail(DCCM_ERR_ARG, "dccm_remap_create: bad sizes");
-    if (nops >= INT32_MAX) return fail(DCCM_ERR_ARG, "dccm_remap_create: nops exceeds int32");
-    int rc = ensure_device();
-    if (rc) return rc;
-    // stable counting sort by destination row: per-row order == table order
-    std::vector<int32_t> rowptr((size_t)n_recv + 1, 0);
+    rowptr.assign((size_t)n_recv + 1, 0);
     for (int64_t i = 0; i < nops; i++) {
         int32_t r = recv_index[i], s = send_index[i];
         if (r < 1 || r > n_recv || s < 1 || s > n_send)
@@ -93,24 +167,86 @@ extern "C" int dccm_remap_create(int64_t nops, const int32_t *send_index, const 
                         (long long)i, s, n_send, r, n_recv);
         rowptr[r]++;
     }
-    int maxnnz = 0;
+    maxnnz = 0;
     for (int r = 0; r < n_recv; r++) {
         maxnnz = std::max(maxnnz, rowptr[r + 1]);
         rowptr[r + 1] += rowptr[r];
     }
-    std::vector<int32_t> col((size_t)nops);
-    std::vector<double> w((size_t)nops);
-    {
-        std::vector<int32_t> fill(rowptr.begin(), rowptr.end() - 1);
-        for (int64_t i = 0; i < nops; i++) {
-            int32_t p = fill[recv_index[i] - 1]++;
-            col[p] = send_index[i] - 1;
-            w[p] = coef[i];
-        }
+    col.resize((size_t)nops);
+    w.resize((size_t)nops);
+    std::vector<int32_t> fill(rowptr.begin(), rowptr.end() - 1);
+    for (int64_t i = 0; i < nops; i++) {
+        int32_t p = fill[recv_index[i] - 1]++;
+        col[p] = send_index[i] - 1;
+        w[p] = coef[i];
     }
+    return DCCM_OK;
+}
+}  // namespace
+
+// Host-only: which storage form would dccm_remap_create_lonlat pick (no GPU needed).
+extern "C" int dccm_remap_classify(int64_t nops, const int32_t *send_index, const int32_t *recv_index,
+                                   const double *coef, int n_send, int n_recv, int gnxs, int gnxr,
+                                   int *kind, int64_t *stored_entries)
+{
+    std::vector<int32_t> rowptr, col, zptr, zdi, zjs;
+    std::vector<double> w, zw;
+    int maxnnz = 0;
+    if (nops < 0 || n_send < 1 || n_recv < 1) return fail(DCCM_ERR_ARG, "dccm_remap_classify: bad sizes");
+    int rc = build_csr(nops, send_index, recv_index, coef, n_send, n_recv, rowptr, col, w, maxnnz);
+    if (rc) return rc;
+    *kind = 0; *stored_entries = nops;
+    if (gnxs > 0 && gnxr > 0 && n_send % gnxs == 0 && n_recv % gnxr == 0 && nops > 0 &&
+        detect_zonal(rowptr, col, w, gnxs, gnxr, n_recv / gnxr, zptr, zdi, zjs, zw)) {
+        *kind = 1; *stored_entries = (int64_t)zw.size();
+    }
+    return DCCM_OK;
+}
+
+extern "C" int dccm_remap_create(int64_t nops, const int32_t *send_index, const int32_t *recv_index,
+                                 const double *coef, int n_send, int n_recv, dccm_remap **out)
+{
+    return dccm_remap_create_lonlat(nops, send_index, recv_index, coef, n_send, n_recv, 0, 0, out);
+}
+
+extern "C" int dccm_remap_create_lonlat(int64_t nops, const int32_t *send_index, const int32_t *recv_index,
+                                        const double *coef, int n_send, int n_recv, int gnxs, int gnxr,
+                                        dccm_remap **out)
+{
+    *out = nullptr;
+    if (nops < 0 || n_send < 1 || n_recv < 1) return fail(DCCM_ERR_ARG, "dccm_remap_create: bad sizes");
+    if (nops >= INT32_MAX) return fail(DCCM_ERR_ARG, "dccm_remap_create: nops exceeds int32");
+    int rc = ensure_device();
+    if (rc) return rc;
+    std::vector<int32_t> rowptr, col;
+    std::vector<double> w;
+    int maxnnz = 0;
+    rc = build_csr(nops, send_index, recv_index, coef, n_send, n_recv, rowptr, col, w, maxnnz);
+    if (rc) return rc;
     dccm_remap *h = new dccm_remap();
     h->n_send = n_send; h->n_recv = n_recv; h->nnz = nops; h->max_row_nnz = maxnnz;
     cudaError_t e;
+    if (gnxs > 0 && gnxr > 0 && n_send % gnxs == 0 && n_recv % gnxr == 0 && nops > 0) {
+        std::vector<int32_t> zptr, zdi, zjs;
+        std::vector<double> zw;
+        if (detect_zonal(rowptr, col, w, gnxs, gnxr, n_recv / gnxr, zptr, zdi, zjs, zw)) {
+            h->kind = 1; h->nxs = gnxs; h->nxd = gnxr; h->nyd = n_recv / gnxr; h->znnz = (int64_t)zw.size();
+            std::vector<int32_t> zdj(2 * zdi.size());
+            for (size_t k = 0; k < zdi.size(); k++) { zdj[2 * k] = zdi[k]; zdj[2 * k + 1] = zjs[k]; }
+            e = cudaMalloc(&h->d_zptr, sizeof(int32_t) * zptr.size());
+            if (e == cudaSuccess) e = cudaMalloc(&h->d_zdj, sizeof(int32_t) * std::max<size_t>(2, zdj.size()));
+            if (e == cudaSuccess) e = cudaMalloc(&h->d_zw, sizeof(double) * std::max<size_t>(1, zw.size()));
+            if (e == cudaSuccess) e = cudaMemcpy(h->d_zptr, zptr.data(), sizeof(int32_t) * zptr.size(), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(h->d_zdj, zdj.data(), sizeof(int32_t) * zdj.size(), cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(h->d_zw, zw.data(), sizeof(double) * zw.size(), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) {
+                dccm_remap_destroy(h);
+                return fail(DCCM_ERR_CUDA, "dccm_remap_create: %s", cudaGetErrorString(e));
+            }
+            *out = h;
+            return DCCM_OK;
+        }
+    }
     e = cudaMalloc(&h->d_rowptr, sizeof(int32_t) * ((size_t)n_recv + 1));
     if (e == cudaSuccess) e = cudaMalloc(&h->d_col, sizeof(int32_t) * std::max<size_t>(1, (size_t)nops));
     if (e == cudaSuccess) e = cudaMalloc(&h->d_w, sizeof(double) * std::max<size_t>(1, (size_t)nops));
@@ -134,6 +270,7 @@ extern "C" void dccm_remap_destroy(dccm_remap *h)
             it = (it->second == h) ? g_registry.erase(it) : std::next(it);
     }
     cudaFree(h->d_rowptr); cudaFree(h->d_col); cudaFree(h->d_w);
+    cudaFree(h->d_zptr); cudaFree(h->d_zdj); cudaFree(h->d_zw);
     h->send_buf.release(); h->recv_buf.release();
     delete h;
 }
@@ -167,8 +304,12 @@ extern "C" int dccm_remap_apply_device(dccm_remap *h, const double *d_send, int 
     int fields_per_y = ((nfb + gy - 1) / gy) * FB;
     gy = (num_of_data + fields_per_y - 1) / fields_per_y;
     dim3 grid(gx, gy);
-    remap_csr_kernel<FB><<<grid, kThreads, 0, st>>>(h->d_rowptr, h->d_col, h->d_w, d_send, sn1, d_recv, rn1,
-                                                   h->n_recv, num_of_data, fields_per_y);
+    if (h->kind == 1)
+        remap_zonal_kernel<FB><<<grid, kThreads, 0, st>>>(h->d_zptr, h->d_zdj, h->d_zw, h->nxs, h->nxd,
+                                                         d_send, sn1, d_recv, rn1, h->n_recv, num_of_data, fields_per_y);
+    else
+        remap_csr_kernel<FB><<<grid, kThreads, 0, st>>>(h->d_rowptr, h->d_col, h->d_w, d_send, sn1, d_recv, rn1,
+                                                       h->n_recv, num_of_data, fields_per_y);
     DCCM_CUDA_TRY(cudaGetLastError());
     return DCCM_OK;
 }

@@ -53,7 +53,7 @@ class SurfaceExchange:
     """
 
     def __init__(self, A, O, S, kmax, ncmax=1, index_h2ovap=1, tabs=None, consts=None, members=1,
-                 fast=True, device=None, layout=None):
+                 fast=True, device=None, layout=None, structured=True):
         """layout (sharded runs, sharding.py): {"A"|"S"|"O": (n_own, n_ext, off)} -- cells this rank
         owns, cells of its source buffers (own + halo rows) and where the owned cells start in them;
         A/O/S are then objects with .im/.jm/.n of the LOCAL band."""
@@ -76,7 +76,9 @@ class SurfaceExchange:
         self.nnz = {}
         for key, (send_i, recv_i, coef) in tabs.items():
             s, d = key[0].upper(), key[1].upper()
-            self.ops[key] = RemapOperator(send_i, recv_i, coef, layout[s][1], layout[d][0])
+            gx = {"A": A.im, "S": S.im, "O": O.im}
+            self.ops[key] = RemapOperator(send_i, recv_i, coef, layout[s][1], layout[d][0],
+                                          gnxs=gx[s] if structured else 0, gnxr=gx[d] if structured else 0)
             self.nnz[key] = len(coef)
         nA, nS, nO, M = A.n, S.n, O.n, members
         nAx, nSx, nOx = layout["A"][1], layout["S"][1], layout["O"][1]
@@ -239,6 +241,8 @@ class SurfaceExchange:
 
         def remap(key, D, nsrc, ndst):
             return 12 * self.nnz[key] + 4 * (ndst + 1) + 8 * D * M * (nsrc + ndst)
+        # NOTE: the accounting keeps the CSR table bytes even for tables stored as zonal stencils
+        # (kind 1), so "algorithmic bytes" stay comparable across builds (SURVEY 8d formula).
 
         b = {}
         b["fwd"] = 8 * M * nA * ((9 + nc) * (K + 1) + 2 * K + 3 * K + (3 + nc) * K + 8)

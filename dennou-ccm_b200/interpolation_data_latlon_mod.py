@@ -18,14 +18,20 @@ _handles = {}            # (recv, send, tag) -> RemapOperator
 class RemapOperator:
     """One operation_index_type entry (ref :67-83) living on the device as row-sorted CSR."""
 
-    def __init__(self, send_index, recv_index, coef, n_send, n_recv):
+    def __init__(self, send_index, recv_index, coef, n_send, n_recv, gnxs=0, gnxr=0):
+        """gnxs / gnxr: longitudes per row of the source / destination grid (0 = unknown): lets the
+        library store a zonally repeating table as one stencil per latitude row (kind 1)."""
         send_index, recv_index, coef = L.i32(send_index), L.i32(recv_index), L.f64(coef)
         assert len(send_index) == len(recv_index) == len(coef)
         self.n_send, self.n_recv = int(n_send), int(n_recv)
         h = C.c_void_p()
-        L.check(L.lib().dccm_remap_create(len(coef), L.ip(send_index), L.ip(recv_index), L.dp(coef),
-                                          self.n_send, self.n_recv, C.byref(h)))
+        L.check(L.lib().dccm_remap_create_lonlat(len(coef), L.ip(send_index), L.ip(recv_index), L.dp(coef),
+                                                 self.n_send, self.n_recv, int(gnxs), int(gnxr), C.byref(h)))
         self._h = h
+
+    @property
+    def kind(self):
+        return int(L.lib().dccm_remap_kind(self._h))
 
     def __del__(self):
         if getattr(self, "_h", None):

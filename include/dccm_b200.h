@@ -100,9 +100,21 @@ typedef struct dccm_remap dccm_remap;
  * send/recv indices and coefS in operation (= table) order. */
 int dccm_remap_create(int64_t nops, const int32_t *send_index, const int32_t *recv_index,
                       const double *coef, int n_send, int n_recv, dccm_remap **out);
+/* Same, with the i-fastest row lengths of the two grids (GNXS, GNXR of set_mappingTable_interpCoef,
+ * ref common/grid_mapping_util_jones99.f90:446-462).  When every destination latitude row applies one
+ * longitude-shifted stencil -- true for all tables the reference generator produces -- the table is
+ * stored as that O(ny) stencil (dccm_remap_kind() == 1) instead of O(nx*ny) CSR.  Results are
+ * bit-identical either way; gnxs = gnxr = 0 skips the detection. */
+int dccm_remap_create_lonlat(int64_t nops, const int32_t *send_index, const int32_t *recv_index,
+                             const double *coef, int n_send, int n_recv, int gnxs, int gnxr,
+                             dccm_remap **out);
+/* host-only: the storage form dccm_remap_create_lonlat would choose (kind, entries kept) */
+int dccm_remap_classify(int64_t nops, const int32_t *send_index, const int32_t *recv_index,
+                        const double *coef, int n_send, int n_recv, int gnxs, int gnxr,
+                        int *kind, int64_t *stored_entries);
 void dccm_remap_destroy(dccm_remap *h);
 int64_t dccm_remap_nnz(const dccm_remap *h);
-/* 0 = general CSR, 1 = separable lat x lon stencil (tables compressed to O(I+J)) */
+/* 0 = general destination-row CSR, 1 = zonal stencil (one stencil per destination latitude row) */
 int dccm_remap_kind(const dccm_remap *h);
 /* recv_data(:,:) = 0 ; recv(r_i,d) += send(s_i,d)*coef(i), d = 1..num_of_data  (ref :293-302) */
 int dccm_remap_apply_host(dccm_remap *h, const double *send, int sn1, int sn2,

@@ -131,3 +131,39 @@ def test_no_cpu_fallback_without_gpu(dccm):
                                         *[z.copy() for _ in range(5)], *[np.zeros((5, 6)) for _ in range(6)],
                                         np.zeros((4, 5, 6)), np.zeros((4, 5, 6)), z.copy(), z.copy(),
                                         np.zeros((5, 6)), np.array([0.995, 0.01]), np.zeros((5, 6)), np.zeros((5, 6)))
+
+
+def test_zonal_stencil_detection_is_exact(dccm, orc):
+    """Every table the reference generator can produce (equal longitudes, or an axisymmetric source)
+    repeats one stencil along each destination latitude row; the library then keeps O(ny) entries
+    instead of O(nx*ny).  Detection is bitwise and host-only (dccm_remap_classify)."""
+    import ctypes as C
+    L = dccm._lib
+
+    def classify(tab, src, dst, hint=True):
+        s, r, c = tab.index(src.im, dst.im)
+        k, n = C.c_int(), C.c_int64()
+        L.check(L.lib().dccm_remap_classify(len(c), L.ip(s), L.ip(r), L.dp(c), src.n, dst.n,
+                                            src.im if hint else 0, dst.im if hint else 0, C.byref(k), C.byref(n)))
+        return k.value, n.value, len(c)
+
+    T = dccm.tables
+    A, O, S = pair(orc, dccm, "T106_1deg")
+    for tab, s, d in ((T.gen_table_jones99(A, S, 2), A, S), (T.gen_table_bilinear(A, S), A, S),
+                      (T.gen_table_jones99(S, A, 1), S, A), (T.gen_table_bilinear(S, A), S, A)):
+        kind, kept, nnz = classify(tab, s, d)
+        assert kind == 1 and kept * d.im == nnz
+        assert classify(tab, s, d, hint=False)[0] == 0          # no grid hint -> general CSR
+    # mismatched longitudes (320 vs 360): not shift invariant -> CSR
+    assert classify(T.gen_table_jones99(O, S, 1, 1), O, S)[0] == 0
+    assert classify(T.gen_table_bilinear(S, O, 1), S, O)[0] == 0
+    # axisymmetric source (shipped Pl42 ocean): zonal; axisymmetric destination: one long row -> CSR
+    A, O, S = pair(orc, dccm, "T21_Pl42")
+    assert classify(T.gen_table_jones99(O, S, 1), O, S)[0] == 1
+    assert classify(T.gen_table_jones99(S, O, 1), S, O)[0] == 0
+    # a single perturbed weight breaks the pattern and must be noticed
+    s, r, c = T.gen_table_jones99(S, A, 1).index(S.im, A.im)
+    c2 = c.copy(); c2[len(c2) // 2] = np.nextafter(c2[len(c2) // 2], 2.0)
+    k, n = C.c_int(), C.c_int64()
+    L.check(L.lib().dccm_remap_classify(len(c2), L.ip(s), L.ip(r), L.dp(c2), S.n, A.n, S.im, A.im, C.byref(k), C.byref(n)))
+    assert k.value == 0

@@ -55,6 +55,22 @@ def test_remap_bit_exact_vs_oracle(gpu, orc, dccm, S, name):
         assert np.abs((got * w).sum(1) / (ref * w).sum(1) - 1.0).max() <= CONS
 
 
+@pytest.mark.parametrize("name", ["T21_Pl42", "T42_T42", "T106_1deg"])
+def test_remap_zonal_stencil_form_bit_exact(gpu, orc, dccm, S, name):
+    """Given the grids' row lengths the library stores zonally repeating tables as one stencil per
+    latitude row (kind 1); results are the same bits as the CSR form and the oracle."""
+    kinds = []
+    for label, s, d, tab in _tables(orc, dccm, name):
+        send_i, recv_i, coef = tab.index(s.im, d.im)
+        op = dccm.RemapOperator(send_i, recv_i, coef, s.n, d.n, gnxs=s.im, gnxr=d.im)
+        kinds.append(op.kind)
+        x = S.generic_fields(np, s, 11)
+        got = op.apply_host(x, rn2=13, num_of_data=11)
+        ref = orc.remap_apply(send_i, recv_i, coef, x, d.n, 13, 11)
+        assert np.array_equal(got, ref), f"{name} {label} kind {op.kind}"
+    assert 1 in kinds, kinds
+
+
 @pytest.mark.parametrize("D", [1, 5, 8, 17, 43])
 def test_remap_field_counts_and_zero_fill(gpu, orc, dccm, S, D):
     """recv_data(:,:) = 0 covers ALL rn2 columns and rows beyond the table
