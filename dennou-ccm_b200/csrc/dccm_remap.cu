@@ -113,7 +113,7 @@ remap_zonal_kernel(const int32_t *__restrict__ zptr, const int32_t *__restrict__
 }
 
 // Is the (row-sorted) table a zonal stencil on an (nxs x .) -> (nxd x nyd) grid pair?  Exact test:
-// every row of a destination latitude must repeat row iD = 0 shifted in longitude, weights bitwise.
+// every row of a destination latitude must repeat row iD = 0 shifted in longitude with equal weights.
 bool detect_zonal(const std::vector<int32_t> &rowptr, const std::vector<int32_t> &col, const std::vector<double> &w,
                   int nxs, int nxd, int nyd, std::vector<int32_t> &zptr, std::vector<int32_t> &zdi,
                   std::vector<int32_t> &zjs, std::vector<double> &zw)
@@ -141,7 +141,9 @@ bool detect_zonal(const std::vector<int32_t> &rowptr, const std::vector<int32_t>
                 if (i >= nxs) i -= nxs;
                 if (nxs == 1) i = 0;
                 if (col[k1 + k] != js[k] * nxs + i) return false;
-                if (memcmp(&w[k1 + k], &ww[k], sizeof(double)) != 0) return false;
+                // value equality: +0.0 and -0.0 weights are interchangeable (acc starts at +0.0 and
+                // x + (+-0) == x), anything else must match exactly; NaN never matches
+                if (!(w[k1 + k] == ww[k])) return false;
             }
         }
     }
