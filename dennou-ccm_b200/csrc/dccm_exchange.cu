@@ -61,6 +61,7 @@ __device__ __forceinline__ void gather(const Csr &t, int r, const double *__rest
         for (int e = e0; e < e1; e++) {
             int i = iD + __ldg(&t.col[2 * e]);
             if (i >= t.nxs) i -= t.nxs;
+            if (t.nxs == 1) i = 0;                   // axisymmetric source
             const double *p = s0 + (int64_t)__ldg(&t.col[2 * e + 1]) * t.nxs + i;
             const double ww = __ldg(&t.w[e]);
 #pragma unroll

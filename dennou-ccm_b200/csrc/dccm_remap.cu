@@ -94,6 +94,7 @@ remap_zonal_kernel(const int32_t *__restrict__ zptr, const int32_t *__restrict__
         for (int e = e0; e < e1; e++) {
             int i = iD + __ldg(&zdj[2 * e]);
             if (i >= nxs) i -= nxs;
+            if (nxs == 1) i = 0;                     // axisymmetric source: every longitude reads column 1
             const int64_t c = (int64_t)__ldg(&zdj[2 * e + 1]) * nxs + i;
             const double ww = __ldg(&zw[e]);
             if (nf == FB) {
