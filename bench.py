@@ -393,6 +393,11 @@ def run_ours(args, rank, world):
 
     if not args.no_e2e:
         line["e2e"] = run_e2e(torch, ex, col_in, atm_sfc, ocn_sfc, args)
+        if world == 1 and M == 1 and not args.no_dropin:
+            try:
+                line["e2e_dropin"] = run_e2e_dropin(torch, dccm, ex, A, O, S, K, nc, col_in, atm_sfc, ocn_sfc)
+            except Exception as e:
+                line["e2e_dropin"] = {"error": repr(e)}
     if not args.no_cpu and rank == 0 and world == 1:
         try:
             line["cpu_baseline"] = cpu_baseline(dccm, wl)
@@ -459,6 +464,101 @@ def run_e2e(torch, ex, col_in, atm_sfc, ocn_sfc, args):
             "note": "pinned host buffers, H2D of all column/surface inputs and D2H of tendencies + remapped fields inside the timed region"}
 
 
+def run_e2e_dropin(torch, dccm, ex, A, O, S, K, nc, col_in, atm_sfc, ocn_sfc, steps=2):
+    """The exchange through the UNCHANGED reference interfaces only, host arrays in and out of every
+    call, as a maintainer gets it by linking fortran/*.f90: VDiffForward (host) -> interpolate_data x4
+    -> unpack to (IA,JA) halo arrays -> DSFCM_Util_SfcBulkFlux_Get (host) -> pack -> interpolate_data x4
+    -> level-1 update -> VDiffBackward (host).  Host pack/unpack is numpy, like the reference glue."""
+    import ctypes as C
+    L = dccm._lib
+    lib = L.lib()
+    m = dccm.interpolation_data_latlon_mod
+    nA, nS, nO = A.n, S.n, O.n
+    ids = {"A": 1, "O": 2, "S": 3}
+    for key, op in ex.ops.items():            # operation_index(recv, send, tag): tag 1 bilinear, 2 conservative
+        L.check(lib.dccm_interp_register(ids[key[1].upper()], ids[key[0].upper()], 1 if key.endswith("bil") else 2, op._h))
+    pin = lambda *shape: torch.empty(shape, dtype=torch.float64, pin_memory=True)
+    hp = lambda t: t.numpy().ctypes.data_as(L.f64p)
+    h_in = {k: pin(*v.shape).copy_(v) for k, v in col_in.items()}
+    h_atm = {k: pin(nA).copy_(v[0]) for k, v in atm_sfc.items()}
+    h_ocn = {k: pin(nO).copy_(v[0]) for k, v in ocn_sfc.items()}
+    tend = {"DUDt": pin(K, nA), "DVDt": pin(K, nA), "DTempDt": pin(K, nA), "DQMixDt": pin(nc, K, nA)}
+    a2s_bil, a2s_cons, o2s_bil, o2s_cons = pin(13, nA), pin(4, nA), pin(2, nO), pin(3, nO)
+    s_bil, s_cons, s_obil, s_ocons = pin(13, nS), pin(4, nS), pin(2, nS), pin(3, nS)
+    s2a, s2o, a_recv, o_recv = pin(9, nS), pin(12, nS), pin(9, nA), pin(12, nO)
+    IA, JA = S.im + 2, S.jm + 2
+    names3 = dccm.dsfcm.OUT3
+    halo = {k: pin(3, JA, IA) for k in names3 + ["SfcTemp", "SfcAlbedo"]}
+    halo.update(DelVarImplCPL=pin(4, JA, IA), ImplCplCoef1=pin(4, JA, IA), ImplCplCoef2=pin(4, JA, IA))
+    for k in ("WindU", "WindV", "SfcAirTemp", "QVap1", "SDwRFlx", "LDwRFlx", "SIceCon", "SfcHeight", "SfcPress"):
+        halo[k] = pin(JA, IA)
+    for t in halo.values():
+        t.fill_(1.0)
+    halo["SfcHeight"].zero_()
+    sig = np.array([ex.sig1, 0.01])
+    I = (slice(1, -1), slice(1, -1))
+    unpack = lambda dst, src: dst[I].copy_(src.view(S.jm, S.im))                  # ref sfc/dccm_sfc_mod.f90:900-951
+    interior = lambda t, n: t[n][I].reshape(-1)                                  # ref :787-809
+
+    def interp(recv, send, tag, x, y):
+        L.check(lib.dccm_interpolate_data(ids[recv], ids[send], tag, x.shape[1], x.shape[0], hp(x),
+                                          y.shape[1], y.shape[0], hp(y), x.shape[0]))
+
+    def one():
+        vh = ex.vdiff._h
+        L.check(lib.dccm_vdiff_forward_host(vh, *[hp(h_in[k]) for k in dccm.dcpam_sfc_implicit_coupling_mod.IN_ORDER],
+                                            hp(tend["DUDt"]), hp(tend["DVDt"]), hp(tend["DTempDt"]), hp(tend["DQMixDt"]),
+                                            hp(a2s_bil[5:9]), hp(a2s_bil[9:13])))
+        for l, k in enumerate(("WindU", "WindV", "SfcAirTemp", "QVap1", "SfcPress")):
+            a2s_bil[l].copy_(h_atm[k])
+        for l, k in enumerate(("LDwRFlx", "SDwRFlx", "RainFall", "SnowFall")):
+            a2s_cons[l].copy_(h_atm[k])
+        o2s_bil[0].copy_(h_ocn["SfcTempO"]); o2s_bil[1].copy_(h_ocn["SfcTempI"])
+        o2s_cons[0].copy_(h_ocn["SIceCon"]); o2s_cons[1].copy_(h_ocn["SfcAlbedoO"]); o2s_cons[2].copy_(h_ocn["SfcAlbedoI"])
+        interp("S", "A", 1, a2s_bil, s_bil); interp("S", "A", 2, a2s_cons, s_cons)
+        interp("S", "O", 1, o2s_bil, s_obil); interp("S", "O", 2, o2s_cons, s_ocons)
+        for l, k in enumerate(("WindU", "WindV", "SfcAirTemp", "QVap1", "SfcPress")):
+            unpack(halo[k], s_bil[l])
+        for c in range(4):
+            unpack(halo["ImplCplCoef1"][c], s_bil[5 + c]); unpack(halo["ImplCplCoef2"][c], s_bil[9 + c])
+        unpack(halo["LDwRFlx"], s_cons[0]); unpack(halo["SDwRFlx"], s_cons[1])
+        unpack(halo["SfcTemp"][0], s_obil[0]); unpack(halo["SfcTemp"][1], s_obil[1])
+        unpack(halo["SIceCon"], s_ocons[0]); unpack(halo["SfcAlbedo"][0], s_ocons[1]); unpack(halo["SfcAlbedo"][1], s_ocons[2])
+        L.check(lib.dccm_bulkflux_get_host(IA, JA, *[hp(halo[k]) for k in names3[:8]], hp(halo["DelVarImplCPL"]),
+                                           *[hp(halo[k]) for k in names3[8:]],
+                                           *[hp(halo[k]) for k in ("WindU", "WindV", "SfcAirTemp", "QVap1", "SDwRFlx", "LDwRFlx",
+                                                                   "ImplCplCoef1", "ImplCplCoef2", "SfcTemp", "SfcAlbedo", "SIceCon")],
+                                           sig.ctypes.data_as(L.f64p), hp(halo["SfcHeight"]), hp(halo["SfcPress"])))
+        s2a[0].copy_(interior(halo["LUwRFlx"], 2)); s2a[1].copy_(interior(halo["SUwRFlx"], 2))
+        s2a[2].copy_(interior(halo["SenHFlx"], 2)); s2a[3].copy_(interior(halo["QVapMFlx"], 2))
+        s2a[4].copy_(interior(halo["SfcAlbedo"], 2))
+        for c in range(4):
+            s2a[5 + c].copy_(interior(halo["DelVarImplCPL"], c))
+        s2o[0].copy_(interior(halo["SfcHFlx_ns"], 0)); s2o[1].copy_(interior(halo["SfcHFlx_sr"], 0))
+        s2o[2].copy_(s_cons[3]); s2o[3].copy_(s_cons[2]); s2o[4].copy_(interior(halo["QVapMFlx"], 0))
+        torch.neg(interior(halo["WindStressX"], 2), out=s2o[5]); torch.neg(interior(halo["WindStressY"], 2), out=s2o[6])
+        s2o[7].copy_(interior(halo["SfcHFlx_ns"], 1)); s2o[8].copy_(interior(halo["SfcHFlx_sr"], 1))
+        s2o[9].copy_(interior(halo["QVapMFlx"], 1))
+        s2o[10].copy_(interior(halo["DSfcHFlxDTs"], 0)); s2o[11].copy_(interior(halo["DSfcHFlxDTs"], 1))
+        interp("A", "S", 2, s2a[:4], a_recv[:4]); interp("A", "S", 1, s2a[4:], a_recv[4:])
+        interp("O", "S", 2, s2o[:10], o_recv[:10]); interp("O", "S", 1, s2o[10:], o_recv[10:])
+        tend["DUDt"][0].copy_(a_recv[5]); tend["DVDt"][0].copy_(a_recv[6])                  # ref atm/dccm_atm_mod.f90:832-835
+        tend["DTempDt"][0].copy_(a_recv[7]); tend["DQMixDt"][0, 0].copy_(a_recv[8])
+        L.check(lib.dccm_vdiff_backward_host(vh, hp(tend["DUDt"]), hp(tend["DVDt"]), hp(tend["DTempDt"]), hp(tend["DQMixDt"])))
+
+    one()
+    # the drop-in path and the resident path must agree bit for bit on what the ocean receives
+    same = bool(torch.equal(o_recv, ex.o_recv.cpu())) and bool(torch.equal(tend["DTempDt"], ex.tend["DTempDt"].cpu()))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": 1.0 / dt, "unit": "exchanges/s", "ms_per_step": 1e3 * dt, "steps": steps,
+            "matches_resident_path_bitwise": same,
+            "note": "reference interfaces only (forward_host, interpolate_data x8, bulkflux_get_host, backward_host), "
+                    "pinned host arrays, every call copies its arguments in and out; host pack/unpack in numpy/torch-cpu"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -468,6 +568,7 @@ def main():
     ap.add_argument("--workload", default="T1279_0p1deg", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the reference-interface-only e2e leg")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of as a CUDA graph")
     ap.add_argument("--unfused", action="store_true", help="surface step as 4 remaps + bulk flux + pack")
     ap.add_argument("--reference-order", action="store_true", help="bit-exact column solves (IEEE divisions)")
