@@ -239,8 +239,17 @@ def run_ours(args, rank, world):
         if M > 1:
             raise SystemExit("ensemble workloads shard by member (replicas): run them with --gpus 1 per member block")
         sh = importlib.import_module("dennou-ccm_b200.sharding")
-        ex = sh.ShardedExchange(A, O, S, K, nc, 1, rank=rank, world=world, dist=dist,
-                                fast=not args.reference_order, device=dev)
+        ex, halo_mode = None, args.halo
+        if args.halo == "peer":
+            try:
+                ex = sh.PeerShardedExchange(A, O, S, K, nc, 1, rank=rank, world=world, dist=dist,
+                                            fast=not args.reference_order, device=dev)
+            except Exception as e:          # no peer access / symmetric memory: NCCL send/recv halo instead
+                sys.stderr.write(f"[bench] peer-memory halo unavailable ({e!r}); using NCCL send/recv\n")
+                halo_mode = "nccl"
+        if ex is None:
+            ex = sh.ShardedExchange(A, O, S, K, nc, 1, rank=rank, world=world, dist=dist,
+                                    fast=not args.reference_order, device=dev)
         (ja0, ja1), (jo0, jo1) = ex.plan.bands["A"][rank], ex.plan.bands["O"][rank]
     else:
         ex = exch_mod.SurfaceExchange(A, O, S, K, nc, 1, members=M, fast=not args.reference_order, device=dev)
@@ -384,8 +393,10 @@ def run_ours(args, rank, world):
         "clocks": clocks, "gpu_launches": launches,
     }
     if world > 1:
-        line["config"]["sharding"] = (f"{world} latitude bands (row blocks), halo rows via NCCL send/recv: "
-                                      f"{ex.plan.halo_bytes(rank, {'A': 17, 'O': 5, 'S': 21})} B received on rank {rank} per exchange")
+        how = ("read in place from the neighbours' buffers over NVLink peer memory inside the surface / remap kernels, "
+               "2 device barriers per exchange" if halo_mode == "peer" else "packed NCCL send/recv, one message per neighbour")
+        line["config"]["sharding"] = (f"{world} latitude bands (row blocks); halo rows {how}; "
+                                      f"{ex.plan.halo_bytes(rank, {'A': 17, 'O': 5, 'S': 21})} B of halo on rank {rank} per exchange")
         line["roofline"]["note"] = "per-rank kernel on rank 0's band; achieved = rank-0 bytes / rank-0 time"
         line["roofline"]["achieved"] = ex.algorithmic_bytes()["fwd"] / (part_ms["fwd"] * 1e-3) / 1e9
         line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
@@ -569,6 +580,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-dropin", action="store_true", help="skip the reference-interface-only e2e leg")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="multi-GPU halo: peer-memory reads or NCCL send/recv")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of as a CUDA graph")
     ap.add_argument("--unfused", action="store_true", help="surface step as 4 remaps + bulk flux + pack")
     ap.add_argument("--reference-order", action="store_true", help="bit-exact column solves (IEEE divisions)")

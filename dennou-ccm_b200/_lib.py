@@ -33,6 +33,11 @@ class SfcFields(C.Structure):
     _fields_ = [(n, vp) for n in _names]
 
 
+class SrcSeg(C.Structure):
+    """dccm_src_seg: a send buffer whose boundary rows live in the neighbouring ranks' buffers."""
+    _fields_ = [("lo", vp), ("own", vp), ("hi", vp), ("b0", C.c_int64), ("b1", C.c_int64)]
+
+
 def build(force=False, verbose=False):
     """Compile libdccm_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
@@ -83,6 +88,7 @@ _SIGS = {
     "dccm_remap_kind": (C.c_int, [vp]),
     "dccm_remap_apply_host": (C.c_int, [vp, f64p, C.c_int, C.c_int, f64p, C.c_int, C.c_int, C.c_int]),
     "dccm_remap_apply_device": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
+    "dccm_remap_apply_seg_device": (C.c_int, [vp, C.POINTER(SrcSeg), C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
     "dccm_interp_register": (C.c_int, [C.c_int, C.c_int, C.c_int, vp]),
     "dccm_interpolate_data": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f64p,
                                         C.c_int, C.c_int, f64p, C.c_int]),
@@ -91,6 +97,8 @@ _SIGS = {
                                        C.POINTER(SfcFields), C.c_double, vp]),
     "dccm_sfc_exchange_device": (C.c_int, [vp] * 4 + [vp] * 4 + [C.c_int, C.c_double, vp, vp, C.c_int64,
                                            C.POINTER(SfcFields), vp]),
+    "dccm_sfc_exchange_seg_device": (C.c_int, [vp] * 4 + [C.POINTER(SrcSeg)] * 4 + [C.c_int64, C.c_int64, C.c_int, C.c_double,
+                                               vp, vp, C.c_int64, C.POINTER(SfcFields), vp]),
     "dccm_vdiff_create": (C.c_int, [C.c_int] * 5 + [C.c_double] * 4 + [C.POINTER(vp)]),
     "dccm_vdiff_destroy": (None, [vp]),
     "dccm_vdiff_set_mode": (C.c_int, [vp, C.c_int]),

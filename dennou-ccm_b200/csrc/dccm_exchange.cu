@@ -34,7 +34,7 @@ struct Csr {                       // one table: CSR (kind 0) or zonal stencil (
 
 struct SfcArgs {
     Csr as_bil, as_cons, os_bil, os_cons;
-    const double *a2s_bil, *a2s_cons, *o2s_bil, *o2s_cons;   // (13M, nA) (4M, nA) (2M, nO) (3M, nO)
+    SrcSeg a2s_bil, a2s_cons, o2s_bil, o2s_cons;             // (13M, nA) (4M, nA) (2M, nO) (3M, nO)
     double *s2a, *s2o;                                        // (9M, nS) (12M, nS)
     dccm_sfc_fields full;                                     // optional API-complete outputs, slot stride M*nS
     int has_full;
@@ -47,12 +47,12 @@ struct SfcArgs {
 // time BEFORE any of the dependent source loads is issued, so a thread has up to CH*D gathers in
 // flight instead of D (rows of these tables hold 1-4 entries); accumulation stays in table order.
 template <int D, int CH>
-__device__ __forceinline__ void gather(const Csr &t, int r, const double *__restrict__ src, int64_t n_src,
+__device__ __forceinline__ void gather(const Csr &t, int r, const SrcSeg &src, int64_t n_src,
                                        int M, int m, double (&acc)[D])
 {
 #pragma unroll
     for (int d = 0; d < D; d++) acc[d] = 0.0;
-    const double *s0 = src + (int64_t)m * n_src;
+    const int64_t o0 = (int64_t)m * n_src;
     const int64_t lstride = (int64_t)M * n_src;
     if (t.kind == 1) {
         // zonal stencil: rowptr = per-latitude-row pointer, col = interleaved (di, jS) pairs
@@ -62,7 +62,7 @@ __device__ __forceinline__ void gather(const Csr &t, int r, const double *__rest
             int i = iD + __ldg(&t.col[2 * e]);
             if (i >= t.nxs) i -= t.nxs;
             if (t.nxs == 1) i = 0;                   // axisymmetric source
-            const double *p = s0 + (int64_t)__ldg(&t.col[2 * e + 1]) * t.nxs + i;
+            const double *p = src.at((int64_t)__ldg(&t.col[2 * e + 1]) * t.nxs + i) + o0;
             const double ww = __ldg(&t.w[e]);
 #pragma unroll
             for (int d = 0; d < D; d++) acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(p + d * lstride), ww));
@@ -83,7 +83,7 @@ __device__ __forceinline__ void gather(const Csr &t, int r, const double *__rest
 #pragma unroll
         for (int j = 0; j < CH; j++) {
             if (kb + j < k1) {
-                const double *p = s0 + c[j];
+                const double *p = src.at(c[j]) + o0;
 #pragma unroll
                 for (int d = 0; d < D; d++) v[j][d] = __ldg(p + d * lstride);
             }
@@ -176,6 +176,23 @@ extern "C" int dccm_sfc_exchange_device(const dccm_remap *as_bil, const dccm_rem
                                         int members, double sig1, double *s2a, double *s2o, int64_t s_ld,
                                         const dccm_sfc_fields *full, void *stream)
 {
+    if (!a2s_bil || !a2s_cons || !o2s_bil || !o2s_cons) return fail(DCCM_ERR_ARG, "dccm_sfc_exchange: null buffer");
+    dccm_src_seg a{a2s_bil, a2s_bil, a2s_bil, 0, INT64_MAX}, b{a2s_cons, a2s_cons, a2s_cons, 0, INT64_MAX};
+    dccm_src_seg c{o2s_bil, o2s_bil, o2s_bil, 0, INT64_MAX}, d{o2s_cons, o2s_cons, o2s_cons, 0, INT64_MAX};
+    return dccm_sfc_exchange_seg_device(as_bil, as_cons, os_bil, os_cons, &a, &b, &c, &d, 0, 0, members, sig1,
+                                        s2a, s2o, s_ld, full, stream);
+}
+
+extern "C" int dccm_sfc_exchange_seg_device(const dccm_remap *as_bil, const dccm_remap *as_cons,
+                                            const dccm_remap *os_bil, const dccm_remap *os_cons,
+                                            const dccm_src_seg *sa2s_bil, const dccm_src_seg *sa2s_cons,
+                                            const dccm_src_seg *so2s_bil, const dccm_src_seg *so2s_cons,
+                                            int64_t a_ld, int64_t o_ld,
+                                            int members, double sig1, double *s2a, double *s2o, int64_t s_ld,
+                                            const dccm_sfc_fields *full, void *stream)
+{
+    if (!sa2s_bil || !sa2s_cons || !so2s_bil || !so2s_cons) return fail(DCCM_ERR_ARG, "dccm_sfc_exchange: null buffer");
+    const double *a2s_bil = sa2s_bil->own, *a2s_cons = sa2s_cons->own, *o2s_bil = so2s_bil->own, *o2s_cons = so2s_cons->own;
     if (!as_bil || !as_cons || !os_bil || !os_cons) return fail(DCCM_ERR_ARG, "dccm_sfc_exchange: null table handle");
     if (!a2s_bil || !a2s_cons || !o2s_bil || !o2s_cons || !s2a || !s2o)
         return fail(DCCM_ERR_ARG, "dccm_sfc_exchange: null buffer");
@@ -186,12 +203,13 @@ extern "C" int dccm_sfc_exchange_device(const dccm_remap *as_bil, const dccm_rem
         return fail(DCCM_ERR_ARG, "dccm_sfc_exchange: the four tables do not describe the same grid triple");
     SfcArgs a;
     a.as_bil = csr_of(as_bil); a.as_cons = csr_of(as_cons); a.os_bil = csr_of(os_bil); a.os_cons = csr_of(os_cons);
-    a.a2s_bil = a2s_bil; a.a2s_cons = a2s_cons; a.o2s_bil = o2s_bil; a.o2s_cons = o2s_cons;
+    a.a2s_bil = seg_of(sa2s_bil); a.a2s_cons = seg_of(sa2s_cons); a.o2s_bil = seg_of(so2s_bil); a.o2s_cons = seg_of(so2s_cons);
     a.s2a = s2a; a.s2o = s2o;
     a.has_full = full ? 1 : 0;
     if (full) a.full = *full; else memset(&a.full, 0, sizeof a.full);
     if (s_ld != 0 && s_ld < nS) return fail(DCCM_ERR_ARG, "dccm_sfc_exchange: s_ld < surface cells");
-    a.nA = nA; a.nO = nO; a.nS = nS; a.sld = s_ld ? s_ld : nS; a.M = members; a.sig1 = sig1;
+    if ((a_ld && a_ld < nA) || (o_ld && o_ld < nO)) return fail(DCCM_ERR_ARG, "dccm_sfc_exchange: a_ld / o_ld smaller than the tables' source extent");
+    a.nA = a_ld ? a_ld : nA; a.nO = o_ld ? o_ld : nO; a.nS = nS; a.sld = s_ld ? s_ld : nS; a.M = members; a.sig1 = sig1;
     const int64_t n = (int64_t)nS * members;
     const unsigned grid = (unsigned)((n + kThreads - 1) / kThreads);
     static const int minb = getenv("DCCM_SFC_MINB") ? atoi(getenv("DCCM_SFC_MINB")) : 5;   // tuning knob (5 measured best on B200, profiles/)

@@ -32,7 +32,7 @@ constexpr int kThreads = 256;
 template <int FB>
 __global__ void __launch_bounds__(kThreads)
 remap_csr_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                 const double *__restrict__ w, const double *__restrict__ send, int64_t sn1,
+                 const double *__restrict__ w, const SrcSeg send, int64_t sn1,
                  double *__restrict__ recv, int64_t rn1, int n_recv, int nfield, int fields_per_y)
 {
     const int r = blockIdx.x * kThreads + threadIdx.x;
@@ -44,14 +44,15 @@ remap_csr_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__
         double acc[FB];
 #pragma unroll
         for (int d = 0; d < FB; d++) acc[d] = 0.0;
-        const double *s0 = send + (int64_t)d0 * sn1;
+        const int64_t o0 = (int64_t)d0 * sn1;
         if (d0 + FB <= d_end) {
             for (int k = k0; k < k1; k++) {
                 const int c = col[k];
                 const double ww = w[k];
+                const double *sp = send.at(c) + o0;
 #pragma unroll
                 for (int d = 0; d < FB; d++)
-                    acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(s0 + c + (int64_t)d * sn1), ww));
+                    acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(sp + (int64_t)d * sn1), ww));
             }
 #pragma unroll
             for (int d = 0; d < FB; d++) recv[r + (int64_t)(d0 + d) * rn1] = acc[d];
@@ -60,9 +61,10 @@ remap_csr_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__
             for (int k = k0; k < k1; k++) {
                 const int c = col[k];
                 const double ww = w[k];
+                const double *sp = send.at(c) + o0;
 #pragma unroll
                 for (int d = 0; d < FB; d++)
-                    if (d < nf) acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(s0 + c + (int64_t)d * sn1), ww));
+                    if (d < nf) acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(sp + (int64_t)d * sn1), ww));
             }
 #pragma unroll
             for (int d = 0; d < FB; d++)
@@ -76,7 +78,7 @@ template <int FB>
 __global__ void __launch_bounds__(kThreads)
 remap_zonal_kernel(const int32_t *__restrict__ zptr, const int32_t *__restrict__ zdj,
                    const double *__restrict__ zw, int nxs, int nxd,
-                   const double *__restrict__ send, int64_t sn1, double *__restrict__ recv, int64_t rn1,
+                   const SrcSeg send, int64_t sn1, double *__restrict__ recv, int64_t rn1,
                    int n_recv, int nfield, int fields_per_y)
 {
     const int r = blockIdx.x * kThreads + threadIdx.x;
@@ -89,7 +91,7 @@ remap_zonal_kernel(const int32_t *__restrict__ zptr, const int32_t *__restrict__
         double acc[FB];
 #pragma unroll
         for (int d = 0; d < FB; d++) acc[d] = 0.0;
-        const double *s0 = send + (int64_t)d0 * sn1;
+        const int64_t o0 = (int64_t)d0 * sn1;
         const int nf = min(FB, d_end - d0);
         for (int e = e0; e < e1; e++) {
             int i = iD + __ldg(&zdj[2 * e]);
@@ -97,14 +99,15 @@ remap_zonal_kernel(const int32_t *__restrict__ zptr, const int32_t *__restrict__
             if (nxs == 1) i = 0;                     // axisymmetric source: every longitude reads column 1
             const int64_t c = (int64_t)__ldg(&zdj[2 * e + 1]) * nxs + i;
             const double ww = __ldg(&zw[e]);
+            const double *sp = send.at(c) + o0;
             if (nf == FB) {
 #pragma unroll
                 for (int d = 0; d < FB; d++)
-                    acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(s0 + c + (int64_t)d * sn1), ww));
+                    acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(sp + (int64_t)d * sn1), ww));
             } else {
 #pragma unroll
                 for (int d = 0; d < FB; d++)
-                    if (d < nf) acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(s0 + c + (int64_t)d * sn1), ww));
+                    if (d < nf) acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(sp + (int64_t)d * sn1), ww));
             }
         }
 #pragma unroll
@@ -284,7 +287,15 @@ extern "C" int dccm_remap_kind(const dccm_remap *h) { return h ? h->kind : -1; }
 extern "C" int dccm_remap_apply_device(dccm_remap *h, const double *d_send, int sn1,
                                        double *d_recv, int rn1, int rn2, int num_of_data, void *stream)
 {
-    if (!h) return fail(DCCM_ERR_ARG, "dccm_remap_apply: null handle");
+    dccm_src_seg s{d_send, d_send, d_send, 0, INT64_MAX};
+    return dccm_remap_apply_seg_device(h, &s, sn1, d_recv, rn1, rn2, num_of_data, stream);
+}
+
+extern "C" int dccm_remap_apply_seg_device(dccm_remap *h, const dccm_src_seg *seg, int sn1,
+                                           double *d_recv, int rn1, int rn2, int num_of_data, void *stream)
+{
+    if (!h || !seg) return fail(DCCM_ERR_ARG, "dccm_remap_apply: null handle");
+    const SrcSeg d_send = seg_of(seg);
     if (sn1 < h->n_send || rn1 < h->n_recv)
         return fail(DCCM_ERR_ARG, "dccm_remap_apply: sn1=%d < n_send=%d or rn1=%d < n_recv=%d", sn1, h->n_send, rn1, h->n_recv);
     if (num_of_data < 0 || num_of_data > rn2)

@@ -3,6 +3,22 @@
 #pragma once
 #include "dccm_common.h"
 
+// A source buffer of a sharded run as the kernels see it: its first b0 cells are the lower
+// neighbour's boundary rows and the cells from b1 on the upper neighbour's -- read IN PLACE from
+// the neighbours' own send buffers over NVLink peer mappings (no halo copy, no collective); all three
+// bases are pre-offset so that element (cell c, layer l) is base[c + l*ld].  Unsharded: b0 = 0,
+// b1 = INT64_MAX and everything resolves to `own`.
+struct SrcSeg {
+    const double *lo, *own, *hi;
+    int64_t b0, b1;
+#ifdef __CUDACC__
+    __device__ __forceinline__ const double *at(int64_t c) const { return (c < b0 ? lo : (c >= b1 ? hi : own)) + c; }
+#endif
+};
+
+inline SrcSeg seg_of(const double *p) { return SrcSeg{p, p, p, 0, INT64_MAX}; }
+inline SrcSeg seg_of(const dccm_src_seg *s) { return SrcSeg{s->lo, s->own, s->hi, s->b0, s->b1}; }
+
 struct dccm_remap {
     int n_send = 0, n_recv = 0;
     int64_t nnz = 0;

@@ -230,3 +230,99 @@ class ShardedExchange(SurfaceExchange):
     def halo_from_sfc(self):
         if self.world > 1:
             self.halo_out()
+
+
+class PeerShardedExchange(ShardedExchange):
+    """Sharded exchange whose halo never moves: the surface kernel and the S->A / S->O remaps read
+    the neighbouring bands' boundary rows IN PLACE from the neighbours' own send buffers, which are
+    allocated as symmetric memory and peer-mapped over NVLink (torch.distributed._symmetric_memory).
+    The remap and its halo "collective" are one kernel; per exchange the only inter-GPU operations
+    besides those loads are two device-side barriers (after the forward solve, after the surface
+    kernel), which also order the buffer reuse of the next exchange:
+
+        forward -> B1 -> surface kernel (reads a2s/o2s rows of rank+-1) -> B2 -> remaps (read s2a/s2o rows
+        of rank+-1) -> backward -> [next exchange] forward (overwrites a2s: every reader passed B2) ...
+
+    Falls back to nothing: construct ShardedExchange (NCCL send/recv halo) where peer access is missing.
+    """
+
+    BUFS = (("a2s_bil", 13, "A"), ("a2s_cons", 4, "A"), ("o2s_bil", 2, "O"), ("o2s_cons", 3, "O"),
+            ("s2a", 9, "S"), ("s2o", 12, "S"))
+
+    def __init__(self, A, O, S, kmax, ncmax=1, index_h2ovap=1, rank=0, world=1, plan=None, dist=None, **kw):
+        import ctypes as C
+        import torch
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib as L
+        super().__init__(A, O, S, kmax, ncmax, index_h2ovap, rank=rank, world=world, plan=plan, dist=dist, **kw)
+        assert self.M == 1
+        self.sharded = True                                 # rows are wider than the owned band
+        plan = self.plan
+        self.seg, self.rowlen, self._hdl = {}, {}, {}
+        group = dist.group.WORLD
+        for name, nl, g in self.BUFS:
+            im = plan.grid[g].im
+            nmax = max((plan.ext[g][r][1] - plan.ext[g][r][0]) * im for r in range(world))
+            t = symm.empty((nl, nmax), dtype=torch.float64, device=self.dev)
+            t.zero_()
+            hdl = symm.rendezvous(t, group)
+            old = getattr(self, name)
+            t[:, :old.shape[1]] = old                       # keep whatever set_inputs() already stored
+            setattr(self, name, t)
+            self._hdl[name] = hdl
+            self.rowlen[g] = nmax
+            (j0, j1), (e0, e1) = plan.bands[g][rank], plan.ext[g][rank]
+            seg = L.SrcSeg()
+            own = t.data_ptr()
+            seg.own = own
+            seg.b0, seg.b1 = (j0 - e0) * im, (j1 - e0) * im
+            seg.lo = seg.hi = own
+            if rank > 0 and e0 < j0:
+                peer = hdl.get_buffer(rank - 1, (nl, nmax), torch.float64)
+                seg.lo = peer.data_ptr() + 8 * (e0 - plan.ext[g][rank - 1][0]) * im
+            if rank < world - 1 and e1 > j1:
+                peer = hdl.get_buffer(rank + 1, (nl, nmax), torch.float64)
+                seg.hi = peer.data_ptr() + 8 * (e0 - plan.ext[g][rank + 1][0]) * im
+            self.seg[name] = seg
+        self.vdiff.set_coef_stride(self.rowlen["A"])
+        self._bar = self._hdl["a2s_bil"]
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    def halo_to_sfc(self):
+        if self.world > 1:
+            self._bar.barrier(channel=0)
+
+    def halo_from_sfc(self):
+        if self.world > 1:
+            self._bar.barrier(channel=1)
+
+    def sfc_fused(self, store_full=False):
+        import ctypes as C
+        from . import _lib as L
+        o, s = self.ops, self.seg
+        L.check(L.lib().dccm_sfc_exchange_seg_device(
+            o["as_bil"]._h, o["as_cons"]._h, o["os_bil"]._h, o["os_cons"]._h,
+            C.byref(s["a2s_bil"]), C.byref(s["a2s_cons"]), C.byref(s["o2s_bil"]), C.byref(s["o2s_cons"]),
+            self.rowlen["A"], self.rowlen["O"], 1, float(self.sig1),
+            C.c_void_p(self.s2a.data_ptr() + 8 * self.offS), C.c_void_p(self.s2o.data_ptr() + 8 * self.offS),
+            self.rowlen["S"], None, L.current_stream()))
+        self.launches += 1
+
+    def remap_from_sfc(self):
+        import ctypes as C
+        from . import _lib as L
+
+        def apply(key, name, row0, nrow, recv):
+            seg = L.SrcSeg()
+            base = self.seg[name]
+            o = 8 * row0 * self.rowlen["S"]
+            seg.lo, seg.own, seg.hi, seg.b0, seg.b1 = base.lo + o, base.own + o, base.hi + o, base.b0, base.b1
+            L.check(L.lib().dccm_remap_apply_seg_device(self.ops[key]._h, C.byref(seg), self.rowlen["S"],
+                                                        L.tptr(recv), recv.shape[1], recv.shape[0], nrow,
+                                                        L.current_stream()))
+        apply("sa_cons", "s2a", 0, 4, self.a_recv[:4])
+        apply("sa_bil", "s2a", 4, 5, self.a_recv[4:])
+        apply("so_cons", "s2o", 0, 10, self.o_recv[:10])
+        apply("so_bil", "s2o", 10, 2, self.o_recv[10:])
+        self.launches += 4

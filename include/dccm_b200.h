@@ -121,6 +121,16 @@ int dccm_remap_apply_host(dccm_remap *h, const double *send, int sn1, int sn2,
                           double *recv, int rn1, int rn2, int num_of_data);
 int dccm_remap_apply_device(dccm_remap *h, const double *d_send, int sn1,
                             double *d_recv, int rn1, int rn2, int num_of_data, void *stream);
+/* Sharded runs: a source buffer whose first b0 cells are the lower neighbour's boundary rows and whose
+ * cells from b1 on are the upper neighbour's, read IN PLACE from the neighbours' own buffers through
+ * NVLink peer mappings (CUDA IPC / symmetric memory) -- the remap is fused with its halo "collective".
+ * lo / own / hi are pre-offset so that element (cell c, layer l) is base[c + l*sn1]. */
+typedef struct dccm_src_seg {
+    const double *lo, *own, *hi;
+    int64_t b0, b1;
+} dccm_src_seg;
+int dccm_remap_apply_seg_device(dccm_remap *h, const dccm_src_seg *send, int sn1,
+                                double *d_recv, int rn1, int rn2, int num_of_data, void *stream);
 /* registry keyed like the reference's operation_index(recv_model, send_model, mapping_tag)
  * (ref :88, :289); ids are Jcup component numbers (1-based), tags as in
  * common/dccm_common_params_mod.f90:64-69. */
@@ -186,6 +196,16 @@ int dccm_sfc_exchange_device(const dccm_remap *as_bil, const dccm_remap *as_cons
                              const double *o2s_bil, const double *o2s_cons,
                              int members, double sig1, double *s2a, double *s2o, int64_t s_ld,
                              const dccm_sfc_fields *full, void *stream);
+
+/* same, source buffers given as peer-mapped segments; a_ld / o_ld = cells per row of the ATM / OCN
+ * send buffers (0 = the tables' source extent) */
+int dccm_sfc_exchange_seg_device(const dccm_remap *as_bil, const dccm_remap *as_cons,
+                                 const dccm_remap *os_bil, const dccm_remap *os_cons,
+                                 const dccm_src_seg *a2s_bil, const dccm_src_seg *a2s_cons,
+                                 const dccm_src_seg *o2s_bil, const dccm_src_seg *o2s_cons,
+                                 int64_t a_ld, int64_t o_ld,
+                                 int members, double sig1, double *s2a, double *s2o, int64_t s_ld,
+                                 const dccm_sfc_fields *full, void *stream);
 
 /* ------------------------------------------------------------------ implicit coupling (K3/K4)
  * Replaces dcpam_sfc_implicit_coupling_mod, ref atm/dcpam_sfc_implicit_coupling_mod.f90. */
