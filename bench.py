@@ -383,7 +383,7 @@ def run_ours(args, rank, world):
         "remapped_cell_fields_per_s": ex.remapped_cell_fields() * value,
         "exchange_algorithmic_gbytes": bytes_alg[total_key] / 1e9,
         "exchange_hbm_gbs": bytes_alg[total_key] / (ms * 1e-3) / 1e9,
-        "exchange_frac_of_peak": bytes_alg[total_key] / (ms * 1e-3) / 1e9 / peak,
+        "exchange_frac_of_peak": bytes_alg[total_key] / (ms * 1e-3) / 1e9 / (peak * world),   # per GPU
         "part_ms": part_ms,
         "part_gbs": {n: bytes_alg[n] / (part_ms[n] * 1e-3) / 1e9 for n in bytes_alg if n in part_ms},
         "part_algorithmic_gbytes": {n: bytes_alg[n] / 1e9 for n in bytes_alg if n in part_ms},
