@@ -8,7 +8,7 @@
 !!     call dccm_register_operation(recv_comp_name, send_comp_name, mapping_tag)
 !!
 !! and replace the body of interpolate_data_latlon (ref :293-302) by the call in
-!! fortran/interpolate_data.f90 (or keep it as a fallback-free thin wrapper).
+!! fortran/shim_interpolate_data.f90 (or keep it as a fallback-free thin wrapper).
 subroutine dccm_register_operation(recv_comp_name, send_comp_name, mapping_tag)
   use interpolation_data_latlon_mod      ! needs `operation_index` made public (or move this inside the module)
   use jcup_interface, only: jcup_get_comp_num_from_name
