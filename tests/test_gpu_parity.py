@@ -428,3 +428,37 @@ def test_sharded_exchange_two_gpus_bit_exact(gpu):
                         "--master-addr", "127.0.0.1", "--master-port", "29631",
                         os.path.join(here, "sharded_gpu_check.py"), "T106_1deg"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_host_pipelined_exchange_equals_resident(gpu, orc, dccm, S):
+    """exchange_host.HostPipelinedExchange (host inputs -> host outputs, latitude slabs pipelined over
+    three streams, halo rows copied between slabs) gives the bits of the resident single-shot step."""
+    import torch
+    X = importlib.import_module("dennou-ccm_b200.exchange")
+    XH = importlib.import_module("dennou-ccm_b200.exchange_host")
+    A, O, Sx = pair(orc, dccm, "T106_1deg")
+    K, nc, nslab = 12, 2, 5
+    ex = X.SurfaceExchange(A, O, Sx, K, nc, 1, device=gpu)
+    ex.set_inputs(S.column_inputs(torch, A, K, nc, dev=gpu),
+                  {k: v[None] for k, v in S.atm_surface_fields(torch, A, dev=gpu).items()},
+                  {k: v[None] for k, v in S.ocn_surface_fields(torch, O, dev=gpu).items()})
+    ex.step()
+    hx = XH.HostPipelinedExchange(A, O, Sx, K, nc, 1, nslab=nslab, device=gpu)
+    for s in range(nslab):
+        (a0, a1), (o0, o1) = hx.bands(s)
+        for k, t in S.column_inputs(np, A, K, nc, a0, a1).items():
+            hx.h_in[s][k].copy_(torch.from_numpy(t))
+        for k, t in S.atm_surface_fields(np, A, a0, a1).items():
+            hx.h_in[s]["a:" + k].copy_(torch.from_numpy(t))
+        for k, t in S.ocn_surface_fields(np, O, o0, o1).items():
+            hx.h_in[s]["o:" + k].copy_(torch.from_numpy(t))
+    for _ in range(2):                       # twice: stream hand-over between consecutive exchanges
+        hx.step()
+    hx.synchronize()
+    cat = lambda k, dim: torch.cat([hx.h_out[s][k] for s in range(nslab)], dim=dim)
+    # inputs were generated with numpy here and torch there: same formulas, last-bit libm differences
+    for k, dim, ref in (("o_recv", 1, ex.o_recv), ("a_recv", 1, ex.a_recv), ("DUDt", 1, ex.tend["DUDt"]),
+                        ("DQMixDt", 2, ex.tend["DQMixDt"])):
+        got, want = cat(k, dim).numpy(), ref.cpu().numpy()
+        assert got.shape == want.shape
+        assert relerr(got, want, floor=1e-3 * np.abs(want).max()) <= 1e-9, k
