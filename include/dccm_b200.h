@@ -249,6 +249,22 @@ int dccm_vdiff_backward_device(dccm_vdiff *h,
     double *xyz_DUDt, double *xyz_DVDt, double *xyz_DTempDt, double *xyzf_DQMixDt,
     const double *level1, void *stream);
 
+/* ------------------------------------------------------------------ ocean / sea-ice side
+ * Element-wise work of ocn/dccm_ocn_mod.f90 either side of the remaps, on the device.
+ * put: ice-surface selection (ref ocn/dccm_ocn_mod.f90:825-836) written straight into the O->S send layers
+ *      o2s_bil = (SfcTemp ocean, SfcTemp ice), o2s_cons = (SIceCon, SfcAlbedo ocean, SfcAlbedo ice), row length ld.
+ * get: from the 12 remapped S->O / S->I layers (row length ld; order as in dccm_sfc_exchange_device)
+ *      FreshWtFlxS0 = ((Rain+Snow) - Evap)/DensFreshWater, FreshWtFlx0, sea-ice wind stress copies,
+ *      SfcHFlxAO0 = ns + sr, DSfcHFlxAODTs (ref :978-993).
+ * IceMaskMin, degC2K (DSIce) and DensFreshWater (DOGCM) belong to the external models. */
+int dccm_ocn_put_assemble_device(int64_t n, const double *SeaSfcTemp, const double *SfcAlbedoAO,
+                                 const double *SIceCon, const double *SIceSfcTempC, const double *SfcAlbedoAI,
+                                 double IceMaskMin, double degC2K, double *o2s_bil, double *o2s_cons,
+                                 int64_t ld, void *stream);
+int dccm_ocn_get_assemble_device(int64_t n, const double *o_recv, int64_t ld, double DensFreshWater,
+                                 double *FreshWtFlxS0, double *FreshWtFlx0, double *WindStressXAI,
+                                 double *WindStressYAI, double *SfcHFlxAO0, double *DSfcHFlxAODTs, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,8 @@ def lib():
         L.orc_vdiff_forward.argtypes = [C.c_void_p] + [_f64p] * 18
         L.orc_vdiff_backward.argtypes = [C.c_void_p] + [_f64p] * 4
         L.orc_vdiff_get_diag.argtypes = [C.c_void_p, C.c_int, _f64p]
+        L.orc_ocn_put_assemble.argtypes = [C.c_int64] + [_f64p] * 5 + [C.c_double, C.c_double, _f64p, _f64p]
+        L.orc_ocn_get_assemble.argtypes = [C.c_int64] + [_f64p] * 8 + [C.c_double] + [_f64p] * 6
         L.orc_num_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -236,6 +238,25 @@ class VDiff:
         out = np.zeros((K, imax * jmax))
         lib().orc_vdiff_get_diag(self.h, which, out)
         return out
+
+
+def ocn_put_assemble(SeaSfcTemp, AlbAO, SIceCon, SIceSfcTempC, AlbAI, IceMaskMin, degC2K):
+    """ref ocn/dccm_ocn_mod.f90:825-836 -> (SIceSfcTemp [K], SIceAlbedo)"""
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in (SeaSfcTemp, AlbAO, SIceCon, SIceSfcTempC, AlbAI)]
+    n = a[0].size
+    ti, ai = np.full(n, np.nan), np.full(n, np.nan)
+    lib().orc_ocn_put_assemble(n, *a, IceMaskMin, degC2K, ti, ai)
+    return ti, ai
+
+
+def ocn_get_assemble(ns, sr, dFdT, Snow, Rain, Evap, WSX, WSY, DensFreshWater):
+    """ref ocn/dccm_ocn_mod.f90:978-993"""
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in (ns, sr, dFdT, Snow, Rain, Evap, WSX, WSY)]
+    n = a[0].size
+    names = ("FreshWtFlxS0", "FreshWtFlx0", "WindStressXAI", "WindStressYAI", "SfcHFlxAO0", "DSfcHFlxAODTs")
+    out = {k: np.full(n, np.nan) for k in names}
+    lib().orc_ocn_get_assemble(n, *a, DensFreshWater, *[out[k] for k in names])
+    return out
 
 
 def num_threads():

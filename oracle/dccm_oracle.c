@@ -967,3 +967,38 @@ void orc_vdiff_get_diag(const orc_vdiff *h, int which, double *out)
     const double *M = which == 0 ? h->UVMtx : which == 1 ? h->TempMtx : h->QMixMtx;
     memcpy(out, M + NC * (size_t)K * 1, sizeof(double) * NC * K);
 }
+
+/* ------------------------------------------------------------------ ocean / sea-ice glue */
+
+/* ref ocn/dccm_ocn_mod.f90:825-836: ice-surface selection by IceMaskMin (degC2K, IceMaskMin: DSIce) */
+void orc_ocn_put_assemble(int64_t n, const double *SeaSfcTemp, const double *AlbAO, const double *SIceCon,
+                          const double *SIceSfcTempC, const double *AlbAI, double IceMaskMin, double degC2K,
+                          double *SIceSfcTemp, double *SIceAlbedo)
+{
+    for (int64_t c = 0; c < n; c++) {
+        if (SIceCon[c] >= IceMaskMin) {
+            SIceSfcTemp[c] = SIceSfcTempC[c] + degC2K;
+            SIceAlbedo[c] = AlbAI[c];
+        } else {
+            SIceSfcTemp[c] = SeaSfcTemp[c];
+            SIceAlbedo[c] = AlbAO[c];
+        }
+    }
+}
+
+/* ref ocn/dccm_ocn_mod.f90:978-993 */
+void orc_ocn_get_assemble(int64_t n, const double *ns, const double *sr, const double *dFdT,
+                          const double *Snow, const double *Rain, const double *EvapAO,
+                          const double *WSXAO, const double *WSYAO, double DensFreshWater,
+                          double *FreshWtFlxS0, double *FreshWtFlx0, double *WSXAI, double *WSYAI,
+                          double *SfcHFlxAO0, double *DSfcHFlxAODTs)
+{
+    for (int64_t c = 0; c < n; c++) {
+        FreshWtFlxS0[c] = ((Rain[c] + Snow[c]) - EvapAO[c]) / DensFreshWater;
+        FreshWtFlx0[c] = FreshWtFlxS0[c];
+        WSXAI[c] = WSXAO[c];
+        WSYAI[c] = WSYAO[c];
+        SfcHFlxAO0[c] = ns[c] + sr[c];
+        DSfcHFlxAODTs[c] = dFdT[c];
+    }
+}

@@ -102,6 +102,16 @@ void orc_vdiff_backward(orc_vdiff *h,
 /* copy of the swept diagonal b'(k) (k = 1..kmax; k=1 unspecified, see defect C-1) */
 void orc_vdiff_get_diag(const orc_vdiff *h, int which, double *out);
 
+/* ---- ocean / sea-ice glue, element-wise (ref ocn/dccm_ocn_mod.f90:825-836, :978-993) ---- */
+void orc_ocn_put_assemble(int64_t n, const double *SeaSfcTemp, const double *AlbAO, const double *SIceCon,
+                          const double *SIceSfcTempC, const double *AlbAI, double IceMaskMin, double degC2K,
+                          double *SIceSfcTemp, double *SIceAlbedo);
+void orc_ocn_get_assemble(int64_t n, const double *ns, const double *sr, const double *dFdT,
+                          const double *Snow, const double *Rain, const double *EvapAO,
+                          const double *WSXAO, const double *WSYAO, double DensFreshWater,
+                          double *FreshWtFlxS0, double *FreshWtFlx0, double *WSXAI, double *WSYAI,
+                          double *SfcHFlxAO0, double *DSfcHFlxAODTs);
+
 int orc_num_threads(void);
 
 #ifdef __cplusplus

@@ -462,3 +462,29 @@ def test_host_pipelined_exchange_equals_resident(gpu, orc, dccm, S):
         got, want = cat(k, dim).numpy(), ref.cpu().numpy()
         assert got.shape == want.shape
         assert relerr(got, want, floor=1e-3 * np.abs(want).max()) <= 1e-9, k
+
+
+def test_ocn_glue_kernels_bit_exact(gpu, orc, dccm, S):
+    """the ocean / sea-ice glue's element-wise work on the device, writing the O->S send
+    layers in place and assembling the S->O results (ref ocn/dccm_ocn_mod.f90:825-851, :978-993)."""
+    import torch
+    O = dccm.tables.regular_LonLatGrid(360, 180)
+    f = S.ocn_surface_fields(np, O)
+    n, ld = O.n, O.n + 64
+    tsC = f["SfcTempI"] - 273.15
+    IceMaskMin = 0.05
+    want_ti, want_ai = orc.ocn_put_assemble(f["SfcTempO"], f["SfcAlbedoO"], f["SIceCon"], tsC, f["SfcAlbedoI"], IceMaskMin, 273.15)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=gpu)
+    bil = torch.full((2, ld), float("nan"), dtype=torch.float64, device=gpu)
+    cons = torch.full((3, ld), float("nan"), dtype=torch.float64, device=gpu)
+    dccm.dccm_ocn_mod.ocn_put_assemble(t(f["SfcTempO"]), t(f["SfcAlbedoO"]), t(f["SIceCon"]), t(tsC), t(f["SfcAlbedoI"]),
+                                       IceMaskMin, 273.15, bil, cons)
+    assert np.array_equal(bil[0, :n].cpu().numpy(), f["SfcTempO"]) and np.array_equal(bil[1, :n].cpu().numpy(), want_ti)
+    assert np.array_equal(cons[0, :n].cpu().numpy(), f["SIceCon"]) and np.array_equal(cons[2, :n].cpu().numpy(), want_ai)
+    assert torch.isnan(bil[:, n:]).all()
+    assert ((f["SIceCon"] >= IceMaskMin) != (f["SIceCon"] > 0)).any()       # the mask threshold matters here
+    r = S.generic_fields(np, O, 12)
+    got = dccm.dccm_ocn_mod.ocn_get_assemble(t(r), 1000.0)
+    want = orc.ocn_get_assemble(r[0], r[1], r[10], r[2], r[3], r[4], r[5], r[6], 1000.0)
+    for k in want:
+        assert np.array_equal(got[k].cpu().numpy(), want[k]), k

@@ -338,3 +338,14 @@ def test_golden_vectors_are_stable(orc, dccm, S):
                     assert np.array_equal(a, b), (name, k)
                 else:
                     assert relerr(a, b, floor=1e-300) <= 1e-13, (name, k)
+
+
+def test_ocn_glue_known_answers(orc):
+    """ref ocn/dccm_ocn_mod.f90:825-836 (ice-surface selection) and :978-993 (fresh-water / heat flux)"""
+    ti, ai = orc.ocn_put_assemble([280.0, 272.0, 271.5], [0.1, 0.1, 0.1], [0.0, 0.05, 0.6], [-1.0, -2.0, -3.0],
+                                  [0.6, 0.6, 0.6], 0.05, 273.15)
+    assert ti.tolist() == [280.0, -2.0 + 273.15, -3.0 + 273.15] and ai.tolist() == [0.1, 0.6, 0.6]
+    o = orc.ocn_get_assemble([100.0], [-250.0], [15.0], [1e-5], [3e-5], [2.5e-5], [0.1], [-0.2], 1000.0)
+    assert o["FreshWtFlxS0"][0] == ((3e-5 + 1e-5) - 2.5e-5) / 1000.0 and o["FreshWtFlx0"][0] == o["FreshWtFlxS0"][0]
+    assert o["SfcHFlxAO0"][0] == -150.0 and o["DSfcHFlxAODTs"][0] == 15.0
+    assert o["WindStressXAI"][0] == 0.1 and o["WindStressYAI"][0] == -0.2
