@@ -262,3 +262,41 @@ class SurfaceExchange:
     def remapped_cell_fields(self):
         nA, nS, nO, M = self.A.n, self.S.n, self.O.n, self.M
         return M * (22 * nS + 9 * nA + 12 * nO)
+
+
+# ---------------------------------------------------------------------------------------------
+# Legacy 2-component topology: what the shipped exp/ configurations run.
+# The atmosphere computes the surface fluxes itself and ships 12 flux fields straight to the ocean;
+# 4 fields come back (ref common/mod_common_params.f90:76-175, ocn/mod_ocn.f90:615-669,
+# atm/mod_atm.f90:427-442).  Same remap operator (K1), other field lists, no bulk flux / solve.
+A2O_CONS = ["WindStressX", "WindStressY", "LDwRFlx", "SDwRFlx", "LUwRFlx", "SUwRFlx", "LatHFlx", "SenHFlx",
+            "RainFall", "SnowFall"]                      # GMAPTAG_ATM2D_OCN2D_CONSERVE
+A2O_BIL = ["DSfcHFlxDTs", "SfcAirTemp"]                  # GMAPTAG_ATM2D_OCN2D
+O2A_CONS = ["SfcTemp", "SfcAlbedo", "SfcEngyFlxMod"]
+O2A_BIL = ["SfcSnow"]
+
+
+class LegacyExchange:
+    """A<->O exchange of the 2-component mode on the device: 12 + 4 layers through four tables."""
+
+    def __init__(self, A, O, order_ao=1, lon_mode=1, device=None, tabs=None):
+        import torch
+        self.dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.A, self.O = A, O
+        if tabs is None:
+            tabs = {"ao_cons": tables.gen_table_jones99(A, O, order_ao, lon_mode).index(A.im, O.im),
+                    "ao_bil": tables.gen_table_bilinear(A, O, lon_mode).index(A.im, O.im),
+                    "oa_cons": tables.gen_table_jones99(O, A, 1, lon_mode).index(O.im, A.im),
+                    "oa_bil": tables.gen_table_bilinear(O, A, lon_mode).index(O.im, A.im)}
+        self.tabs = tabs
+        g = {"a": A, "o": O}
+        self.ops = {k: RemapOperator(*t, g[k[0]].n, g[k[1]].n, gnxs=g[k[0]].im, gnxr=g[k[1]].im) for k, t in tabs.items()}
+        z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=self.dev)
+        self.a2o = z(12, A.n); self.o_recv = z(12, O.n)
+        self.o2a = z(4, O.n); self.a_recv = z(4, A.n)
+
+    def step(self):
+        self.ops["ao_cons"].apply(self.a2o[:10], self.o_recv[:10])
+        self.ops["ao_bil"].apply(self.a2o[10:], self.o_recv[10:])
+        self.ops["oa_cons"].apply(self.o2a[:3], self.a_recv[:3])
+        self.ops["oa_bil"].apply(self.o2a[3:], self.a_recv[3:])

@@ -488,3 +488,24 @@ def test_ocn_glue_kernels_bit_exact(gpu, orc, dccm, S):
     want = orc.ocn_get_assemble(r[0], r[1], r[10], r[2], r[3], r[4], r[5], r[6], 1000.0)
     for k in want:
         assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+
+
+@pytest.mark.parametrize("name", ["T21_Pl42", "T42_T42"])
+def test_legacy_two_component_exchange_bit_exact(gpu, orc, dccm, S, name):
+    """the legacy A<->O topology the shipped exp/ configs run (12 a2o + 4 o2a layers,
+    ref common/mod_common_params.f90:76-175) goes through the same K1; T21 <-> axisymmetric Pl42 is the
+    shipped grid pair (ref exp/APEI07Couple/common/genmapgen_ATM_T21-OCN_Pl42_conserve.conf:1-4)."""
+    import torch
+    X = importlib.import_module("dennou-ccm_b200.exchange")
+    A, O, _ = pair(orc, dccm, name)
+    lx = X.LegacyExchange(A, O, order_ao=2 if O.im == 1 else 1, device=gpu)
+    a2o, o2a = S.generic_fields(np, A, 12), S.generic_fields(np, O, 4, salt=5.0)
+    lx.a2o.copy_(torch.from_numpy(a2o)); lx.o2a.copy_(torch.from_numpy(o2a))
+    lx.step()
+    torch.cuda.synchronize()
+    want_o = np.concatenate([orc.remap_apply(*lx.tabs["ao_cons"], a2o[:10], O.n), orc.remap_apply(*lx.tabs["ao_bil"], a2o[10:], O.n)])
+    want_a = np.concatenate([orc.remap_apply(*lx.tabs["oa_cons"], o2a[:3], A.n), orc.remap_apply(*lx.tabs["oa_bil"], o2a[3:], A.n)])
+    assert np.array_equal(lx.o_recv.cpu().numpy(), want_o) and np.array_equal(lx.a_recv.cpu().numpy(), want_a)
+    # conservative A->O keeps the global integral (area weights of the destination / source rows)
+    wo, wa = np.repeat(O.y_LatWt, O.im) / O.im, np.repeat(A.y_LatWt, A.im) / A.im
+    assert abs((want_o[2] * wo).sum() / (a2o[2] * wa).sum() - 1.0) <= 1e-11
