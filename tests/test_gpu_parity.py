@@ -499,7 +499,7 @@ def test_legacy_two_component_exchange_bit_exact(gpu, orc, dccm, S, name):
     X = importlib.import_module("dennou-ccm_b200.exchange")
     A, O, _ = pair(orc, dccm, name)
     lx = X.LegacyExchange(A, O, order_ao=2 if O.im == 1 else 1, device=gpu)
-    a2o, o2a = S.generic_fields(np, A, 12), S.generic_fields(np, O, 4, salt=5.0)
+    a2o, o2a = S.generic_fields(np, A, 12) + 2.0, S.generic_fields(np, O, 4, salt=5.0) + 2.0
     lx.a2o.copy_(torch.from_numpy(a2o)); lx.o2a.copy_(torch.from_numpy(o2a))
     lx.step()
     torch.cuda.synchronize()
