@@ -40,7 +40,7 @@ struct dccm_vdiff {
 namespace {
 
 constexpr int kThreads = 128;
-constexpr int kMaxTracer = 4;
+constexpr int kMaxTracer = 8;
 
 struct FwdArgs {
     const double *FX, *FY, *FH, *FQ;
@@ -295,7 +295,11 @@ void launch_forward(int nq, const FwdArgs &a, unsigned grid, cudaStream_t st)
     case 1: vdiff_forward_kernel<1, FAST><<<grid, kThreads, 0, st>>>(a); break;
     case 2: vdiff_forward_kernel<2, FAST><<<grid, kThreads, 0, st>>>(a); break;
     case 3: vdiff_forward_kernel<3, FAST><<<grid, kThreads, 0, st>>>(a); break;
-    default: vdiff_forward_kernel<4, FAST><<<grid, kThreads, 0, st>>>(a); break;
+    case 4: vdiff_forward_kernel<4, FAST><<<grid, kThreads, 0, st>>>(a); break;
+    case 5: vdiff_forward_kernel<5, FAST><<<grid, kThreads, 0, st>>>(a); break;
+    case 6: vdiff_forward_kernel<6, FAST><<<grid, kThreads, 0, st>>>(a); break;
+    case 7: vdiff_forward_kernel<7, FAST><<<grid, kThreads, 0, st>>>(a); break;
+    default: vdiff_forward_kernel<8, FAST><<<grid, kThreads, 0, st>>>(a); break;
     }
 }
 
@@ -390,7 +394,11 @@ extern "C" int dccm_vdiff_backward_device(dccm_vdiff *h, double *DU, double *DV,
     case 1: vdiff_backward_kernel<1><<<grid, kThreads, 0, st>>>(a); break;
     case 2: vdiff_backward_kernel<2><<<grid, kThreads, 0, st>>>(a); break;
     case 3: vdiff_backward_kernel<3><<<grid, kThreads, 0, st>>>(a); break;
-    default: vdiff_backward_kernel<4><<<grid, kThreads, 0, st>>>(a); break;
+    case 4: vdiff_backward_kernel<4><<<grid, kThreads, 0, st>>>(a); break;
+    case 5: vdiff_backward_kernel<5><<<grid, kThreads, 0, st>>>(a); break;
+    case 6: vdiff_backward_kernel<6><<<grid, kThreads, 0, st>>>(a); break;
+    case 7: vdiff_backward_kernel<7><<<grid, kThreads, 0, st>>>(a); break;
+    default: vdiff_backward_kernel<8><<<grid, kThreads, 0, st>>>(a); break;
     }
     DCCM_CUDA_TRY(cudaGetLastError());
     return DCCM_OK;

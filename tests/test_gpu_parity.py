@@ -222,7 +222,7 @@ def _vdiff_case(S, dccm, im, jm, K, nc):
     return g, S.column_inputs(np, g, K, nc)
 
 
-@pytest.mark.parametrize("im,jm,K,nc,iq", [(128, 64, 26, 1, 1), (64, 32, 16, 3, 2), (8, 4, 2, 1, 1), (9, 5, 3, 4, 4)])
+@pytest.mark.parametrize("im,jm,K,nc,iq", [(128, 64, 26, 1, 1), (64, 32, 16, 3, 2), (8, 4, 2, 1, 1), (9, 5, 3, 4, 4), (16, 8, 9, 7, 5)])
 def test_vdiff_reference_order_mode_is_bit_exact(gpu, orc, dccm, S, im, jm, K, nc, iq):
     g, inp = _vdiff_case(S, dccm, im, jm, K, nc)
     args = (g.im, g.jm, K, nc, iq, S.GRAV, S.CPDRY, S.GASRDRY, S.DELTIME)
