@@ -66,8 +66,16 @@ __device__ __forceinline__ void bulk_column(const BulkIn &in, double sig1, BulkO
     double Frac[2], QVapSat[2], SfcVirTemp[2];
     Frac[0] = 1.0 - in.SIceCon;                                                      // :205-206
     Frac[1] = in.SIceCon;
+    // xy_CalcFlag (:268-272): the sea-ice slot of an ice-free column.  The reference still evaluates the
+    // whole slot there and multiplies by bulk coefficients that BulkCoefL82 set to 0; every output of the
+    // slot is then an exact +0.  We write those zeros without evaluating (saturation exp, Ri, Louis
+    // functions, three divisions): same bits for finite inputs, ~1/3 of the column's work saved where
+    // there is no ice (columns of a warp share a latitude row, so the branch is warp-coherent).
+    const bool ice = Frac[1] > 1e-12;
+    QVapSat[1] = 0.0; SfcVirTemp[1] = 1.0;
 #pragma unroll
     for (int n = 0; n < 2; n++) {                                                    // :208-213
+        if (n == 1 && !ice) continue;
         QVapSat[n] = EpsV * Es0 / in.SfcPress
                    * exp(LatentHeatLocal[n] / GasRWet * (1.0 / 273.0 - 1.0 / in.SfcTemp[n]));
         SfcVirTemp[n] = in.SfcTemp[n] * (1.0 + (((1.0 / EpsV) - 1.0) * QVapSat[n]));
@@ -88,6 +96,12 @@ __device__ __forceinline__ void bulk_column(const BulkIn &in, double sig1, BulkO
 
 #pragma unroll
     for (int n = 0; n < 2; n++) {                                                    // :244
+        if (n == 1 && !ice) {
+            o.VelTC[n] = 0.0; o.TempTC[n] = 0.0; o.QVapTC[n] = 0.0;
+            o.WindStressX[n] = 0.0; o.WindStressY[n] = 0.0; o.SenHFlx[n] = 0.0; o.QVapMFlx[n] = 0.0;
+            o.LatHFlx[n] = 0.0; o.LUwRFlx[n] = 0.0; o.SUwRFlx[n] = 0.0;
+            continue;
+        }
         const double tmp = FKarm / log((Height - in.SfcHeight + z0m) / z0m);         // :250-253
         const double CMn = tmp * tmp;
         const double CHn = tmp * (FKarm / log((Height - in.SfcHeight + z0h) / z0h)); // :255-259
@@ -96,7 +110,7 @@ __device__ __forceinline__ void bulk_column(const BulkIn &in, double sig1, BulkO
                         * (VirTemp / Exner - SfcVirTemp[n] / SfcExner)
                         / (vr * vr)
                         * (Height - in.SfcHeight);
-        const bool flag = (n == 0) ? true : (Frac[n] > 1e-12);                       // :268-272
+        const bool flag = (n == 0) ? true : ice;                                     // :268-272
 
         // ---- BulkCoefL82 (:485-568) ----
         double CM, CH, CQ;
