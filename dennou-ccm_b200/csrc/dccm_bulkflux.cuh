@@ -55,7 +55,16 @@ struct BulkOut {
     double SfcTemp3, SfcAlbedo3;
 };
 
-__device__ __forceinline__ void bulk_column(const BulkIn &in, double sig1, BulkOut &o)
+// What the implicit update (phase 2) needs from the flux evaluation (phase 1) besides BulkOut.
+struct BulkMid {
+    double Exner, SfcExner;
+    double Frac[2], QVapSat[2];
+};
+
+// Phase 1 (:194-349): per-slot bulk coefficients, transfer coefficients, fluxes and their
+// area-weighted composite.  Reads neither ImplCplCoef1/2 nor LDwRFlx, so a caller that has those in
+// shared memory can fetch them afterwards (fewer live registers during the heavy part).
+__device__ __forceinline__ void bulk_fluxes(const BulkIn &in, double sig1, BulkOut &o, BulkMid &mid)
 {
     using namespace sfc;
     const double LatentHeatLocal[2] = {LatentHeat, LatentHeat + LatentHeatFusion};   // :198-199
@@ -63,7 +72,8 @@ __device__ __forceinline__ void bulk_column(const BulkIn &in, double sig1, BulkO
     const double z0h = RoughLenHeatFactor * z0m;
     const double HumdCoef = 1.0;
 
-    double Frac[2], QVapSat[2], SfcVirTemp[2];
+    double (&Frac)[2] = mid.Frac, (&QVapSat)[2] = mid.QVapSat;
+    double SfcVirTemp[2];
     Frac[0] = 1.0 - in.SIceCon;                                                      // :205-206
     Frac[1] = in.SIceCon;
     // xy_CalcFlag (:268-272): the sea-ice slot of an ice-free column.  The reference still evaluates the
@@ -86,6 +96,7 @@ __device__ __forceinline__ void bulk_column(const BulkIn &in, double sig1, BulkO
     // correctly rounded power (as good as pow()) at a fraction of its instruction count.
     const double Exner = exp((GasRDry / CpDry) * log(Press1 / RefPress));            // :218
     const double SfcExner = exp((GasRDry / CpDry) * log(in.SfcPress / RefPress));    // :219
+    mid.Exner = Exner; mid.SfcExner = SfcExner;
     const double VelAbs = sqrt(in.WindU * in.WindU + in.WindV * in.WindV);           // :221
     const double Height = in.SfcHeight + GasRDry / Grav * VirTemp * (1.0 - sig1);    // :223-224
 
@@ -93,6 +104,19 @@ __device__ __forceinline__ void bulk_column(const BulkIn &in, double sig1, BulkO
     o.QVapMFlx[2] = 0.0; o.SUwRFlx[2] = 0.0; o.LUwRFlx[2] = 0.0;
     o.SfcTemp3 = 0.0; o.SfcAlbedo3 = 0.0;
     o.VelTC[2] = 0.0; o.TempTC[2] = 0.0; o.QVapTC[2] = 0.0;
+
+    // Slot-independent pieces of the loop body (:250-266), evaluated once: the same expressions give the
+    // same bits for n = 1 and n = 2.  (h+z0)/z0 also appears, negated, under the square roots of the
+    // unstable branch: -(x)/z0 == -(x/z0) exactly.
+    const double hzm = (Height - in.SfcHeight + z0m) / z0m;
+    const double hzh = (z0h == z0m) ? hzm : (Height - in.SfcHeight + z0h) / z0h;
+    const double lgm = log(hzm);
+    const double lgh = (z0h == z0m) ? lgm : log(hzh);
+    const double tmp = FKarm / lgm;                                                  // :250-253
+    const double CMn = tmp * tmp;
+    const double CHn = tmp * (FKarm / lgh);                                          // :255-259
+    const double vr = fmax(VelAbs, VelMinForRi);
+    const double vr2 = vr * vr;
 
 #pragma unroll
     for (int n = 0; n < 2; n++) {                                                    // :244
@@ -102,13 +126,10 @@ __device__ __forceinline__ void bulk_column(const BulkIn &in, double sig1, BulkO
             o.LatHFlx[n] = 0.0; o.LUwRFlx[n] = 0.0; o.SUwRFlx[n] = 0.0;
             continue;
         }
-        const double tmp = FKarm / log((Height - in.SfcHeight + z0m) / z0m);         // :250-253
-        const double CMn = tmp * tmp;
-        const double CHn = tmp * (FKarm / log((Height - in.SfcHeight + z0h) / z0h)); // :255-259
-        const double vr = fmax(VelAbs, VelMinForRi);
-        const double Ri = Grav / (SfcVirTemp[n] / SfcExner)                          // :261-266
-                        * (VirTemp / Exner - SfcVirTemp[n] / SfcExner)
-                        / (vr * vr)
+        const double svx = SfcVirTemp[n] / SfcExner;
+        const double Ri = Grav / svx                                                 // :261-266
+                        * (VirTemp / Exner - svx)
+                        / vr2
                         * (Height - in.SfcHeight);
         const bool flag = (n == 0) ? true : ice;                                     // :268-272
 
@@ -116,14 +137,15 @@ __device__ __forceinline__ void bulk_column(const BulkIn &in, double sig1, BulkO
         double CM, CH, CQ;
         if (flag) {
             if (Ri > 0.0) {
-                CM = CMn / (1.0 + 10.0 * Ri / sqrt(1.0 + 5.0 * Ri));
-                CH = CHn / (1.0 + 15.0 * Ri * sqrt(1.0 + 5.0 * Ri));
+                const double sq = sqrt(1.0 + 5.0 * Ri);
+                CM = CMn / (1.0 + 10.0 * Ri / sq);
+                CH = CHn / (1.0 + 15.0 * Ri * sq);
                 CQ = CH;
             } else {
                 CM = CMn * (1.0 - 10.0 * Ri
-                     / (1.0 + 75.0 * CMn * sqrt(-(Height - in.SfcHeight + z0m) / z0m * Ri)));
+                     / (1.0 + 75.0 * CMn * sqrt(-hzm * Ri)));
                 CH = CHn * (1.0 - 15.0 * Ri
-                     / (1.0 + 75.0 * CHn * sqrt(-(Height - in.SfcHeight + z0h) / z0h * Ri)));
+                     / (1.0 + 75.0 * CHn * sqrt(-hzh * Ri)));
                 CQ = CH;
             }
         } else {
@@ -134,11 +156,12 @@ __device__ __forceinline__ void bulk_column(const BulkIn &in, double sig1, BulkO
         CQ = fmax(fmin(CQ, QVapBulkCoefMax), QVapBulkCoefMin);
 
         // ---- transfer coefficients and fluxes (:286-349) ----
-        o.VelTC[n] = CM * in.SfcPress / (GasRDry * SfcVirTemp[n])
+        const double rt = GasRDry * SfcVirTemp[n];
+        o.VelTC[n] = CM * in.SfcPress / rt
                    * fmin(fmax(VelAbs, VelMinForVel), VelMaxForVel);
-        o.TempTC[n] = CH * in.SfcPress / (GasRDry * SfcVirTemp[n])
+        o.TempTC[n] = CH * in.SfcPress / rt
                     * fmin(fmax(VelAbs, VelMinForTemp), VelMaxForTemp);
-        o.QVapTC[n] = CQ * in.SfcPress / (GasRDry * SfcVirTemp[n])
+        o.QVapTC[n] = CQ * in.SfcPress / rt
                     * fmin(fmax(VelAbs, VelMinForQVap), VelMaxForQVap);
         if (flag) {
             o.WindStressX[n] = -o.VelTC[n] * in.WindU;
@@ -169,6 +192,16 @@ __device__ __forceinline__ void bulk_column(const BulkIn &in, double sig1, BulkO
             o.LatHFlx[n] = 0.0; o.LUwRFlx[n] = 0.0; o.SUwRFlx[n] = 0.0;
         }
     }
+}
+
+// Phase 2 (:353-415): implicit surface-layer update, flux correction, net heat fluxes and dF/dTs.
+__device__ __forceinline__ void bulk_implicit(const BulkIn &in, const BulkMid &mid, BulkOut &o)
+{
+    using namespace sfc;
+    const double LatentHeatLocal[2] = {LatentHeat, LatentHeat + LatentHeatFusion};
+    const double HumdCoef = 1.0;
+    const double Exner = mid.Exner, SfcExner = mid.SfcExner;
+    const double (&Frac)[2] = mid.Frac, (&QVapSat)[2] = mid.QVapSat;
 
     // ---- implicit surface-layer update (:353-382) ----
     {
@@ -182,11 +215,12 @@ __device__ __forceinline__ void bulk_column(const BulkIn &in, double sig1, BulkO
         o.Del[2] = g2 * (o.SenHFlx[2] + in.Coef2[2]);
         o.Del[3] = g3 * (o.QVapMFlx[2] + in.Coef2[3]);
         double lat3 = 0.0;
+        const double cee = CpDry * SfcExner / Exner;
 #pragma unroll
         for (int n = 0; n < 3; n++) {
             o.WindStressX[n] = o.WindStressX[n] - o.VelTC[n] * o.Del[0];
             o.WindStressY[n] = o.WindStressY[n] - o.VelTC[n] * o.Del[1];
-            o.SenHFlx[n] = o.SenHFlx[n] - CpDry * SfcExner / Exner * o.TempTC[n] * o.Del[2];
+            o.SenHFlx[n] = o.SenHFlx[n] - cee * o.TempTC[n] * o.Del[2];
             o.QVapMFlx[n] = o.QVapMFlx[n] - HumdCoef * o.QVapTC[n] * o.Del[3];
             if (n < 2) {
                 o.LatHFlx[n] = LatentHeatLocal[n] * o.QVapMFlx[n];
@@ -215,6 +249,13 @@ __device__ __forceinline__ void bulk_column(const BulkIn &in, double sig1, BulkO
             o.HFlx_ns[n] = 0.0; o.HFlx_sr[n] = 0.0; o.DHFlxDTs[n] = 0.0;
         }
     }
+}
+
+__device__ __forceinline__ void bulk_column(const BulkIn &in, double sig1, BulkOut &o)
+{
+    BulkMid mid;
+    bulk_fluxes(in, sig1, o, mid);
+    bulk_implicit(in, mid, o);
 }
 
 }  // namespace dccm

@@ -15,6 +15,18 @@
 // The 22 remapped input layers and the 21 unused bulk outputs never touch HBM, and the
 // reference's unpack -> (IA,JA) halo arrays -> pack staging disappears.  Optionally the
 // API-complete DSFCM arrays are stored as well (diagnostics / parity tests).
+//
+// Two forms of step 1 for the atmosphere side (17 of the 22 layers):
+//   * staged (sfc_exchange_staged_kernel): when both A->S tables are zonal stencils -- every table the
+//     reference generator writes for the exchange grid, whose longitudes ARE the atmosphere's
+//     (ref tool/gmapgen/gmapgen_main.f90:349-352) -- a CTA owns 128 consecutive cells of ONE surface
+//     latitude row, so all it needs from the atmosphere are 1-3 source rows x (128 + stencil reach)
+//     columns per layer.  Warp 0 reads the row's stencil, and its lanes issue one TMA bulk copy
+//     (cp.async.bulk global -> shared, completion on an mbarrier) per (source row, layer); the ocean-side
+//     gathers run while the tiles land; the accumulation then reads shared memory at compile-time
+//     strides (no per-load address arithmetic, no exposed global latency) in the same table order.
+//   * direct (sfc_exchange_kernel): per-thread global gathers, any table kind.
+// Both give the same bits (tests/test_gpu_parity.py).
 #include <cuda_runtime.h>
 
 #include "dccm_bulkflux.cuh"
@@ -46,7 +58,10 @@ struct SfcArgs {
 // One destination row of one table, D layers.  The row's (col, w) pairs are fetched CH at a
 // time BEFORE any of the dependent source loads is issued, so a thread has up to CH*D gathers in
 // flight instead of D (rows of these tables hold 1-4 entries); accumulation stays in table order.
-template <int D, int CH>
+template <bool SEG>
+__device__ __forceinline__ const double *cell(const SrcSeg &s, int64_t c) { return SEG ? s.at(c) : s.own + c; }
+
+template <int D, int CH, bool SEG>
 __device__ __forceinline__ void gather(const Csr &t, int r, const SrcSeg &src, int64_t n_src,
                                        int M, int m, double (&acc)[D])
 {
@@ -62,7 +77,7 @@ __device__ __forceinline__ void gather(const Csr &t, int r, const SrcSeg &src, i
             int i = iD + __ldg(&t.col[2 * e]);
             if (i >= t.nxs) i -= t.nxs;
             if (t.nxs == 1) i = 0;                   // axisymmetric source
-            const double *p = src.at((int64_t)__ldg(&t.col[2 * e + 1]) * t.nxs + i) + o0;
+            const double *p = cell<SEG>(src, (int64_t)__ldg(&t.col[2 * e + 1]) * t.nxs + i) + o0;
             const double ww = __ldg(&t.w[e]);
 #pragma unroll
             for (int d = 0; d < D; d++) acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(p + d * lstride), ww));
@@ -83,7 +98,7 @@ __device__ __forceinline__ void gather(const Csr &t, int r, const SrcSeg &src, i
 #pragma unroll
         for (int j = 0; j < CH; j++) {
             if (kb + j < k1) {
-                const double *p = src.at(c[j]) + o0;
+                const double *p = cell<SEG>(src, c[j]) + o0;
 #pragma unroll
                 for (int d = 0; d < D; d++) v[j][d] = __ldg(p + d * lstride);
             }
@@ -98,49 +113,41 @@ __device__ __forceinline__ void gather(const Csr &t, int r, const SrcSeg &src, i
     }
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_kernel(const SfcArgs a)
+// Steps 2 and 3 for one cell.  `in` holds what the flux evaluation needs; `late(in, rain, snow)` supplies
+// what only the implicit update and the put side need (ImplCplCoef1/2, LDwRFlx, rain, snow) -- a no-op when
+// they are already there, a shared-memory fetch in the staged kernel, which keeps them out of the
+// registers during the flux evaluation.  Layers that are final after phase 1 are stored at once.
+template <bool FULL, class Late>
+__device__ __forceinline__ void bulk_and_put(const SfcArgs &a, int m, int r, BulkIn &in, Late late)
 {
-    const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    const int64_t nS = a.nS;
-    if (t >= nS * a.M) return;
-    const int m = (int)(t / nS);
-    const int r = (int)(t - (int64_t)m * nS);
     const int M = a.M;
-
-    double ab[13], ac[4], ob[2], oc[3];
-    gather<13, 2>(a.as_bil, r, a.a2s_bil, a.nA, M, m, ab);
-    gather<4, 4>(a.as_cons, r, a.a2s_cons, a.nA, M, m, ac);
-    gather<2, 4>(a.os_bil, r, a.o2s_bil, a.nO, M, m, ob);
-    gather<3, 4>(a.os_cons, r, a.o2s_cons, a.nO, M, m, oc);
-
-    BulkIn in;
-    in.WindU = ab[0]; in.WindV = ab[1]; in.SfcAirTemp = ab[2]; in.QVap1 = ab[3]; in.SfcPress = ab[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) { in.Coef1[k] = ab[5 + k]; in.Coef2[k] = ab[9 + k]; }
-    in.LDwRFlx = ac[0]; in.SDwRFlx = ac[1];
-    const double rain = ac[2], snow = ac[3];
-    in.SfcTemp[0] = ob[0]; in.SfcTemp[1] = ob[1];
-    in.SIceCon = oc[0]; in.SfcAlbedo[0] = oc[1]; in.SfcAlbedo[1] = oc[2];
+    const int64_t nS = a.nS;
     in.SfcHeight = 0.0;                                   // ref sfc/dccm_sfc_mod.f90:885
 
     BulkOut o;
-    bulk_column(in, a.sig1, o);
+    BulkMid mid;
+    bulk_fluxes(in, a.sig1, o, mid);
 
     // packed put-side layers, row = layer * M + member
     const int64_t ld = (int64_t)M * a.sld;                // one layer of all members
     double *pa = a.s2a + (int64_t)m * a.sld + r;
-    pa[0 * ld] = o.LUwRFlx[2]; pa[1 * ld] = o.SUwRFlx[2]; pa[2 * ld] = o.SenHFlx[2]; pa[3 * ld] = o.QVapMFlx[2];
-    pa[4 * ld] = o.SfcAlbedo3;
+    double *po = a.s2o + (int64_t)m * a.sld + r;
+    pa[0 * ld] = o.LUwRFlx[2]; pa[1 * ld] = o.SUwRFlx[2]; pa[4 * ld] = o.SfcAlbedo3;
+
+    double rain, snow;
+    late(in, rain, snow);
+    po[2 * ld] = snow; po[3 * ld] = rain;
+    bulk_implicit(in, mid, o);
+
+    pa[2 * ld] = o.SenHFlx[2]; pa[3 * ld] = o.QVapMFlx[2];
 #pragma unroll
     for (int k = 0; k < 4; k++) pa[(5 + k) * ld] = o.Del[k];
-    double *po = a.s2o + (int64_t)m * a.sld + r;
-    po[0 * ld] = o.HFlx_ns[0]; po[1 * ld] = o.HFlx_sr[0]; po[2 * ld] = snow; po[3 * ld] = rain;
+    po[0 * ld] = o.HFlx_ns[0]; po[1 * ld] = o.HFlx_sr[0];
     po[4 * ld] = o.QVapMFlx[0]; po[5 * ld] = -o.WindStressX[2]; po[6 * ld] = -o.WindStressY[2];
     po[7 * ld] = o.HFlx_ns[1]; po[8 * ld] = o.HFlx_sr[1]; po[9 * ld] = o.QVapMFlx[1];
     po[10 * ld] = o.DHFlxDTs[0]; po[11 * ld] = o.DHFlxDTs[1];
 
-    if (a.has_full) {
+    if (FULL) {
         const dccm_sfc_fields &f = a.full;
         const int64_t c = (int64_t)m * nS + r, ss = (int64_t)M * nS;
 #define ST3(ptr, v) if (f.ptr) { f.ptr[c] = o.v[0]; f.ptr[c + ss] = o.v[1]; f.ptr[c + 2 * ss] = o.v[2]; }
@@ -161,6 +168,206 @@ __global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_kernel(const SfcA
     }
 }
 
+// ---- direct form: every layer gathered from global memory by the cell's own thread
+template <int MINB, bool SEG, bool FULL>
+__global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_kernel(const SfcArgs a)
+{
+    const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t nS = a.nS;
+    if (t >= nS * a.M) return;
+    const int m = (int)(t / nS);
+    const int r = (int)(t - (int64_t)m * nS);
+    const int M = a.M;
+
+    double ab[13], ac[4], ob[2], oc[3];
+    gather<13, 2, SEG>(a.as_bil, r, a.a2s_bil, a.nA, M, m, ab);
+    gather<4, 4, SEG>(a.as_cons, r, a.a2s_cons, a.nA, M, m, ac);
+    gather<2, 4, SEG>(a.os_bil, r, a.o2s_bil, a.nO, M, m, ob);
+    gather<3, 4, SEG>(a.os_cons, r, a.o2s_cons, a.nO, M, m, oc);
+
+    BulkIn in;
+    in.WindU = ab[0]; in.WindV = ab[1]; in.SfcAirTemp = ab[2]; in.QVap1 = ab[3]; in.SfcPress = ab[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { in.Coef1[k] = ab[5 + k]; in.Coef2[k] = ab[9 + k]; }
+    in.LDwRFlx = ac[0]; in.SDwRFlx = ac[1];
+    in.SfcTemp[0] = ob[0]; in.SfcTemp[1] = ob[1];
+    in.SIceCon = oc[0]; in.SfcAlbedo[0] = oc[1]; in.SfcAlbedo[1] = oc[2];
+    bulk_and_put<FULL>(a, m, r, in, [&](BulkIn &, double &rain, double &snow) { rain = ac[2]; snow = ac[3]; });
+}
+
+// ---- staged form: atmosphere rows brought to shared memory by TMA bulk copies
+constexpr int kTileW = 136;        // doubles per staged source row: 128 cells + stencil reach + alignment slack
+constexpr int kMaxEnt = 16;        // longest stencil the staged form takes (bilinear 4, conservative 1-3 (+pairs))
+constexpr int kStageHdr = 640;     // mbarrier + two ZStage records, then the 128-byte aligned tiles
+
+struct ZStage {                    // one table's stencil for the CTA's latitude row, resolved to shared memory
+    double w[kMaxEnt];
+    int soff[kMaxEnt];             // tile offset of (source row, longitude shift) for thread 0, layer 0
+    int row_of_slot[kMaxEnt];
+    int n;
+};
+static_assert(16 + 2 * sizeof(ZStage) <= kStageHdr, "stage header too small");
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(mbar), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA, no tensor map): 16-byte aligned addresses, size a multiple of 16
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+struct StagePlan { int a, b, nslots; };
+
+// Warp 0, all lanes: resolve the stencil of destination row jD into shared-memory offsets and decide
+// which source rows go to which tile slot.  The tile of a slot holds logical source columns [a, b)
+// (both even, so every copy is 16-byte aligned), wrapped into [0, nxs) piece by piece when issued.
+template <int D>
+__device__ __forceinline__ StagePlan stage_plan(const Csr &t, int dmin, int dmax, int jD, int i0, int nact,
+                                                ZStage &zs, int lane)
+{
+    const int e0 = __ldg(&t.rowptr[jD]);
+    const int n = __ldg(&t.rowptr[jD + 1]) - e0;
+    int di = 0, js = -1 - lane;                   // idle lanes: distinct keys, never a row
+    double w = 0.0;
+    if (lane < n) {
+        di = __ldg(&t.col[2 * (e0 + lane)]);
+        js = __ldg(&t.col[2 * (e0 + lane) + 1]);
+        w = __ldg(&t.w[e0 + lane]);
+        if (di > t.nxs / 2) di -= t.nxs;          // westward neighbour
+    }
+    const unsigned same = __match_any_sync(0xffffffffu, js);
+    const int leader = __ffs(same) - 1;
+    const bool first = leader == lane && lane < n;
+    const unsigned firsts = __ballot_sync(0xffffffffu, first);
+    const int slot = __popc(firsts & ((1u << leader) - 1u));
+    StagePlan p;
+    p.a = (i0 + dmin) & ~1;
+    p.b = (i0 + nact + dmax + 1) & ~1;
+    p.nslots = __popc(firsts);
+    if (lane < n) { zs.soff[lane] = slot * (D * kTileW) + (di + i0 - p.a); zs.w[lane] = w; }
+    if (first) zs.row_of_slot[slot] = js;
+    if (lane == 0) zs.n = n;
+    return p;
+}
+
+// Warp 0, all lanes: one bulk copy per (slot, layer) and wrap piece, lanes striding over (slot, layer).
+template <int D, bool SEG>
+__device__ __forceinline__ void stage_issue(const Csr &t, const StagePlan &p, const ZStage &zs, const SrcSeg &src,
+                                            int64_t n_src, int M, int m, double *tile, uint32_t mbar, int lane)
+{
+    const int64_t o0 = (int64_t)m * n_src, lstride = (int64_t)M * n_src;
+    for (int idx = lane; idx < p.nslots * D; idx += 32) {
+        const int s = idx / D, d = idx - s * D;
+        const double *row = cell<SEG>(src, (int64_t)zs.row_of_slot[s] * t.nxs) + o0 + d * lstride;
+        const uint32_t dst = smem_u32(tile + (s * D + d) * kTileW);
+        int cur = p.a;
+        while (cur < p.b) {
+            int wc = cur % t.nxs;
+            if (wc < 0) wc += t.nxs;
+            const int len = min(p.b - cur, t.nxs - wc);
+            bulk_g2s(dst + 8u * (uint32_t)(cur - p.a), row + wc, 8u * (uint32_t)len, mbar);
+            cur += len;
+        }
+    }
+}
+
+// layers [L0, L0+N) of a D-layer tile, accumulated in table order
+template <int D, int L0, int N>
+__device__ __forceinline__ void staged_accumulate(const ZStage &zs, const double *tile, int tid, double (&acc)[N])
+{
+#pragma unroll
+    for (int d = 0; d < N; d++) acc[d] = 0.0;
+    const int n = zs.n;
+    for (int e = 0; e < n; e++) {
+        const double *p = tile + zs.soff[e] + tid + L0 * kTileW;
+        const double ww = zs.w[e];
+#pragma unroll
+        for (int d = 0; d < N; d++) acc[d] = __dadd_rn(acc[d], __dmul_rn(p[d * kTileW], ww));
+    }
+}
+
+struct StageArgs { int slots_bil, slots_cons, dmin_bil, dmax_bil, dmin_cons, dmax_cons, nxd; };
+
+template <int MINB, bool SEG, bool FULL>
+__global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_staged_kernel(const SfcArgs a, const StageArgs g)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    ZStage *zs = reinterpret_cast<ZStage *>(smem + 16);
+    double *tile_bil = reinterpret_cast<double *>(smem + kStageHdr);
+    double *tile_cons = tile_bil + g.slots_bil * (13 * kTileW);
+    const uint32_t mbar = smem_u32(smem);
+    const int tid = threadIdx.x;
+    const int jD = blockIdx.y, i0 = blockIdx.x * kThreads, m = blockIdx.z;
+    const int nact = min(kThreads, g.nxd - i0);
+    const int M = a.M;
+
+    if (tid < 32) {
+        if (tid == 0) mbar_init(mbar, 1);
+        const StagePlan pb = stage_plan<13>(a.as_bil, g.dmin_bil, g.dmax_bil, jD, i0, nact, zs[0], tid);
+        const StagePlan pc = stage_plan<4>(a.as_cons, g.dmin_cons, g.dmax_cons, jD, i0, nact, zs[1], tid);
+        if (tid == 0)
+            mbar_arrive_expect_tx(mbar, 8u * (uint32_t)(pb.nslots * 13 * (pb.b - pb.a) + pc.nslots * 4 * (pc.b - pc.a)));
+        __syncwarp();
+        stage_issue<13, SEG>(a.as_bil, pb, zs[0], a.a2s_bil, a.nA, M, m, tile_bil, mbar, tid);
+        stage_issue<4, SEG>(a.as_cons, pc, zs[1], a.a2s_cons, a.nA, M, m, tile_cons, mbar, tid);
+    }
+
+    // ocean / sea-ice side: direct gathers, in flight while the atmosphere tiles land
+    const int r = jD * g.nxd + i0 + tid;
+    double ob[2], oc[3];
+    if (tid < nact) {
+        gather<2, 4, SEG>(a.os_bil, r, a.o2s_bil, a.nO, M, m, ob);
+        gather<3, 4, SEG>(a.os_cons, r, a.o2s_cons, a.nO, M, m, oc);
+    }
+    __syncthreads();                       // stencil records + barrier initialisation visible to every warp
+    mbar_wait(mbar, 0);                    // tiles complete (every thread waits: no copy outlives the CTA)
+    if (tid >= nact) return;
+
+    BulkIn in;
+    {
+        double v[5], s[1];
+        staged_accumulate<13, 0, 5>(zs[0], tile_bil, tid, v);
+        staged_accumulate<4, 1, 1>(zs[1], tile_cons, tid, s);
+        in.WindU = v[0]; in.WindV = v[1]; in.SfcAirTemp = v[2]; in.QVap1 = v[3]; in.SfcPress = v[4];
+        in.SDwRFlx = s[0];
+    }
+    in.SfcTemp[0] = ob[0]; in.SfcTemp[1] = ob[1];
+    in.SIceCon = oc[0]; in.SfcAlbedo[0] = oc[1]; in.SfcAlbedo[1] = oc[2];
+    bulk_and_put<FULL>(a, m, r, in, [&](BulkIn &q, double &rain, double &snow) {
+        asm volatile("" ::: "memory");        // keep these shared-memory reads after the flux evaluation
+        double c[8], l[1], p[2];
+        staged_accumulate<13, 5, 8>(zs[0], tile_bil, tid, c);
+        staged_accumulate<4, 0, 1>(zs[1], tile_cons, tid, l);
+        staged_accumulate<4, 2, 2>(zs[1], tile_cons, tid, p);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { q.Coef1[k] = c[k]; q.Coef2[k] = c[4 + k]; }
+        q.LDwRFlx = l[0];
+        rain = p[0]; snow = p[1];
+    });
+}
+
 Csr csr_of(const dccm_remap *h)
 {
     if (h->kind == 1) return Csr{h->d_zptr, h->d_zdj, h->d_zw, 1, h->nxs, h->nxd};
@@ -168,6 +375,23 @@ Csr csr_of(const dccm_remap *h)
 }
 
 }  // namespace
+
+namespace {
+int g_minb = getenv("DCCM_SFC_MINB") ? atoi(getenv("DCCM_SFC_MINB")) : 5;         // 5 measured best on B200 (profiles/)
+int g_staged = getenv("DCCM_SFC_STAGED") ? atoi(getenv("DCCM_SFC_STAGED")) : 1;
+int g_last_form = -1;
+}  // namespace
+
+extern "C" int dccm_sfc_exchange_config(int staged, int min_blocks)
+{
+    if (min_blocks >= 0 && min_blocks != 4 && min_blocks != 5 && min_blocks != 6)
+        return fail(DCCM_ERR_ARG, "dccm_sfc_exchange_config: min_blocks must be 4, 5 or 6");
+    if (staged >= 0) g_staged = staged ? 1 : 0;
+    if (min_blocks >= 0) g_minb = min_blocks;
+    return DCCM_OK;
+}
+
+extern "C" int dccm_sfc_exchange_last_form(void) { return g_last_form; }
 
 extern "C" int dccm_sfc_exchange_device(const dccm_remap *as_bil, const dccm_remap *as_cons,
                                         const dccm_remap *os_bil, const dccm_remap *os_cons,
@@ -211,15 +435,69 @@ extern "C" int dccm_sfc_exchange_seg_device(const dccm_remap *as_bil, const dccm
     if ((a_ld && a_ld < nA) || (o_ld && o_ld < nO)) return fail(DCCM_ERR_ARG, "dccm_sfc_exchange: a_ld / o_ld smaller than the tables' source extent");
     a.nA = a_ld ? a_ld : nA; a.nO = o_ld ? o_ld : nO; a.nS = nS; a.sld = s_ld ? s_ld : nS; a.M = members; a.sig1 = sig1;
     const int64_t n = (int64_t)nS * members;
-    const unsigned grid = (unsigned)((n + kThreads - 1) / kThreads);
-    static const int minb = getenv("DCCM_SFC_MINB") ? atoi(getenv("DCCM_SFC_MINB")) : 5;   // tuning knob (5 measured best on B200, profiles/)
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    switch (minb) {
-    case 3: sfc_exchange_kernel<3><<<grid, kThreads, 0, st>>>(a); break;
-    case 6: sfc_exchange_kernel<6><<<grid, kThreads, 0, st>>>(a); break;
-    case 8: sfc_exchange_kernel<8><<<grid, kThreads, 0, st>>>(a); break;
-    case 4: sfc_exchange_kernel<4><<<grid, kThreads, 0, st>>>(a); break;
-    default: sfc_exchange_kernel<5><<<grid, kThreads, 0, st>>>(a); break;
+    const int minb = g_minb, want_staged = g_staged;
+    const bool seg = !(a.a2s_bil.b0 <= 0 && a.a2s_bil.b1 >= (int64_t)INT32_MAX && a.a2s_cons.b0 <= 0 &&
+                       a.a2s_cons.b1 >= (int64_t)INT32_MAX && a.o2s_bil.b0 <= 0 && a.o2s_bil.b1 >= (int64_t)INT32_MAX &&
+                       a.o2s_cons.b0 <= 0 && a.o2s_cons.b1 >= (int64_t)INT32_MAX);
+
+    // staged form: both atmosphere tables zonal stencils on equal, even longitudes; every copy 16-byte aligned
+    auto aligned16 = [](const SrcSeg &s) {
+        return (((uintptr_t)s.lo | (uintptr_t)s.own | (uintptr_t)s.hi) & 15u) == 0;
+    };
+    auto row_cut = [](const SrcSeg &s, int nx) {
+        return (s.b0 <= 0 || s.b0 % nx == 0) && (s.b1 >= (int64_t)INT32_MAX || s.b1 % nx == 0);
+    };
+    const int nx = as_bil->nxd;
+    bool staged = want_staged && as_bil->kind == 1 && as_cons->kind == 1 && nx >= 2 && nx % 2 == 0 &&
+                  as_bil->nxs == nx && as_cons->nxs == nx && as_cons->nxd == nx && as_bil->nyd == as_cons->nyd &&
+                  a.nA % 2 == 0 && aligned16(a.a2s_bil) && aligned16(a.a2s_cons) &&
+                  row_cut(a.a2s_bil, nx) && row_cut(a.a2s_cons, nx) &&
+                  as_bil->z_max_len <= kMaxEnt && as_cons->z_max_len <= kMaxEnt &&
+                  as_bil->z_max_len >= 1 && as_cons->z_max_len >= 1 &&
+                  as_bil->z_dmax - as_bil->z_dmin + 2 + kThreads <= kTileW &&
+                  as_cons->z_dmax - as_cons->z_dmin + 2 + kThreads <= kTileW &&
+                  as_bil->nyd <= 65535 && members <= 65535;
+    StageArgs g{};
+    size_t smem = 0;
+    if (staged) {
+        g.slots_bil = as_bil->z_max_rows; g.slots_cons = as_cons->z_max_rows;
+        g.dmin_bil = as_bil->z_dmin; g.dmax_bil = as_bil->z_dmax;
+        g.dmin_cons = as_cons->z_dmin; g.dmax_cons = as_cons->z_dmax;
+        g.nxd = nx;
+        smem = kStageHdr + sizeof(double) * kTileW * (size_t)(13 * g.slots_bil + 4 * g.slots_cons);
+        if (smem > 200 * 1024) staged = false;
+    }
+    g_last_form = staged ? 1 : 0;
+    if (staged) {
+        dim3 grid((unsigned)((nx + kThreads - 1) / kThreads), (unsigned)as_bil->nyd, (unsigned)members);
+#define DCCM_LAUNCH_STAGED(MB, FULL)                                                                             \
+        do {                                                                                                     \
+            auto kern = seg ? sfc_exchange_staged_kernel<MB, true, FULL> : sfc_exchange_staged_kernel<MB, false, FULL>; \
+            DCCM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+            kern<<<grid, kThreads, smem, st>>>(a, g);                                                            \
+        } while (0)
+        if (a.has_full) DCCM_LAUNCH_STAGED(4, true);       // diagnostics / parity form: all 42 outputs live
+        else switch (minb) {
+        case 4: DCCM_LAUNCH_STAGED(4, false); break;
+        case 6: DCCM_LAUNCH_STAGED(6, false); break;
+        default: DCCM_LAUNCH_STAGED(5, false); break;
+        }
+#undef DCCM_LAUNCH_STAGED
+    } else {
+        const unsigned grid = (unsigned)((n + kThreads - 1) / kThreads);
+#define DCCM_LAUNCH_DIRECT(MB, FULL)                                                                             \
+        do {                                                                                                     \
+            if (seg) sfc_exchange_kernel<MB, true, FULL><<<grid, kThreads, 0, st>>>(a);                          \
+            else sfc_exchange_kernel<MB, false, FULL><<<grid, kThreads, 0, st>>>(a);                             \
+        } while (0)
+        if (a.has_full) DCCM_LAUNCH_DIRECT(4, true);
+        else switch (minb) {
+        case 4: DCCM_LAUNCH_DIRECT(4, false); break;
+        case 6: DCCM_LAUNCH_DIRECT(6, false); break;
+        default: DCCM_LAUNCH_DIRECT(5, false); break;
+        }
+#undef DCCM_LAUNCH_DIRECT
     }
     DCCM_CUDA_TRY(cudaGetLastError());
     return DCCM_OK;

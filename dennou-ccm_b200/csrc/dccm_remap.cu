@@ -28,16 +28,23 @@ namespace {
 
 constexpr int kThreads = 256;
 
-// One thread per destination row; FB fields register-blocked.
-template <int FB>
+template <bool SEG>
+__device__ __forceinline__ const double *cell(const SrcSeg &s, int64_t c) { return SEG ? s.at(c) : s.own + c; }
+
+// One thread per destination row; FB fields register-blocked (the launcher picks the smallest FB that
+// takes all fields of the call in one pass, so a row's (col, w) pairs are read once).  The pairs are
+// fetched CH at a time before the dependent source loads are issued: a thread has up to CH*FB gathers
+// in flight (rows hold 1-6 entries).  Accumulation stays in table order, multiply and add separate.
+template <int FB, bool SEG>
 __global__ void __launch_bounds__(kThreads)
 remap_csr_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                  const double *__restrict__ w, const SrcSeg send, int64_t sn1,
                  double *__restrict__ recv, int64_t rn1, int n_recv, int nfield, int fields_per_y)
 {
+    constexpr int CH = FB <= 5 ? 4 : 2;
     const int r = blockIdx.x * kThreads + threadIdx.x;
     if (r >= n_recv) return;
-    const int k0 = rowptr[r], k1 = rowptr[r + 1];
+    const int k0 = __ldg(&rowptr[r]), k1 = __ldg(&rowptr[r + 1]);
     const int d_begin = blockIdx.y * fields_per_y;
     const int d_end = min(nfield, d_begin + fields_per_y);
     for (int d0 = d_begin; d0 < d_end; d0 += FB) {
@@ -45,36 +52,40 @@ remap_csr_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__
 #pragma unroll
         for (int d = 0; d < FB; d++) acc[d] = 0.0;
         const int64_t o0 = (int64_t)d0 * sn1;
-        if (d0 + FB <= d_end) {
-            for (int k = k0; k < k1; k++) {
-                const int c = col[k];
-                const double ww = w[k];
-                const double *sp = send.at(c) + o0;
+        const int nf = min(FB, d_end - d0);
+        for (int kb = k0; kb < k1; kb += CH) {
+            int c[CH];
+            double ww[CH];
 #pragma unroll
-                for (int d = 0; d < FB; d++)
-                    acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(sp + (int64_t)d * sn1), ww));
+            for (int j = 0; j < CH; j++) {
+                const bool on = kb + j < k1;
+                c[j] = on ? __ldg(&col[kb + j]) : 0;
+                ww[j] = on ? __ldg(&w[kb + j]) : 0.0;
             }
 #pragma unroll
-            for (int d = 0; d < FB; d++) recv[r + (int64_t)(d0 + d) * rn1] = acc[d];
-        } else {
-            const int nf = d_end - d0;
-            for (int k = k0; k < k1; k++) {
-                const int c = col[k];
-                const double ww = w[k];
-                const double *sp = send.at(c) + o0;
+            for (int j = 0; j < CH; j++) {
+                if (kb + j < k1) {
+                    const double *sp = cell<SEG>(send, c[j]) + o0;
+                    if (nf == FB) {
 #pragma unroll
-                for (int d = 0; d < FB; d++)
-                    if (d < nf) acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(sp + (int64_t)d * sn1), ww));
+                        for (int d = 0; d < FB; d++)
+                            acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(sp + (int64_t)d * sn1), ww[j]));
+                    } else {
+#pragma unroll
+                        for (int d = 0; d < FB; d++)
+                            if (d < nf) acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(sp + (int64_t)d * sn1), ww[j]));
+                    }
+                }
             }
-#pragma unroll
-            for (int d = 0; d < FB; d++)
-                if (d < nf) recv[r + (int64_t)(d0 + d) * rn1] = acc[d];
         }
+#pragma unroll
+        for (int d = 0; d < FB; d++)
+            if (d < nf) recv[r + (int64_t)(d0 + d) * rn1] = acc[d];
     }
 }
 
 // kind 1: zonal stencil, one thread per destination cell, no per-cell table reads.
-template <int FB>
+template <int FB, bool SEG>
 __global__ void __launch_bounds__(kThreads)
 remap_zonal_kernel(const int32_t *__restrict__ zptr, const int32_t *__restrict__ zdj,
                    const double *__restrict__ zw, int nxs, int nxd,
@@ -99,7 +110,7 @@ remap_zonal_kernel(const int32_t *__restrict__ zptr, const int32_t *__restrict__
             if (nxs == 1) i = 0;                     // axisymmetric source: every longitude reads column 1
             const int64_t c = (int64_t)__ldg(&zdj[2 * e + 1]) * nxs + i;
             const double ww = __ldg(&zw[e]);
-            const double *sp = send.at(c) + o0;
+            const double *sp = cell<SEG>(send, c) + o0;
             if (nf == FB) {
 #pragma unroll
                 for (int d = 0; d < FB; d++)
@@ -237,6 +248,21 @@ extern "C" int dccm_remap_create_lonlat(int64_t nops, const int32_t *send_index,
         std::vector<double> zw;
         if (detect_zonal(rowptr, col, w, gnxs, gnxr, n_recv / gnxr, zptr, zdi, zjs, zw)) {
             h->kind = 1; h->nxs = gnxs; h->nxd = gnxr; h->nyd = n_recv / gnxr; h->znnz = (int64_t)zw.size();
+            h->z_dmin = INT32_MAX; h->z_dmax = INT32_MIN;
+            for (int jD = 0; jD < h->nyd; jD++) {
+                const int e0 = zptr[jD], e1 = zptr[jD + 1];
+                h->z_max_len = std::max(h->z_max_len, e1 - e0);
+                int rows = 0;
+                for (int e = e0; e < e1; e++) {
+                    bool first = true;
+                    for (int f = e0; f < e; f++) first = first && zjs[f] != zjs[e];
+                    rows += first;
+                    const int sd = zdi[e] > gnxs / 2 ? zdi[e] - gnxs : zdi[e];
+                    h->z_dmin = std::min(h->z_dmin, sd); h->z_dmax = std::max(h->z_dmax, sd);
+                }
+                h->z_max_rows = std::max(h->z_max_rows, rows);
+            }
+            if (zw.empty()) h->z_dmin = h->z_dmax = 0;
             std::vector<int32_t> zdj(2 * zdi.size());
             for (size_t k = 0; k < zdi.size(); k++) { zdj[2 * k] = zdi[k]; zdj[2 * k + 1] = zjs[k]; }
             e = cudaMalloc(&h->d_zptr, sizeof(int32_t) * zptr.size());
@@ -310,20 +336,40 @@ extern "C" int dccm_remap_apply_seg_device(dccm_remap *h, const dccm_src_seg *se
                                         sizeof(double) * (size_t)(rn1 - h->n_recv), num_of_data, st));
     if (num_of_data == 0) return DCCM_OK;
     const int gx = (h->n_recv + kThreads - 1) / kThreads;
-    // enough CTAs to fill the machine: split fields over grid.y when rows are few
-    constexpr int FB = 8;
+    const bool use_seg = !(d_send.b0 <= 0 && d_send.b1 >= (int64_t)INT32_MAX);
+    // field block: the smallest compiled size that takes the whole call in one pass; when rows are too few
+    // to fill the machine the fields are split over grid.y instead (blocks of 2)
+    static const int kFB[] = {2, 4, 5, 8, 10, 13};
+    int FB = 13;
+    for (int f : kFB) if (num_of_data <= f) { FB = f; break; }
+    const int want = 4 * num_sms();
+    if (gx < want && num_of_data > 2) FB = 2;
     int nfb = (num_of_data + FB - 1) / FB;
-    int want = 4 * num_sms();
     int gy = std::min(nfb, std::max(1, (want + gx - 1) / gx));
     int fields_per_y = ((nfb + gy - 1) / gy) * FB;
     gy = (num_of_data + fields_per_y - 1) / fields_per_y;
     dim3 grid(gx, gy);
-    if (h->kind == 1)
-        remap_zonal_kernel<FB><<<grid, kThreads, 0, st>>>(h->d_zptr, h->d_zdj, h->d_zw, h->nxs, h->nxd,
-                                                         d_send, sn1, d_recv, rn1, h->n_recv, num_of_data, fields_per_y);
-    else
-        remap_csr_kernel<FB><<<grid, kThreads, 0, st>>>(h->d_rowptr, h->d_col, h->d_w, d_send, sn1, d_recv, rn1,
-                                                       h->n_recv, num_of_data, fields_per_y);
+#define DCCM_REMAP_LAUNCH(F, S)                                                                                   \
+    do {                                                                                                          \
+        if (h->kind == 1)                                                                                         \
+            remap_zonal_kernel<F, S><<<grid, kThreads, 0, st>>>(h->d_zptr, h->d_zdj, h->d_zw, h->nxs, h->nxd,     \
+                                                               d_send, sn1, d_recv, rn1, h->n_recv, num_of_data, \
+                                                               fields_per_y);                                    \
+        else                                                                                                      \
+            remap_csr_kernel<F, S><<<grid, kThreads, 0, st>>>(h->d_rowptr, h->d_col, h->d_w, d_send, sn1, d_recv, \
+                                                             rn1, h->n_recv, num_of_data, fields_per_y);         \
+    } while (0)
+#define DCCM_REMAP_FB(F) do { if (use_seg) DCCM_REMAP_LAUNCH(F, true); else DCCM_REMAP_LAUNCH(F, false); } while (0)
+    switch (FB) {
+    case 2: DCCM_REMAP_FB(2); break;
+    case 4: DCCM_REMAP_FB(4); break;
+    case 5: DCCM_REMAP_FB(5); break;
+    case 8: DCCM_REMAP_FB(8); break;
+    case 10: DCCM_REMAP_FB(10); break;
+    default: DCCM_REMAP_FB(13); break;
+    }
+#undef DCCM_REMAP_FB
+#undef DCCM_REMAP_LAUNCH
     DCCM_CUDA_TRY(cudaGetLastError());
     return DCCM_OK;
 }

@@ -39,5 +39,9 @@ struct dccm_remap {
     int32_t *d_zptr = nullptr;     // (nyd + 1)
     int32_t *d_zdj = nullptr;      // interleaved (di, jS) pairs
     double *d_zw = nullptr;
+    // what a CTA that stages source tiles in shared memory must provision (TMA path of the fused
+    // surface kernel): longest stencil, most distinct source rows in one stencil, and the range of
+    // the longitude offsets taken as signed shifts (di > nxs/2 is a westward neighbour)
+    int z_max_len = 0, z_max_rows = 0, z_dmin = 0, z_dmax = 0;
     dccm::DevBuf send_buf, recv_buf;
 };

@@ -197,6 +197,14 @@ int dccm_sfc_exchange_device(const dccm_remap *as_bil, const dccm_remap *as_cons
                              int members, double sig1, double *s2a, double *s2o, int64_t s_ld,
                              const dccm_sfc_fields *full, void *stream);
 
+/* Which form of the kernel the next calls launch: staged = 1 (default) lets a CTA bring its atmosphere source
+ * rows to shared memory with TMA bulk copies whenever both A->S tables are zonal stencils, 0 forces the
+ * per-thread global gathers; min_blocks = CTAs per SM the kernel is compiled for (4, 5 or 6).  A negative value
+ * keeps the current setting.  Results are bit-identical in every configuration. */
+int dccm_sfc_exchange_config(int staged, int min_blocks);
+/* 1 if the last dccm_sfc_exchange_*_device call launched the staged form, 0 if the direct one */
+int dccm_sfc_exchange_last_form(void);
+
 /* same, source buffers given as peer-mapped segments; a_ld / o_ld = cells per row of the ATM / OCN
  * send buffers (0 = the tables' source extent) */
 int dccm_sfc_exchange_seg_device(const dccm_remap *as_bil, const dccm_remap *as_cons,

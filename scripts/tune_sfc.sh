@@ -1,7 +1,10 @@
 #!/bin/bash
+# Fused surface kernel variants: parity tests, then the default workload per (form, CTAs/SM).
+# Usage: gpurun -- bash scripts/tune_sfc.sh TAG "staged:minb ..."
 OUT=gpurun_out/${1:-tune}; mkdir -p $OUT
-( timeout 600 python -m pytest tests -m gpu -q -k "bulk or exchange or golden" ) > $OUT/pytest.log 2>&1; echo "pytest exit $?"; tail -3 $OUT/pytest.log
-for mb in ${2:-4 5 6}; do
-  DCCM_SFC_MINB=$mb timeout 300 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu > $OUT/sfc_minb$mb.json 2>$OUT/err$mb.log
-  python -c "import json; d=json.load(open('$OUT/sfc_minb$mb.json')); print('minb',$mb,d['part_ms'], d['value'])"
+( timeout 900 python -m pytest tests -m gpu -q -x ) > $OUT/pytest.log 2>&1; echo "pytest exit $?"; tail -5 $OUT/pytest.log
+for v in ${2:-1:5 1:6 1:4 0:5}; do
+  st=${v%%:*}; mb=${v##*:}
+  DCCM_SFC_STAGED=$st DCCM_SFC_MINB=$mb timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu > $OUT/sfc_s${st}_b$mb.json 2>$OUT/err_s${st}_b$mb.log
+  python -c "import json; d=json.load(open('$OUT/sfc_s${st}_b$mb.json')); print('staged',$st,'minb',$mb,d['part_ms'], d['value'])" || tail -5 $OUT/err_s${st}_b$mb.log
 done

@@ -385,6 +385,60 @@ def test_exchange_step_vs_oracle(gpu, orc, dccm, S, name, K, fast):
     assert np.abs((got * wA).sum(1) / (want * wA).sum(1) - 1.0).max() <= CONS
 
 
+@pytest.mark.parametrize("name,members", [("T21_Pl42", 1), ("T42_T42", 3), ("T21_1deg", 1), ("T106_1deg", 2)])
+def test_fused_surface_kernel_staged_and_direct_forms_bit_exact(gpu, orc, dccm, S, name, members):
+    """The TMA-staged form of the fused surface kernel (atmosphere rows in shared memory) and the direct form
+    (per-thread global gathers) against the unfused remap -> bulk flux -> pack sequence: same bits in the 21
+    put-side layers and in the API-complete DSFCM arrays; rows shorter and longer than a CTA, wrap-around
+    pieces (T21: one CTA holds a whole latitude circle), ragged last CTA (T106: 320 = 2.5 CTAs), ensembles."""
+    import torch
+    X = importlib.import_module("dennou-ccm_b200.exchange")
+    L = dccm._lib
+    A, O, Sx = pair(orc, dccm, name)
+    tabs = X.build_tables(A, O, Sx)
+    M, K = members, 8
+    tt = lambda d: {k: torch.as_tensor(v, device=gpu).contiguous() for k, v in d.items()}
+    cols = [tt(S.column_inputs(np, A, K, 1, member=m)) for m in range(M)]
+    atms = [tt(S.atm_surface_fields(np, A, member=m)) for m in range(M)]
+    ocns = [tt(S.ocn_surface_fields(np, O, member=m)) for m in range(M)]
+    ex = X.SurfaceExchange(A, O, Sx, K, 1, 1, tabs=tabs, members=M, device=gpu)
+    ex.set_inputs({k: torch.cat([c[k] for c in cols], dim=-1).contiguous() for k in cols[0]},
+                  {k: torch.stack([a[k] for a in atms]) for k in atms[0]},
+                  {k: torch.stack([o[k] for o in ocns]) for k in ocns[0]})
+    ex.forward()
+    ex.remap_to_sfc(); ex.bulk(); ex.pack_sfc()
+    torch.cuda.synchronize()
+    want = {"s2a": ex.s2a.clone(), "s2o": ex.s2o.clone()}
+    want_full = {k: v.clone() for k, v in ex.sfc_out.items()}
+    want_full["s_obil"] = ex.s_obil.clone(); want_full["s_ocons"] = ex.s_ocons.clone()
+    forms = []
+    try:
+        for staged in (1, 0):
+            for minb in (5, 4, 6):
+                for full in (False, True):
+                    L.check(L.lib().dccm_sfc_exchange_config(staged, minb))
+                    ex.s2a.fill_(float("nan")); ex.s2o.fill_(float("nan"))
+                    if full:
+                        for v in ex.sfc_out.values():
+                            v.fill_(float("nan"))
+                        ex.s_obil[2 * M:].fill_(float("nan")); ex.s_ocons[3 * M:].fill_(float("nan"))
+                    ex.sfc_fused(store_full=full)
+                    torch.cuda.synchronize()
+                    forms.append(L.lib().dccm_sfc_exchange_last_form())
+                    tag = f"staged={staged} minb={minb} full={full}"
+                    assert torch.equal(ex.s2a, want["s2a"]), tag + " s2a"
+                    assert torch.equal(ex.s2o, want["s2o"]), tag + " s2o"
+                    if full:
+                        for k, v in ex.sfc_out.items():
+                            assert torch.equal(v, want_full[k]), tag + " " + k
+                        assert torch.equal(ex.s_obil, want_full["s_obil"]), tag
+                        assert torch.equal(ex.s_ocons, want_full["s_ocons"]), tag
+    finally:
+        L.check(L.lib().dccm_sfc_exchange_config(1, 5))
+    # every A->S table of these grid pairs is a zonal stencil on even longitudes: the staged form must have run
+    assert forms[:6] == [1] * 6 and forms[6:] == [0] * 6, forms
+
+
 def test_exchange_ensemble_members_match_single_runs(gpu, orc, dccm, S):
     """BASELINE config 2: members batched along the layer axis share the tables; member m of the
     batch equals a single-member run on member m's inputs, bit for bit."""
