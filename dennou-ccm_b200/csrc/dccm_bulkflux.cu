@@ -63,6 +63,25 @@ __global__ void __launch_bounds__(kThreads) bulkflux_kernel(const BulkArgs a)
 
 DevBuf g_buf;   // scratch of the host entry point
 
+// FastArith against the plain operators, element by element: counts[0] = accepted quotients / reciprocals /
+// roots whose bits differ from `a/b`, `1.0/b`, `sqrt(|a|)` (must be 0), counts[1] = operations whose fast path
+// was not acceptable (they take the IEEE re-evaluation in the product kernels).
+__global__ void fast_arith_selftest_kernel(const double *a, const double *b, int64_t n, unsigned long long *counts)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = a[i], y = b[i];
+    unsigned long long bad = 0, rej = 0;
+    { FastArith f; const double q = f.div(x, y);
+      if (!f.good()) rej++; else if (__double_as_longlong(q) != __double_as_longlong(x / y)) bad++; }
+    { FastArith f; const double q = f.rcp(y);
+      if (!f.good()) rej++; else if (__double_as_longlong(q) != __double_as_longlong(1.0 / y)) bad++; }
+    { FastArith f; const double q = f.root(fabs(x));
+      if (!f.good()) rej++; else if (__double_as_longlong(q) != __double_as_longlong(sqrt(fabs(x)))) bad++; }
+    if (bad) atomicAdd(&counts[0], bad);
+    if (rej) atomicAdd(&counts[1], rej);
+}
+
 }  // namespace
 
 extern "C" int dccm_bulkflux_device(int nx, int ny, int ld, int64_t off, int64_t slot_stride,
@@ -81,6 +100,22 @@ extern "C" int dccm_bulkflux_device(int nx, int ny, int ld, int64_t off, int64_t
     const unsigned grid = (unsigned)((n + kThreads - 1) / kThreads);
     bulkflux_kernel<<<grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
     DCCM_CUDA_TRY(cudaGetLastError());
+    return DCCM_OK;
+}
+
+extern "C" int dccm_selftest_fast_arith_device(const double *d_a, const double *d_b, int64_t n,
+                                               int64_t *mismatches, int64_t *rejected)
+{
+    int rc = ensure_device();
+    if (rc) return rc;
+    unsigned long long *d_counts = nullptr, h[2] = {0, 0};
+    DCCM_CUDA_TRY(cudaMalloc(&d_counts, sizeof h));
+    DCCM_CUDA_TRY(cudaMemset(d_counts, 0, sizeof h));
+    fast_arith_selftest_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_a, d_b, n, d_counts);
+    cudaError_t e = cudaMemcpy(h, d_counts, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d_counts);
+    DCCM_CUDA_TRY(e);
+    *mismatches = (int64_t)h[0]; *rejected = (int64_t)h[1];
     return DCCM_OK;
 }
 

@@ -55,6 +55,77 @@ struct BulkOut {
     double SfcTemp3, SfcAlbedo3;
 };
 
+// ---- fp64 division / reciprocal / square root without the per-operation branch ------------------
+// nvcc expands every fp64 `a / b`, `1.0 / b` and `sqrt(x)` into a short Newton sequence on the
+// MUFU.RCP64H / MUFU.RSQ64H seed, followed by a test that accepts the result when the exponents are
+// in range and otherwise BRANCHES to an out-of-line routine (denormals, infinities, NaN, zero).  The
+// ~40 divisions of a column are then ~40 basic blocks and the scheduler cannot overlap their
+// dependent DFMA chains -- the fused surface kernel spent a quarter of its cycles waiting on them.
+// FastArith issues exactly the compiler's fast-path instruction sequence (same seeds, same
+// operations, hence the same, correctly rounded, bits) but only ACCUMULATES the acceptance test in
+// `ok`; a column for which any test failed is re-evaluated with IeeeArith (plain operators) by the
+// caller.  Results are therefore bit-identical to plain `/` and `sqrt` for every input.
+struct IeeeArith {
+    __device__ __forceinline__ double div(double a, double b) { return a / b; }
+    __device__ __forceinline__ double rcp(double b) { return 1.0 / b; }
+    __device__ __forceinline__ double root(double x) { return sqrt(x); }
+    __device__ __forceinline__ bool good() const { return true; }
+};
+
+struct FastArith {
+    bool ok = true;
+    __device__ __forceinline__ bool good() const { return ok; }
+
+    static __device__ __forceinline__ int rcp64h(double b)
+    {
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));     // MUFU.RCP64H on the high word
+        return __double2hiint(r);
+    }
+    static __device__ __forceinline__ double newton_rcp(double r, double b)
+    {
+        double e = fma(-b, r, 1.0);
+        e = fma(e, e, e);
+        r = fma(r, e, r);
+        e = fma(-b, r, 1.0);
+        return fma(r, e, r);
+    }
+    __device__ __forceinline__ double div(double a, double b)
+    {
+        const double r = newton_rcp(__hiloint2double(rcp64h(b), 1), b);
+        double q = __dmul_rn(a, r);
+        const double rem = fma(-b, q, a);
+        q = fma(r, rem, q);
+        const float t = __fmaf_rn(0.0f, __int_as_float(__double2hiint(b)), __int_as_float(__double2hiint(q)));
+        ok = ok && (fabsf(__int_as_float(__double2hiint(a))) >= 6.5827683646048100446e-37f)
+                && (fabsf(t) > 1.469367938527859385e-39f);
+        return q;
+    }
+    __device__ __forceinline__ double rcp(double b)
+    {
+        const int lo = __double2hiint(b) + 0x300402;
+        ok = ok && (fabsf(__int_as_float(lo)) >= 5.8789094863358348022e-39f);
+        return newton_rcp(__hiloint2double(rcp64h(b), lo), b);
+    }
+    __device__ __forceinline__ double root(double x)
+    {
+        double s;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(s) : "d"(x));   // MUFU.RSQ64H on the high word
+        const int lo = __double2hiint(x) - 0x03500000;
+        ok = ok && ((unsigned)lo < 0x7ca00000u);
+        const double r0 = __hiloint2double(__double2hiint(s), lo);
+        double t = __dmul_rn(r0, r0);
+        t = fma(x, -t, 1.0);
+        const double u = fma(t, 0.375, 0.5);
+        t = __dmul_rn(r0, t);
+        const double r = fma(u, t, r0);
+        const double g = __dmul_rn(x, r);
+        const double rh = __hiloint2double(__double2hiint(r) - 0x00100000, __double2loint(r));
+        const double rem = fma(g, -g, x);
+        return fma(rem, rh, g);
+    }
+};
+
 // What the implicit update (phase 2) needs from the flux evaluation (phase 1) besides BulkOut.
 struct BulkMid {
     double Exner, SfcExner;
@@ -64,7 +135,8 @@ struct BulkMid {
 // Phase 1 (:194-349): per-slot bulk coefficients, transfer coefficients, fluxes and their
 // area-weighted composite.  Reads neither ImplCplCoef1/2 nor LDwRFlx, so a caller that has those in
 // shared memory can fetch them afterwards (fewer live registers during the heavy part).
-__device__ __forceinline__ void bulk_fluxes(const BulkIn &in, double sig1, BulkOut &o, BulkMid &mid)
+template <class Arith>
+__device__ __forceinline__ void bulk_fluxes(const BulkIn &in, double sig1, BulkOut &o, BulkMid &mid, Arith &ar)
 {
     using namespace sfc;
     const double LatentHeatLocal[2] = {LatentHeat, LatentHeat + LatentHeatFusion};   // :198-199
@@ -86,18 +158,18 @@ __device__ __forceinline__ void bulk_fluxes(const BulkIn &in, double sig1, BulkO
 #pragma unroll
     for (int n = 0; n < 2; n++) {                                                    // :208-213
         if (n == 1 && !ice) continue;
-        QVapSat[n] = EpsV * Es0 / in.SfcPress
-                   * exp(LatentHeatLocal[n] / GasRWet * (1.0 / 273.0 - 1.0 / in.SfcTemp[n]));
+        QVapSat[n] = ar.div(EpsV * Es0, in.SfcPress)
+                   * exp(LatentHeatLocal[n] / GasRWet * (1.0 / 273.0 - ar.rcp(in.SfcTemp[n])));
         SfcVirTemp[n] = in.SfcTemp[n] * (1.0 + (((1.0 / EpsV) - 1.0) * QVapSat[n]));
     }
     const double VirTemp = in.SfcAirTemp * (1.0 + (((1.0 / EpsV) - 1.0) * in.QVap1));   // :215
     const double Press1 = in.SfcPress * sig1;                                        // :217
     // x**kappa as exp(kappa*log(x)): |log x| << 1 here, so the result is within 1 ulp of the
     // correctly rounded power (as good as pow()) at a fraction of its instruction count.
-    const double Exner = exp((GasRDry / CpDry) * log(Press1 / RefPress));            // :218
-    const double SfcExner = exp((GasRDry / CpDry) * log(in.SfcPress / RefPress));    // :219
+    const double Exner = exp((GasRDry / CpDry) * log(ar.div(Press1, RefPress)));            // :218
+    const double SfcExner = exp((GasRDry / CpDry) * log(ar.div(in.SfcPress, RefPress)));    // :219
     mid.Exner = Exner; mid.SfcExner = SfcExner;
-    const double VelAbs = sqrt(in.WindU * in.WindU + in.WindV * in.WindV);           // :221
+    const double VelAbs = ar.root(in.WindU * in.WindU + in.WindV * in.WindV);           // :221
     const double Height = in.SfcHeight + GasRDry / Grav * VirTemp * (1.0 - sig1);    // :223-224
 
     o.WindStressX[2] = 0.0; o.WindStressY[2] = 0.0; o.SenHFlx[2] = 0.0; o.LatHFlx[2] = 0.0;   // :226-240
@@ -108,13 +180,13 @@ __device__ __forceinline__ void bulk_fluxes(const BulkIn &in, double sig1, BulkO
     // Slot-independent pieces of the loop body (:250-266), evaluated once: the same expressions give the
     // same bits for n = 1 and n = 2.  (h+z0)/z0 also appears, negated, under the square roots of the
     // unstable branch: -(x)/z0 == -(x/z0) exactly.
-    const double hzm = (Height - in.SfcHeight + z0m) / z0m;
-    const double hzh = (z0h == z0m) ? hzm : (Height - in.SfcHeight + z0h) / z0h;
+    const double hzm = ar.div(Height - in.SfcHeight + z0m, z0m);
+    const double hzh = (z0h == z0m) ? hzm : ar.div(Height - in.SfcHeight + z0h, z0h);
     const double lgm = log(hzm);
     const double lgh = (z0h == z0m) ? lgm : log(hzh);
-    const double tmp = FKarm / lgm;                                                  // :250-253
+    const double tmp = ar.div(FKarm, lgm);                                                 // :250-253
     const double CMn = tmp * tmp;
-    const double CHn = tmp * (FKarm / lgh);                                          // :255-259
+    const double CHn = tmp * ar.div(FKarm, lgh);                                         // :255-259
     const double vr = fmax(VelAbs, VelMinForRi);
     const double vr2 = vr * vr;
 
@@ -126,10 +198,10 @@ __device__ __forceinline__ void bulk_fluxes(const BulkIn &in, double sig1, BulkO
             o.LatHFlx[n] = 0.0; o.LUwRFlx[n] = 0.0; o.SUwRFlx[n] = 0.0;
             continue;
         }
-        const double svx = SfcVirTemp[n] / SfcExner;
-        const double Ri = Grav / svx                                                 // :261-266
-                        * (VirTemp / Exner - svx)
-                        / vr2
+        const double svx = ar.div(SfcVirTemp[n], SfcExner);
+        const double Ri = ar.div(ar.div(Grav, svx)                                   // :261-266
+                                 * (ar.div(VirTemp, Exner) - svx),
+                                 vr2)
                         * (Height - in.SfcHeight);
         const bool flag = (n == 0) ? true : ice;                                     // :268-272
 
@@ -137,15 +209,15 @@ __device__ __forceinline__ void bulk_fluxes(const BulkIn &in, double sig1, BulkO
         double CM, CH, CQ;
         if (flag) {
             if (Ri > 0.0) {
-                const double sq = sqrt(1.0 + 5.0 * Ri);
-                CM = CMn / (1.0 + 10.0 * Ri / sq);
-                CH = CHn / (1.0 + 15.0 * Ri * sq);
+                const double sq = ar.root(1.0 + 5.0 * Ri);
+                CM = ar.div(CMn, 1.0 + ar.div(10.0 * Ri, sq));
+                CH = ar.div(CHn, 1.0 + 15.0 * Ri * sq);
                 CQ = CH;
             } else {
-                CM = CMn * (1.0 - 10.0 * Ri
-                     / (1.0 + 75.0 * CMn * sqrt(-hzm * Ri)));
-                CH = CHn * (1.0 - 15.0 * Ri
-                     / (1.0 + 75.0 * CHn * sqrt(-hzh * Ri)));
+                CM = CMn * (1.0 - ar.div(10.0 * Ri,
+                                         1.0 + 75.0 * CMn * ar.root(-hzm * Ri)));
+                CH = CHn * (1.0 - ar.div(15.0 * Ri,
+                                         1.0 + 75.0 * CHn * ar.root(-hzh * Ri)));
                 CQ = CH;
             }
         } else {
@@ -157,17 +229,17 @@ __device__ __forceinline__ void bulk_fluxes(const BulkIn &in, double sig1, BulkO
 
         // ---- transfer coefficients and fluxes (:286-349) ----
         const double rt = GasRDry * SfcVirTemp[n];
-        o.VelTC[n] = CM * in.SfcPress / rt
+        o.VelTC[n] = ar.div(CM * in.SfcPress, rt)
                    * fmin(fmax(VelAbs, VelMinForVel), VelMaxForVel);
-        o.TempTC[n] = CH * in.SfcPress / rt
+        o.TempTC[n] = ar.div(CH * in.SfcPress, rt)
                     * fmin(fmax(VelAbs, VelMinForTemp), VelMaxForTemp);
-        o.QVapTC[n] = CQ * in.SfcPress / rt
+        o.QVapTC[n] = ar.div(CQ * in.SfcPress, rt)
                     * fmin(fmax(VelAbs, VelMinForQVap), VelMaxForQVap);
         if (flag) {
             o.WindStressX[n] = -o.VelTC[n] * in.WindU;
             o.WindStressY[n] = -o.VelTC[n] * in.WindV;
             o.SenHFlx[n] = -CpDry * SfcExner * o.TempTC[n]
-                         * (in.SfcAirTemp / Exner - in.SfcTemp[n] / SfcExner);
+                         * (ar.div(in.SfcAirTemp, Exner) - ar.div(in.SfcTemp[n], SfcExner));
             o.QVapMFlx[n] = -HumdCoef * o.QVapTC[n] * (in.QVap1 - QVapSat[n]);
             o.LatHFlx[n] = LatentHeatLocal[n] * o.QVapMFlx[n];
             const double t2 = in.SfcTemp[n] * in.SfcTemp[n];
@@ -195,7 +267,8 @@ __device__ __forceinline__ void bulk_fluxes(const BulkIn &in, double sig1, BulkO
 }
 
 // Phase 2 (:353-415): implicit surface-layer update, flux correction, net heat fluxes and dF/dTs.
-__device__ __forceinline__ void bulk_implicit(const BulkIn &in, const BulkMid &mid, BulkOut &o)
+template <class Arith>
+__device__ __forceinline__ void bulk_implicit(const BulkIn &in, const BulkMid &mid, BulkOut &o, Arith &ar)
 {
     using namespace sfc;
     const double LatentHeatLocal[2] = {LatentHeat, LatentHeat + LatentHeatFusion};
@@ -205,17 +278,17 @@ __device__ __forceinline__ void bulk_implicit(const BulkIn &in, const BulkMid &m
 
     // ---- implicit surface-layer update (:353-382) ----
     {
-        const double DFsDT1 = -CpDry * SfcExner * o.TempTC[2] / Exner;
-        const double g0 = 1.0 / (in.Coef1[0] + o.VelTC[2]);
-        const double g1 = 1.0 / (in.Coef1[1] + o.VelTC[2]);
-        const double g2 = 1.0 / (in.Coef1[2] - DFsDT1);
-        const double g3 = 1.0 / (in.Coef1[3] + HumdCoef * o.QVapTC[2]);
+        const double DFsDT1 = ar.div(-CpDry * SfcExner * o.TempTC[2], Exner);
+        const double g0 = ar.rcp(in.Coef1[0] + o.VelTC[2]);
+        const double g1 = ar.rcp(in.Coef1[1] + o.VelTC[2]);
+        const double g2 = ar.rcp(in.Coef1[2] - DFsDT1);
+        const double g3 = ar.rcp(in.Coef1[3] + HumdCoef * o.QVapTC[2]);
         o.Del[0] = g0 * (o.WindStressX[2] + in.Coef2[0]);
         o.Del[1] = g1 * (o.WindStressY[2] + in.Coef2[1]);
         o.Del[2] = g2 * (o.SenHFlx[2] + in.Coef2[2]);
         o.Del[3] = g3 * (o.QVapMFlx[2] + in.Coef2[3]);
         double lat3 = 0.0;
-        const double cee = CpDry * SfcExner / Exner;
+        const double cee = ar.div(CpDry * SfcExner, Exner);
 #pragma unroll
         for (int n = 0; n < 3; n++) {
             o.WindStressX[n] = o.WindStressX[n] - o.VelTC[n] * o.Del[0];
@@ -244,18 +317,25 @@ __device__ __forceinline__ void bulk_implicit(const BulkIn &in, const BulkMid &m
             o.DHFlxDTs[n] = +4.0 * StB * (t * t * t)
                           + CpDry * o.TempTC[n]
                           + LatentHeatLocal[n] * HumdCoef * o.QVapTC[n]
-                            * (LatentHeatLocal[n] * QVapSat[n] / (GasRWet * (t * t)));
+                            * ar.div(LatentHeatLocal[n] * QVapSat[n], GasRWet * (t * t));
         } else {
             o.HFlx_ns[n] = 0.0; o.HFlx_sr[n] = 0.0; o.DHFlxDTs[n] = 0.0;
         }
     }
 }
 
+// one column, fast arithmetic with the IEEE re-evaluation when a fast path was not acceptable
 __device__ __forceinline__ void bulk_column(const BulkIn &in, double sig1, BulkOut &o)
 {
     BulkMid mid;
-    bulk_fluxes(in, sig1, o, mid);
-    bulk_implicit(in, mid, o);
+    FastArith fa;
+    bulk_fluxes(in, sig1, o, mid, fa);
+    bulk_implicit(in, mid, o, fa);
+    if (!fa.good()) {
+        IeeeArith ia;
+        bulk_fluxes(in, sig1, o, mid, ia);
+        bulk_implicit(in, mid, o, ia);
+    }
 }
 
 }  // namespace dccm

@@ -126,7 +126,8 @@ __device__ __forceinline__ void bulk_and_put(const SfcArgs &a, int m, int r, Bul
 
     BulkOut o;
     BulkMid mid;
-    bulk_fluxes(in, a.sig1, o, mid);
+    FastArith fa;                                         // branch-free division / sqrt, validity accumulated
+    bulk_fluxes(in, a.sig1, o, mid, fa);
 
     // packed put-side layers, row = layer * M + member
     const int64_t ld = (int64_t)M * a.sld;                // one layer of all members
@@ -137,7 +138,13 @@ __device__ __forceinline__ void bulk_and_put(const SfcArgs &a, int m, int r, Bul
     double rain, snow;
     late(in, rain, snow);
     po[2 * ld] = snow; po[3 * ld] = rain;
-    bulk_implicit(in, mid, o);
+    bulk_implicit(in, mid, o, fa);
+    if (!fa.good()) {                                     // exponent out of the fast paths' range somewhere: IEEE operators
+        IeeeArith ia;
+        bulk_fluxes(in, a.sig1, o, mid, ia);
+        bulk_implicit(in, mid, o, ia);
+        pa[0 * ld] = o.LUwRFlx[2]; pa[1 * ld] = o.SUwRFlx[2]; pa[4 * ld] = o.SfcAlbedo3;
+    }
 
     pa[2 * ld] = o.SenHFlx[2]; pa[3 * ld] = o.QVapMFlx[2];
 #pragma unroll

@@ -176,6 +176,13 @@ typedef struct dccm_sfc_fields {
 int dccm_bulkflux_device(int nx, int ny, int ld, int64_t off, int64_t slot_stride,
                          const dccm_sfc_fields *f, double sig1, void *stream);
 
+/* Self-test of the branch-free fp64 division / reciprocal / square root the bulk-flux kernels use
+ * (csrc/dccm_bulkflux.cuh, FastArith): evaluates a[i]/b[i], 1/b[i], sqrt(|a[i]|) both ways on the device.
+ * mismatches = accepted fast results whose bits differ from the plain operator (must be 0);
+ * rejected = operations outside the fast paths' exponent range (re-evaluated with plain operators). */
+int dccm_selftest_fast_arith_device(const double *d_a, const double *d_b, int64_t n,
+                                    int64_t *mismatches, int64_t *rejected);
+
 /* ------------------------------------------------------------------ fused surface step (K1+K2)
  * The surface component's whole coupling step, get -> bulk flux -> put, in one kernel:
  * replaces jcup_get_data x16 -> interpolate_data -> unpack (ref sfc/dccm_sfc_mod.f90:865-881,

@@ -8,3 +8,8 @@ for v in ${2:-1:5 1:6 1:4 0:5}; do
   DCCM_SFC_STAGED=$st DCCM_SFC_MINB=$mb timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu > $OUT/sfc_s${st}_b$mb.json 2>$OUT/err_s${st}_b$mb.log
   python -c "import json; d=json.load(open('$OUT/sfc_s${st}_b$mb.json')); print('staged',$st,'minb',$mb,d['part_ms'], d['value'])" || tail -5 $OUT/err_s${st}_b$mb.log
 done
+if [ -n "$3" ]; then   # one ncu --set full capture of the fused surface kernel (third launch: after warm-up)
+  DCCM_SFC_STAGED=${3%%:*} DCCM_SFC_MINB=${3##*:} timeout 600 ncu --set full --clock-control none --import-source on \
+      -k regex:'sfc_exchange' -s 3 -c 1 -o $OUT/sfc_prof python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > $OUT/ncu.log 2>&1
+  tail -2 $OUT/ncu.log
+fi

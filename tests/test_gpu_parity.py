@@ -143,6 +143,35 @@ def test_remap_device_resident_equals_host(gpu, orc, dccm, S):
 
 # ------------------------------------------------------------------ K2 bulk flux
 
+def test_branch_free_division_and_sqrt_match_the_operators_bitwise(gpu, dccm):
+    """FastArith (the compiler's own fast-path sequences without the per-operation branch) against `/`, `1.0/x`
+    and `sqrt` on the device: every accepted result has the operator's bits; operands with extreme exponents,
+    zeros, infinities and NaN are rejected (and then take the IEEE re-evaluation), never wrong."""
+    import ctypes as C
+    import torch
+    L = dccm._lib
+    g = torch.Generator(device=gpu); g.manual_seed(1234)
+    n = 1 << 22
+    def draw(spread):
+        m = torch.rand(n, generator=g, device=gpu, dtype=torch.float64) + 1.0
+        e = torch.randint(-spread, spread + 1, (n,), generator=g, device=gpu)
+        s = torch.randint(0, 2, (n,), generator=g, device=gpu, dtype=torch.float64) * 2.0 - 1.0
+        return torch.ldexp(m * s, e)
+    for spread, max_rej in ((40, 0), (300, None), (1070, None)):
+        a, b = draw(spread), draw(spread)
+        if spread == 1070:      # specials
+            a[:8] = torch.tensor([0.0, -0.0, float("inf"), float("nan"), 1.0, 1.0, 5e-324, 1e308], device=gpu)
+            b[:8] = torch.tensor([1.0, 1.0, 1.0, 1.0, 0.0, float("inf"), 3.0, 1e-308], device=gpu)
+        bad, rej = C.c_int64(-1), C.c_int64(-1)
+        L.check(L.lib().dccm_selftest_fast_arith_device(L.tptr(a), L.tptr(b), n, C.byref(bad), C.byref(rej)))
+        print(f"exponent spread 2^+-{spread}: {rej.value} of {3 * n} operations rejected, {bad.value} mismatches")
+        assert bad.value == 0
+        if max_rej is not None:
+            assert rej.value <= max_rej
+        if spread == 1070:
+            assert rej.value > 0
+
+
 def _bulk_case(S, dccm, im, jm):
     from test_oracle_kat import _bulk_inputs
     g = dccm.tables.get_LonLatGrid(im, jm)
@@ -430,7 +459,8 @@ def test_fused_surface_kernel_staged_and_direct_forms_bit_exact(gpu, orc, dccm, 
                     assert torch.equal(ex.s2o, want["s2o"]), tag + " s2o"
                     if full:
                         for k, v in ex.sfc_out.items():
-                            assert torch.equal(v, want_full[k]), tag + " " + k
+                            rows = 2 * M if k in ("SfcHFlx_ns", "SfcHFlx_sr", "DSfcHFlxDTs") else v.shape[0]   # 2-slot arrays
+                            assert torch.equal(v[:rows], want_full[k][:rows]), tag + " " + k
                         assert torch.equal(ex.s_obil, want_full["s_obil"]), tag
                         assert torch.equal(ex.s_ocons, want_full["s_ocons"]), tag
     finally:
