@@ -112,7 +112,7 @@ struct FastArith {
         double s;
         asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(s) : "d"(x));   // MUFU.RSQ64H on the high word
         const int lo = __double2hiint(x) - 0x03500000;
-        ok = ok && ((unsigned)lo < 0x7ca00000u);
+        ok = ok && ((unsigned)lo < 0x7ca00000u || x == 0.0);      // sqrt(+-0) = +-0 (calm wind) is taken here too
         const double r0 = __hiloint2double(__double2hiint(s), lo);
         double t = __dmul_rn(r0, r0);
         t = fma(x, -t, 1.0);
@@ -122,7 +122,7 @@ struct FastArith {
         const double g = __dmul_rn(x, r);
         const double rh = __hiloint2double(__double2hiint(r) - 0x00100000, __double2loint(r));
         const double rem = fma(g, -g, x);
-        return fma(rem, rh, g);
+        return x == 0.0 ? x : fma(rem, rh, g);
     }
 };
 
@@ -306,20 +306,36 @@ __device__ __forceinline__ void bulk_implicit(const BulkIn &in, const BulkMid &m
         }
     }
 
-    // ---- net heat fluxes and dF/dTs for ocean / sea ice (:384-415) ----
+    // ---- net non-solar heat flux for ocean / sea ice (:384-400); the parts of that block that do not
+    //      depend on the implicit update are in bulk_static_net ----
 #pragma unroll
     for (int n = 0; n < 2; n++) {
         const bool flag = (n == 0) ? true : (Frac[n] > 1e-12);
+        if (flag) o.HFlx_ns[n] = +o.LUwRFlx[n] - in.LDwRFlx + o.LatHFlx[n] + o.SenHFlx[n];
+        else o.HFlx_ns[n] = 0.0;
+    }
+}
+
+// The statements of the net-flux block (:384-415) that only need phase-1 values: net solar flux and
+// dF/dTs.  Separate so that a caller can evaluate and store them before it fetches the phase-2 inputs.
+template <class Arith>
+__device__ __forceinline__ void bulk_static_net(const BulkIn &in, const BulkMid &mid, BulkOut &o, Arith &ar)
+{
+    using namespace sfc;
+    const double LatentHeatLocal[2] = {LatentHeat, LatentHeat + LatentHeatFusion};
+    const double HumdCoef = 1.0;
+#pragma unroll
+    for (int n = 0; n < 2; n++) {
+        const bool flag = (n == 0) ? true : (mid.Frac[n] > 1e-12);
         if (flag) {
-            o.HFlx_ns[n] = +o.LUwRFlx[n] - in.LDwRFlx + o.LatHFlx[n] + o.SenHFlx[n];
             o.HFlx_sr[n] = o.SUwRFlx[n] - in.SDwRFlx;
             const double t = in.SfcTemp[n];
             o.DHFlxDTs[n] = +4.0 * StB * (t * t * t)
                           + CpDry * o.TempTC[n]
                           + LatentHeatLocal[n] * HumdCoef * o.QVapTC[n]
-                            * ar.div(LatentHeatLocal[n] * QVapSat[n], GasRWet * (t * t));
+                            * ar.div(LatentHeatLocal[n] * mid.QVapSat[n], GasRWet * (t * t));
         } else {
-            o.HFlx_ns[n] = 0.0; o.HFlx_sr[n] = 0.0; o.DHFlxDTs[n] = 0.0;
+            o.HFlx_sr[n] = 0.0; o.DHFlxDTs[n] = 0.0;
         }
     }
 }
@@ -330,10 +346,12 @@ __device__ __forceinline__ void bulk_column(const BulkIn &in, double sig1, BulkO
     BulkMid mid;
     FastArith fa;
     bulk_fluxes(in, sig1, o, mid, fa);
+    bulk_static_net(in, mid, o, fa);
     bulk_implicit(in, mid, o, fa);
     if (!fa.good()) {
         IeeeArith ia;
         bulk_fluxes(in, sig1, o, mid, ia);
+        bulk_static_net(in, mid, o, ia);
         bulk_implicit(in, mid, o, ia);
     }
 }

@@ -29,6 +29,8 @@
 // Both give the same bits (tests/test_gpu_parity.py).
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "dccm_bulkflux.cuh"
 #include "dccm_remap_internal.h"
 
@@ -53,6 +55,8 @@ struct SfcArgs {
     int64_t nA, nO, nS, sld;      // sld: cells per (layer, member) row of s2a / s2o (>= nS)
     int M;
     double sig1;
+    int *redo;                    // [0] cells listed, [1] CTAs of the redo kernel done, [2..] (member, cell) pairs
+    int redo_cap;
 };
 
 // One destination row of one table, D layers.  The row's (col, w) pairs are fetched CH at a
@@ -113,11 +117,89 @@ __device__ __forceinline__ void gather(const Csr &t, int r, const SrcSeg &src, i
     }
 }
 
+// The two ocean-side tables of one cell (CSR: ocean and exchange-grid longitudes differ), software-pipelined.
+// A CSR gather is three dependent global round trips (row pointers -> (col, w) pairs -> source values); done
+// table after table that is six, and they were 35 % of the fused kernel's stall samples.  Here the row pointers
+// of BOTH tables are requested first (rows()), then the first CH pairs of both (pairs()), then all the source
+// values (finish()) -- three round trips in total, and the staged kernel slots its TMA issue between them.
+// Rows longer than CH entries (rare: CH = 4 covers bilinear rows and nearly all conservative ones) continue
+// with the plain loop.  Accumulation order per table and per layer is table order, as everywhere.
+template <bool SEG>
+struct OceanGather {
+    static constexpr int CH = 4;
+    int kb0, kb1, kc0, kc1;
+    int cb[CH], cc[CH];
+    double wb[CH], wc[CH];
+
+    __device__ __forceinline__ void rows(const Csr &tb, const Csr &tc, int r)
+    {
+        kb0 = __ldg(&tb.rowptr[r]); kb1 = __ldg(&tb.rowptr[r + 1]);
+        kc0 = __ldg(&tc.rowptr[r]); kc1 = __ldg(&tc.rowptr[r + 1]);
+    }
+    __device__ __forceinline__ void pairs(const Csr &tb, const Csr &tc)
+    {
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            const bool ob = kb0 + j < kb1, oc = kc0 + j < kc1;
+            cb[j] = ob ? __ldg(&tb.col[kb0 + j]) : 0;
+            wb[j] = ob ? __ldg(&tb.w[kb0 + j]) : 0.0;
+            cc[j] = oc ? __ldg(&tc.col[kc0 + j]) : 0;
+            wc[j] = oc ? __ldg(&tc.w[kc0 + j]) : 0.0;
+        }
+    }
+    template <int D>
+    static __device__ __forceinline__ void tail(const Csr &t, int k, int k1, const SrcSeg &src, int64_t o0,
+                                                int64_t lstride, double (&acc)[D])
+    {
+        for (; k < k1; k++) {
+            const double *p = cell<SEG>(src, __ldg(&t.col[k])) + o0;
+            const double ww = __ldg(&t.w[k]);
+#pragma unroll
+            for (int d = 0; d < D; d++) acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(p + d * lstride), ww));
+        }
+    }
+    __device__ __forceinline__ void finish(const Csr &tb, const Csr &tc, const SrcSeg &sb, const SrcSeg &sc,
+                                           int64_t n_src, int M, int m, double (&ob)[2], double (&oc)[3])
+    {
+        const int64_t o0 = (int64_t)m * n_src, lstride = (int64_t)M * n_src;
+        double vb[CH][2], vc[CH][3];
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            if (kb0 + j < kb1) {
+                const double *p = cell<SEG>(sb, cb[j]) + o0;
+#pragma unroll
+                for (int d = 0; d < 2; d++) vb[j][d] = __ldg(p + d * lstride);
+            }
+            if (kc0 + j < kc1) {
+                const double *p = cell<SEG>(sc, cc[j]) + o0;
+#pragma unroll
+                for (int d = 0; d < 3; d++) vc[j][d] = __ldg(p + d * lstride);
+            }
+        }
+        ob[0] = ob[1] = 0.0; oc[0] = oc[1] = oc[2] = 0.0;
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            if (kb0 + j < kb1) {
+#pragma unroll
+                for (int d = 0; d < 2; d++) ob[d] = __dadd_rn(ob[d], __dmul_rn(vb[j][d], wb[j]));
+            }
+            if (kc0 + j < kc1) {
+#pragma unroll
+                for (int d = 0; d < 3; d++) oc[d] = __dadd_rn(oc[d], __dmul_rn(vc[j][d], wc[j]));
+            }
+        }
+        tail<2>(tb, kb0 + CH, kb1, sb, o0, lstride, ob);
+        tail<3>(tc, kc0 + CH, kc1, sc, o0, lstride, oc);
+    }
+};
+
 // Steps 2 and 3 for one cell.  `in` holds what the flux evaluation needs; `late(in, rain, snow)` supplies
 // what only the implicit update and the put side need (ImplCplCoef1/2, LDwRFlx, rain, snow) -- a no-op when
 // they are already there, a shared-memory fetch in the staged kernel, which keeps them out of the
 // registers during the flux evaluation.  Layers that are final after phase 1 are stored at once.
-template <bool FULL, class Late>
+// With Arith = FastArith a cell whose operands left the fast paths' exponent range is appended to the redo
+// list (and its stores are overwritten by sfc_exchange_redo_kernel, Arith = IeeeArith, right after).
+template <class Arith, bool FULL, class Late>
 __device__ __forceinline__ void bulk_and_put(const SfcArgs &a, int m, int r, BulkIn &in, Late late)
 {
     const int M = a.M;
@@ -126,33 +208,33 @@ __device__ __forceinline__ void bulk_and_put(const SfcArgs &a, int m, int r, Bul
 
     BulkOut o;
     BulkMid mid;
-    FastArith fa;                                         // branch-free division / sqrt, validity accumulated
-    bulk_fluxes(in, a.sig1, o, mid, fa);
+    Arith ar;
+    bulk_fluxes(in, a.sig1, o, mid, ar);
+    bulk_static_net(in, mid, o, ar);
 
-    // packed put-side layers, row = layer * M + member
+    // packed put-side layers, row = layer * M + member; whatever is final is stored at once
     const int64_t ld = (int64_t)M * a.sld;                // one layer of all members
     double *pa = a.s2a + (int64_t)m * a.sld + r;
     double *po = a.s2o + (int64_t)m * a.sld + r;
     pa[0 * ld] = o.LUwRFlx[2]; pa[1 * ld] = o.SUwRFlx[2]; pa[4 * ld] = o.SfcAlbedo3;
+    po[1 * ld] = o.HFlx_sr[0]; po[8 * ld] = o.HFlx_sr[1];
+    po[10 * ld] = o.DHFlxDTs[0]; po[11 * ld] = o.DHFlxDTs[1];
 
     double rain, snow;
     late(in, rain, snow);
     po[2 * ld] = snow; po[3 * ld] = rain;
-    bulk_implicit(in, mid, o, fa);
-    if (!fa.good()) {                                     // exponent out of the fast paths' range somewhere: IEEE operators
-        IeeeArith ia;
-        bulk_fluxes(in, a.sig1, o, mid, ia);
-        bulk_implicit(in, mid, o, ia);
-        pa[0 * ld] = o.LUwRFlx[2]; pa[1 * ld] = o.SUwRFlx[2]; pa[4 * ld] = o.SfcAlbedo3;
+    bulk_implicit(in, mid, o, ar);
+    if (!ar.good()) {
+        const int slot = atomicAdd(&a.redo[0], 1);
+        if (slot < a.redo_cap) { a.redo[2 + 2 * slot] = m; a.redo[3 + 2 * slot] = r; }
     }
 
     pa[2 * ld] = o.SenHFlx[2]; pa[3 * ld] = o.QVapMFlx[2];
 #pragma unroll
     for (int k = 0; k < 4; k++) pa[(5 + k) * ld] = o.Del[k];
-    po[0 * ld] = o.HFlx_ns[0]; po[1 * ld] = o.HFlx_sr[0];
+    po[0 * ld] = o.HFlx_ns[0];
     po[4 * ld] = o.QVapMFlx[0]; po[5 * ld] = -o.WindStressX[2]; po[6 * ld] = -o.WindStressY[2];
-    po[7 * ld] = o.HFlx_ns[1]; po[8 * ld] = o.HFlx_sr[1]; po[9 * ld] = o.QVapMFlx[1];
-    po[10 * ld] = o.DHFlxDTs[0]; po[11 * ld] = o.DHFlxDTs[1];
+    po[7 * ld] = o.HFlx_ns[1]; po[9 * ld] = o.QVapMFlx[1];
 
     if (FULL) {
         const dccm_sfc_fields &f = a.full;
@@ -176,16 +258,10 @@ __device__ __forceinline__ void bulk_and_put(const SfcArgs &a, int m, int r, Bul
 }
 
 // ---- direct form: every layer gathered from global memory by the cell's own thread
-template <int MINB, bool SEG, bool FULL>
-__global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_kernel(const SfcArgs a)
+template <class Arith, bool SEG, bool FULL>
+__device__ __forceinline__ void direct_cell(const SfcArgs &a, int m, int r)
 {
-    const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    const int64_t nS = a.nS;
-    if (t >= nS * a.M) return;
-    const int m = (int)(t / nS);
-    const int r = (int)(t - (int64_t)m * nS);
     const int M = a.M;
-
     double ab[13], ac[4], ob[2], oc[3];
     gather<13, 2, SEG>(a.as_bil, r, a.a2s_bil, a.nA, M, m, ab);
     gather<4, 4, SEG>(a.as_cons, r, a.a2s_cons, a.nA, M, m, ac);
@@ -199,7 +275,45 @@ __global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_kernel(const SfcA
     in.LDwRFlx = ac[0]; in.SDwRFlx = ac[1];
     in.SfcTemp[0] = ob[0]; in.SfcTemp[1] = ob[1];
     in.SIceCon = oc[0]; in.SfcAlbedo[0] = oc[1]; in.SfcAlbedo[1] = oc[2];
-    bulk_and_put<FULL>(a, m, r, in, [&](BulkIn &, double &rain, double &snow) { rain = ac[2]; snow = ac[3]; });
+    bulk_and_put<Arith, FULL>(a, m, r, in, [&](BulkIn &, double &rain, double &snow) { rain = ac[2]; snow = ac[3]; });
+}
+
+template <int MINB, bool SEG, bool FULL>
+__global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_kernel(const SfcArgs a)
+{
+    const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t nS = a.nS;
+    if (t >= nS * a.M) return;
+    const int m = (int)(t / nS);
+    direct_cell<FastArith, SEG, FULL>(a, m, (int)(t - (int64_t)m * nS));
+}
+
+// ---- redo: the cells the fast arithmetic did not accept (normally none), again with the plain IEEE
+// operators; launched after either form.  More cells than the list holds: every cell is redone.
+// The last CTA to finish clears the list for the next call.
+template <bool SEG, bool FULL>
+__global__ void __launch_bounds__(kThreads) sfc_exchange_redo_kernel(const SfcArgs a)
+{
+    const int listed = a.redo[0];
+    if (listed > 0) {
+        const int64_t stride = (int64_t)gridDim.x * kThreads;
+        const int64_t t0 = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+        if (listed <= a.redo_cap) {
+            for (int64_t t = t0; t < listed; t += stride)
+                direct_cell<IeeeArith, SEG, FULL>(a, a.redo[2 + 2 * t], a.redo[3 + 2 * t]);
+        } else {
+            const int64_t nS = a.nS;
+            for (int64_t t = t0; t < nS * a.M; t += stride) {
+                const int m = (int)(t / nS);
+                direct_cell<IeeeArith, SEG, FULL>(a, m, (int)(t - (int64_t)m * nS));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(&a.redo[1], 1) == (int)gridDim.x - 1) { a.redo[0] = 0; a.redo[1] = 0; __threadfence(); }
+        }
+    }
 }
 
 // ---- staged form: atmosphere rows brought to shared memory by TMA bulk copies
@@ -330,6 +444,12 @@ __global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_staged_kernel(con
     const int nact = min(kThreads, g.nxd - i0);
     const int M = a.M;
 
+    // ocean / sea-ice side: in flight while the atmosphere tiles are planned, issued and land
+    const int r = jD * g.nxd + i0 + tid;
+    const bool ocsr = a.os_bil.kind == 0 && a.os_cons.kind == 0;
+    OceanGather<SEG> og;
+    if (ocsr && tid < nact) og.rows(a.os_bil, a.os_cons, r);
+
     if (tid < 32) {
         if (tid == 0) mbar_init(mbar, 1);
         const StagePlan pb = stage_plan<13>(a.as_bil, g.dmin_bil, g.dmax_bil, jD, i0, nact, zs[0], tid);
@@ -341,12 +461,15 @@ __global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_staged_kernel(con
         stage_issue<4, SEG>(a.as_cons, pc, zs[1], a.a2s_cons, a.nA, M, m, tile_cons, mbar, tid);
     }
 
-    // ocean / sea-ice side: direct gathers, in flight while the atmosphere tiles land
-    const int r = jD * g.nxd + i0 + tid;
     double ob[2], oc[3];
     if (tid < nact) {
-        gather<2, 4, SEG>(a.os_bil, r, a.o2s_bil, a.nO, M, m, ob);
-        gather<3, 4, SEG>(a.os_cons, r, a.o2s_cons, a.nO, M, m, oc);
+        if (ocsr) {
+            og.pairs(a.os_bil, a.os_cons);
+            og.finish(a.os_bil, a.os_cons, a.o2s_bil, a.o2s_cons, a.nO, M, m, ob, oc);
+        } else {
+            gather<2, 4, SEG>(a.os_bil, r, a.o2s_bil, a.nO, M, m, ob);
+            gather<3, 4, SEG>(a.os_cons, r, a.o2s_cons, a.nO, M, m, oc);
+        }
     }
     __syncthreads();                       // stencil records + barrier initialisation visible to every warp
     mbar_wait(mbar, 0);                    // tiles complete (every thread waits: no copy outlives the CTA)
@@ -362,7 +485,7 @@ __global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_staged_kernel(con
     }
     in.SfcTemp[0] = ob[0]; in.SfcTemp[1] = ob[1];
     in.SIceCon = oc[0]; in.SfcAlbedo[0] = oc[1]; in.SfcAlbedo[1] = oc[2];
-    bulk_and_put<FULL>(a, m, r, in, [&](BulkIn &q, double &rain, double &snow) {
+    bulk_and_put<FastArith, FULL>(a, m, r, in, [&](BulkIn &q, double &rain, double &snow) {
         asm volatile("" ::: "memory");        // keep these shared-memory reads after the flux evaluation
         double c[8], l[1], p[2];
         staged_accumulate<13, 5, 8>(zs[0], tile_bil, tid, c);
@@ -436,6 +559,7 @@ extern "C" int dccm_sfc_exchange_seg_device(const dccm_remap *as_bil, const dccm
     a.as_bil = csr_of(as_bil); a.as_cons = csr_of(as_cons); a.os_bil = csr_of(os_bil); a.os_cons = csr_of(os_cons);
     a.a2s_bil = seg_of(sa2s_bil); a.a2s_cons = seg_of(sa2s_cons); a.o2s_bil = seg_of(so2s_bil); a.o2s_cons = seg_of(so2s_cons);
     a.s2a = s2a; a.s2o = s2o;
+    a.redo = as_bil->d_redo; a.redo_cap = dccm_remap::kRedoCap;
     a.has_full = full ? 1 : 0;
     if (full) a.full = *full; else memset(&a.full, 0, sizeof a.full);
     if (s_ld != 0 && s_ld < nS) return fail(DCCM_ERR_ARG, "dccm_sfc_exchange: s_ld < surface cells");
@@ -505,6 +629,18 @@ extern "C" int dccm_sfc_exchange_seg_device(const dccm_remap *as_bil, const dccm
         default: DCCM_LAUNCH_DIRECT(5, false); break;
         }
 #undef DCCM_LAUNCH_DIRECT
+    }
+    DCCM_CUDA_TRY(cudaGetLastError());
+    // cells outside the fast arithmetic's exponent range (normally none): plain IEEE operators
+    {
+        const unsigned rgrid = (unsigned)std::min<int64_t>((n + kThreads - 1) / kThreads, 4 * (int64_t)num_sms());
+        if (seg) {
+            if (a.has_full) sfc_exchange_redo_kernel<true, true><<<rgrid, kThreads, 0, st>>>(a);
+            else sfc_exchange_redo_kernel<true, false><<<rgrid, kThreads, 0, st>>>(a);
+        } else {
+            if (a.has_full) sfc_exchange_redo_kernel<false, true><<<rgrid, kThreads, 0, st>>>(a);
+            else sfc_exchange_redo_kernel<false, false><<<rgrid, kThreads, 0, st>>>(a);
+        }
     }
     DCCM_CUDA_TRY(cudaGetLastError());
     return DCCM_OK;

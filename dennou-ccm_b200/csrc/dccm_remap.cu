@@ -242,7 +242,12 @@ extern "C" int dccm_remap_create_lonlat(int64_t nops, const int32_t *send_index,
     if (rc) return rc;
     dccm_remap *h = new dccm_remap();
     h->n_send = n_send; h->n_recv = n_recv; h->nnz = nops; h->max_row_nnz = maxnnz;
-    cudaError_t e;
+    cudaError_t e = cudaMalloc(&h->d_redo, sizeof(int) * (2 + 2 * (size_t)dccm_remap::kRedoCap));
+    if (e == cudaSuccess) e = cudaMemset(h->d_redo, 0, sizeof(int) * 2);
+    if (e != cudaSuccess) {
+        dccm_remap_destroy(h);
+        return fail(DCCM_ERR_CUDA, "dccm_remap_create: %s", cudaGetErrorString(e));
+    }
     if (gnxs > 0 && gnxr > 0 && n_send % gnxs == 0 && n_recv % gnxr == 0 && nops > 0) {
         std::vector<int32_t> zptr, zdi, zjs;
         std::vector<double> zw;
@@ -302,7 +307,7 @@ extern "C" void dccm_remap_destroy(dccm_remap *h)
             it = (it->second == h) ? g_registry.erase(it) : std::next(it);
     }
     cudaFree(h->d_rowptr); cudaFree(h->d_col); cudaFree(h->d_w);
-    cudaFree(h->d_zptr); cudaFree(h->d_zdj); cudaFree(h->d_zw);
+    cudaFree(h->d_zptr); cudaFree(h->d_zdj); cudaFree(h->d_zw); cudaFree(h->d_redo);
     h->send_buf.release(); h->recv_buf.release();
     delete h;
 }

@@ -43,5 +43,9 @@ struct dccm_remap {
     // surface kernel): longest stencil, most distinct source rows in one stencil, and the range of
     // the longitude offsets taken as signed shifts (di > nxs/2 is a westward neighbour)
     int z_max_len = 0, z_max_rows = 0, z_dmin = 0, z_dmax = 0;
+    // fused surface kernel: cells to re-evaluate with plain IEEE operators (csrc/dccm_exchange.cu); the list of
+    // the A->S bilinear handle is the one used.  Allocated at creation (never inside a stream capture).
+    static constexpr int kRedoCap = 16384;
+    int *d_redo = nullptr;         // [count, done, (member, cell) x kRedoCap]
     dccm::DevBuf send_buf, recv_buf;
 };

@@ -469,6 +469,47 @@ def test_fused_surface_kernel_staged_and_direct_forms_bit_exact(gpu, orc, dccm, 
     assert forms[:6] == [1] * 6 and forms[6:] == [0] * 6, forms
 
 
+@pytest.mark.parametrize("how", ["few", "all"])
+def test_fused_surface_kernel_redo_list_for_out_of_range_operands(gpu, orc, dccm, S, how):
+    """Cells whose divisions leave the exponent range of the branch-free arithmetic (denormal pressure here) are
+    listed by the fused kernel and re-evaluated with the plain IEEE operators by the redo kernel: same bits --
+    infinities and NaN included -- as the unfused sequence.  "all": more cells than the list holds (every cell
+    is redone); a second, clean call afterwards shows the list was cleared."""
+    import torch
+    X = importlib.import_module("dennou-ccm_b200.exchange")
+    L = dccm._lib
+    A, O, Sx = pair(orc, dccm, "T106_1deg")
+    tabs = X.build_tables(A, O, Sx)
+    K = 8
+    tt = lambda d: {k: torch.as_tensor(v, device=gpu).contiguous() for k, v in d.items()}
+    col, atm, ocn = tt(S.column_inputs(np, A, K, 1)), tt(S.atm_surface_fields(np, A)), tt(S.ocn_surface_fields(np, O))
+    clean = {k: v.clone() for k, v in atm.items()}
+    if how == "few":
+        atm["SfcPress"][1000:1003] = 1e-310
+        atm["WindU"][5000] = 0.0; atm["WindV"][5000] = 0.0        # calm: sqrt(0) stays on the fast path
+        atm["SfcAirTemp"][20000] = float("inf")
+    else:
+        atm["SfcPress"][:] = 1e-310
+    same = lambda a, b: torch.equal(torch.nan_to_num(a, nan=1.25e300), torch.nan_to_num(b, nan=1.25e300))
+    ex = X.SurfaceExchange(A, O, Sx, K, 1, 1, tabs=tabs, device=gpu)
+    try:
+        for inputs in (atm, clean):
+            ex.set_inputs(col, {k: v[None] for k, v in inputs.items()}, {k: v[None] for k, v in ocn.items()})
+            ex.forward()
+            ex.remap_to_sfc(); ex.bulk(); ex.pack_sfc()
+            torch.cuda.synchronize()
+            want = (ex.s2a.clone(), ex.s2o.clone())
+            assert inputs is clean or not bool(torch.isfinite(want[1]).all())
+            for staged in (1, 0):
+                L.check(L.lib().dccm_sfc_exchange_config(staged, 5))
+                ex.s2a.zero_(); ex.s2o.zero_()
+                ex.sfc_fused()
+                torch.cuda.synchronize()
+                assert same(ex.s2a, want[0]) and same(ex.s2o, want[1]), (how, staged, inputs is clean)
+    finally:
+        L.check(L.lib().dccm_sfc_exchange_config(1, 5))
+
+
 def test_exchange_ensemble_members_match_single_runs(gpu, orc, dccm, S):
     """BASELINE config 2: members batched along the layer axis share the tables; member m of the
     batch equals a single-member run on member m's inputs, bit for bit."""
