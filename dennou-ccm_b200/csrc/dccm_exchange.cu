@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kThreads) sfc_exchange_redo_kernel(const SfcAr
 }
 
 // ---- staged form: atmosphere rows brought to shared memory by TMA bulk copies
-constexpr int kTileW = 132;        // doubles per staged source row: 128 cells + stencil reach (<= 2) + alignment slack
+constexpr int kTileW = 136;        // doubles per staged source row: 128 cells + stencil reach + alignment slack
 constexpr int kMaxEnt = 16;        // longest stencil the staged form takes (bilinear 4, conservative 1-3 (+pairs))
 constexpr int kStageHdr = 640;     // mbarrier + two ZStage records, then the 128-byte aligned tiles
 
@@ -444,9 +444,6 @@ __global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_staged_kernel(con
     const int nact = min(kThreads, g.nxd - i0);
     const int M = a.M;
 
-    if (tid == 0) mbar_init(mbar, 1);
-    __syncthreads();                       // barrier initialised; the only CTA-wide barrier, and nobody waits long at it
-
     // ocean / sea-ice side: in flight while the atmosphere tiles are planned, issued and land
     const int r = jD * g.nxd + i0 + tid;
     const bool ocsr = a.os_bil.kind == 0 && a.os_cons.kind == 0;
@@ -454,12 +451,12 @@ __global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_staged_kernel(con
     if (ocsr && tid < nact) og.rows(a.os_bil, a.os_cons, r);
 
     if (tid < 32) {
+        if (tid == 0) mbar_init(mbar, 1);
         const StagePlan pb = stage_plan<13>(a.as_bil, g.dmin_bil, g.dmax_bil, jD, i0, nact, zs[0], tid);
         const StagePlan pc = stage_plan<4>(a.as_cons, g.dmin_cons, g.dmax_cons, jD, i0, nact, zs[1], tid);
-        __syncwarp();
-        // the arrive releases the stencil records written above to whoever completes a wait on the barrier
         if (tid == 0)
             mbar_arrive_expect_tx(mbar, 8u * (uint32_t)(pb.nslots * 13 * (pb.b - pb.a) + pc.nslots * 4 * (pc.b - pc.a)));
+        __syncwarp();
         stage_issue<13, SEG>(a.as_bil, pb, zs[0], a.a2s_bil, a.nA, M, m, tile_bil, mbar, tid);
         stage_issue<4, SEG>(a.as_cons, pc, zs[1], a.a2s_cons, a.nA, M, m, tile_cons, mbar, tid);
     }
@@ -474,7 +471,8 @@ __global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_staged_kernel(con
             gather<3, 4, SEG>(a.os_cons, r, a.o2s_cons, a.nO, M, m, oc);
         }
     }
-    mbar_wait(mbar, 0);                    // tiles and stencil records complete (every thread waits: no copy outlives the CTA)
+    __syncthreads();                       // stencil records + barrier initialisation visible to every warp
+    mbar_wait(mbar, 0);                    // tiles complete (every thread waits: no copy outlives the CTA)
     if (tid >= nact) return;
 
     BulkIn in;
