@@ -274,7 +274,7 @@ __device__ __forceinline__ void bulk_implicit(const BulkIn &in, const BulkMid &m
     const double LatentHeatLocal[2] = {LatentHeat, LatentHeat + LatentHeatFusion};
     const double HumdCoef = 1.0;
     const double Exner = mid.Exner, SfcExner = mid.SfcExner;
-    const double (&Frac)[2] = mid.Frac, (&QVapSat)[2] = mid.QVapSat;
+    const double (&Frac)[2] = mid.Frac;
 
     // ---- implicit surface-layer update (:353-382) ----
     {
