@@ -200,7 +200,7 @@ class SurfaceExchange:
             L.tptr(self.a2s_bil), L.tptr(self.a2s_cons), L.tptr(self.o2s_bil), L.tptr(self.o2s_cons),
             self.M, float(self.sig1), C.c_void_p(self.s2a.data_ptr() + 8 * self.offS),
             C.c_void_p(self.s2o.data_ptr() + 8 * self.offS), self.s2a.shape[1], full, L.current_stream()))
-        self.launches += 1
+        self.launches += 2            # the surface kernel + the (normally empty) IEEE redo kernel
 
     def remap_from_sfc(self):
         M = self.M

@@ -307,7 +307,7 @@ class PeerShardedExchange(ShardedExchange):
             self.rowlen["A"], self.rowlen["O"], 1, float(self.sig1),
             C.c_void_p(self.s2a.data_ptr() + 8 * self.offS), C.c_void_p(self.s2o.data_ptr() + 8 * self.offS),
             self.rowlen["S"], None, L.current_stream()))
-        self.launches += 1
+        self.launches += 2            # the surface kernel + the (normally empty) IEEE redo kernel
 
     def remap_from_sfc(self):
         import ctypes as C
