@@ -43,6 +43,15 @@ DESCR = {
 }
 
 
+def load_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/roofline_traffic.json); None when there is no capture for the workload."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))[workload]["traffic_bytes"])
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -388,7 +397,8 @@ def run_ours(args, rank, world):
         "part_gbs": {n: bytes_alg[n] / (part_ms[n] * 1e-3) / 1e9 for n in bytes_alg if n in part_ms},
         "part_algorithmic_gbytes": {n: bytes_alg[n] / 1e9 for n in bytes_alg if n in part_ms},
         "roofline": {"bound": "hbm", "kernel": "vdiff_forward_kernel", "achieved": fwd_gbs, "peak": peak,
-                     "unit": "GB/s", "frac": fwd_gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": fwd_gbs / peak, "traffic": load_traffic(wl) if world == 1 else None,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bytes_alg["fwd"]},
         "clocks": clocks, "gpu_launches": launches,
     }
