@@ -33,6 +33,18 @@ class SfcFields(C.Structure):
     _fields_ = [(n, vp) for n in _names]
 
 
+class AtmSfcFlx(C.Structure):
+    """dccm_atm_sfcflx of include/dccm_b200.h (device pointers, 27 in + 11 out)."""
+    _in = ["SurfMomFluxX", "SurfMomFluxY", "SurfVelTransCoef", "SurfTempTransCoef", "SurfQVapTransCoef",
+           "SurfHumidCoef", "DUDt1", "DVDt1", "DTempDtVDiff1", "DQVapDt1", "HeatFlux0", "QVapFlux0", "ExnerR0",
+           "ExnerZ1", "TempN1", "DSurfTempDt", "SnowFrac", "DQVapSatDTempOnLiq", "DQVapSatDTempOnSol",
+           "RadLDwFlux0", "RadLUwFlux0", "RadSDwFlux0", "RadSUwFlux0", "DelRadLDwFlux00", "DelRadLDwFlux01",
+           "DelRadLUwFlux00", "DelRadLUwFlux01"]
+    _out = ["TauXAtm", "TauYAtm", "SensAtm", "LatentAtm", "LDWRFlxAtm", "LUWRFlxAtm", "SDWRFlxAtm", "SUWRFlxAtm",
+            "SurfAirTemp", "DSurfLatentFlxDTs", "DSurfHFlxDTs"]
+    _fields_ = [(n, vp) for n in _in + _out]
+
+
 class SrcSeg(C.Structure):
     """dccm_src_seg: a send buffer whose boundary rows live in the neighbouring ranks' buffers."""
     _fields_ = [("lo", vp), ("own", vp), ("hi", vp), ("b0", C.c_int64), ("b1", C.c_int64)]
@@ -104,6 +116,9 @@ _SIGS = {
     "dccm_sfc_exchange_last_form": (C.c_int, []),
     "dccm_ocn_put_assemble_device": (C.c_int, [C.c_int64] + [vp] * 5 + [C.c_double, C.c_double, vp, vp, C.c_int64, vp]),
     "dccm_ocn_get_assemble_device": (C.c_int, [C.c_int64, vp, C.c_int64, C.c_double] + [vp] * 6 + [vp]),
+    "dccm_avg_accumulate_device": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp]),
+    "dccm_avg_finish_device": (C.c_int, [vp, C.c_int64, C.c_int, vp]),
+    "dccm_atm_store_surf_flx_device": (C.c_int, [C.c_int64, C.POINTER(AtmSfcFlx), C.c_double, C.c_double, C.c_double, vp]),
     "dccm_vdiff_create": (C.c_int, [C.c_int] * 5 + [C.c_double] * 4 + [C.POINTER(vp)]),
     "dccm_vdiff_destroy": (None, [vp]),
     "dccm_vdiff_set_mode": (C.c_int, [vp, C.c_int]),

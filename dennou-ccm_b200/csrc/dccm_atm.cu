@@ -1,0 +1,59 @@
+// dccm_atm.cu -- the atmosphere component's element-wise surface-flux bookkeeping after the backward
+// solve: dcpam_StoreAtmSurfFlxInfo, ref atm/dcpam_main_mod.f90:1040-1114.
+// Level-1 tendencies of the implicit solve correct the explicit surface fluxes; the results are what the
+// legacy 2-component glue ships to the ocean (ref atm/mod_atm.f90:653-667).  One thread per column, every
+// operand read once; operation order as written in the reference (the library is built with -fmad=false).
+// The saturation functions (xy_CalcDQVapSatDTempOnLiq/OnSol, DCPAM `saturate`) belong to the external model:
+// their values are inputs, the snow-fraction blend of :1068-1070 is done here.
+#include <cuda_runtime.h>
+
+#include "dccm_common.h"
+
+using namespace dccm;
+
+namespace {
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads)
+atm_store_surf_flx_kernel(int64_t n, const dccm_atm_sfcflx f, double LatentHeat, double CpDry, double delta_t)
+{
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= n) return;
+    const double dTs = f.DSurfTempDt[c], dT1 = f.DTempDtVDiff1[c];
+    const double ex0 = f.ExnerR0[c], ex1 = f.ExnerZ1[c];
+    const double velTC = f.SurfVelTransCoef[c], tempTC = f.SurfTempTransCoef[c], qTC = f.SurfQVapTransCoef[c];
+    const double humid = f.SurfHumidCoef[c];
+    const double snow = f.SnowFrac[c];
+    const double dqsat = (1.0 - snow) * f.DQVapSatDTempOnLiq[c] + snow * f.DQVapSatDTempOnSol[c];   // :1068-1070
+
+    f.TauXAtm[c] = f.SurfMomFluxX[c] - velTC * f.DUDt1[c] * 2.0 * delta_t;                           // :1078
+    f.TauYAtm[c] = f.SurfMomFluxY[c] - velTC * f.DVDt1[c] * 2.0 * delta_t;                           // :1079
+    f.SensAtm[c] = f.HeatFlux0[c] - CpDry * ex0 * tempTC * (dT1 / ex1 - dTs / ex0) * 2.0 * delta_t;  // :1081-1084
+    f.LatentAtm[c] = LatentHeat * (f.QVapFlux0[c]                                                    // :1085-1090
+                                   - humid * qTC * (f.DQVapDt1[c] - dqsat * dTs) * 2.0 * delta_t);
+    f.LDWRFlxAtm[c] = f.RadLDwFlux0[c] + 2.0 * delta_t * (dTs * f.DelRadLDwFlux00[c] + dT1 * f.DelRadLDwFlux01[c]);   // :1092-1095
+    f.LUWRFlxAtm[c] = f.RadLUwFlux0[c] + 2.0 * delta_t * (dTs * f.DelRadLUwFlux00[c] + dT1 * f.DelRadLUwFlux01[c]);   // :1096-1099
+    f.SDWRFlxAtm[c] = f.RadSDwFlux0[c];                                                              // :1101
+    f.SUWRFlxAtm[c] = f.RadSUwFlux0[c];                                                              // :1102
+    f.SurfAirTemp[c] = ex0 / ex1 * f.TempN1[c];                                                      // :1106
+    const double dlat = LatentHeat * humid * qTC * dqsat;                                            // :1107
+    f.DSurfLatentFlxDTs[c] = dlat;
+    f.DSurfHFlxDTs[c] = CpDry * tempTC + dlat - f.DelRadLDwFlux00[c];                                // :1108-1112
+}
+}  // namespace
+
+extern "C" int dccm_atm_store_surf_flx_device(int64_t n, const dccm_atm_sfcflx *f, double LatentHeat, double CpDry,
+                                              double DelTime, void *stream)
+{
+    if (!f) return fail(DCCM_ERR_ARG, "dccm_atm_store_surf_flx: null field table");
+    if (n < 1) return fail(DCCM_ERR_ARG, "dccm_atm_store_surf_flx: n must be >= 1");
+    const void *const *p = reinterpret_cast<const void *const *>(f);
+    for (size_t i = 0; i < sizeof(*f) / sizeof(void *); i++)
+        if (!p[i]) return fail(DCCM_ERR_ARG, "dccm_atm_store_surf_flx: field pointer %zu is NULL", i);
+    int rc = ensure_device();
+    if (rc) return rc;
+    atm_store_surf_flx_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0,
+                                reinterpret_cast<cudaStream_t>(stream)>>>(n, *f, LatentHeat, CpDry, DelTime);
+    DCCM_CUDA_TRY(cudaGetLastError());
+    return DCCM_OK;
+}

@@ -47,7 +47,46 @@ ocn_get_kernel(int64_t n, const double *__restrict__ r, int64_t ld, double DensF
     SfcHFlxAO0[c] = ns + sr;                                                      // :990
     DSfcHFlxAODTs[c] = r[c + 10 * ld];                                            // :991
 }
+// Jcup RECV_MODE='AVG' (ref ocn/dccm_ocn_mod.f90:652-672: every S->O / S->I variable): the receiver sees the
+// mean of what the sender put during the coupling interval.  acc = x on the first put of an interval,
+// acc = acc + x afterwards, acc = acc / count when the interval closes; layers are rows of length ld.
+__global__ void __launch_bounds__(kThreads)
+avg_accumulate_kernel(double *__restrict__ acc, const double *__restrict__ x, int64_t n, int first)
+{
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= n) return;
+    acc[c] = first ? x[c] : acc[c] + x[c];
+}
+
+__global__ void __launch_bounds__(kThreads) avg_finish_kernel(double *__restrict__ acc, int64_t n, double count)
+{
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= n) return;
+    acc[c] = acc[c] / count;
+}
 }  // namespace
+
+extern "C" int dccm_avg_accumulate_device(double *acc, const double *x, int64_t n, int first, void *stream)
+{
+    if (!acc || !x || n < 1) return fail(DCCM_ERR_ARG, "dccm_avg_accumulate: bad arguments");
+    int rc = ensure_device();
+    if (rc) return rc;
+    avg_accumulate_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        acc, x, n, first);
+    DCCM_CUDA_TRY(cudaGetLastError());
+    return DCCM_OK;
+}
+
+extern "C" int dccm_avg_finish_device(double *acc, int64_t n, int count, void *stream)
+{
+    if (!acc || n < 1 || count < 1) return fail(DCCM_ERR_ARG, "dccm_avg_finish: bad arguments");
+    int rc = ensure_device();
+    if (rc) return rc;
+    avg_finish_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        acc, n, (double)count);
+    DCCM_CUDA_TRY(cudaGetLastError());
+    return DCCM_OK;
+}
 
 extern "C" int dccm_ocn_put_assemble_device(int64_t n, const double *SeaSfcTemp, const double *SfcAlbedoAO,
                                             const double *SIceCon, const double *SIceSfcTempC, const double *SfcAlbedoAI,

@@ -22,3 +22,26 @@ def ocn_get_assemble(o_recv, DensFreshWater, n=None):
     L.check(L.lib().dccm_ocn_get_assemble_device(n, L.tptr(o_recv), ld, float(DensFreshWater),
                                                  *[L.tptr(out[k]) for k in names], L.current_stream()))
     return out
+
+
+class TimeAverage:
+    """Jcup RECV_MODE='AVG' of the S->O / S->I variables (ref ocn/dccm_ocn_mod.f90:652-672), device resident:
+    put() the surface component's layers at every surface step, get() the mean when the coupling interval
+    closes (and start the next interval).  The mean commutes with the (linear) remap, so averaging the 12 packed
+    S->O send layers once replaces twelve host-side Jcup buffers."""
+
+    def __init__(self, like):
+        import torch
+        self.acc = torch.zeros_like(like)
+        self.count = 0
+
+    def put(self, x):
+        L.check(L.lib().dccm_avg_accumulate_device(L.tptr(self.acc), L.tptr(x), x.numel(), int(self.count == 0),
+                                                   L.current_stream()))
+        self.count += 1
+
+    def get(self):
+        assert self.count > 0, "no put since the last get"
+        L.check(L.lib().dccm_avg_finish_device(L.tptr(self.acc), self.acc.numel(), self.count, L.current_stream()))
+        self.count = 0
+        return self.acc

@@ -280,6 +280,33 @@ int dccm_ocn_get_assemble_device(int64_t n, const double *o_recv, int64_t ld, do
                                  double *FreshWtFlxS0, double *FreshWtFlx0, double *WindStressXAI,
                                  double *WindStressYAI, double *SfcHFlxAO0, double *DSfcHFlxAODTs, void *stream);
 
+/* Jcup RECV_MODE='AVG' (ref ocn/dccm_ocn_mod.f90:652-672): time mean over the coupling interval of what the
+ * surface component put, kept on the device.  accumulate: acc = x (first != 0) or acc = acc + x;
+ * finish: acc = acc / count.  Jcup itself is not vendored in the reference tree; this is its documented
+ * behaviour restated (parity unpinned), the arithmetic is pinned by the oracle (orc_avg_*). */
+int dccm_avg_accumulate_device(double *acc, const double *x, int64_t n, int first, void *stream);
+int dccm_avg_finish_device(double *acc, int64_t n, int count, void *stream);
+
+/* ------------------------------------------------------------------ atmosphere side
+ * dcpam_StoreAtmSurfFlxInfo, ref atm/dcpam_main_mod.f90:1040-1114: surface fluxes corrected with the level-1
+ * tendencies of the implicit solve, element-wise over n columns (all pointers device, length n, none NULL).
+ * DQVapSatDTempOnLiq / OnSol come from DCPAM's `saturate` module (external); the snow-fraction blend is done here. */
+typedef struct dccm_atm_sfcflx {
+    /* in */
+    const double *SurfMomFluxX, *SurfMomFluxY, *SurfVelTransCoef, *SurfTempTransCoef, *SurfQVapTransCoef, *SurfHumidCoef;
+    const double *DUDt1, *DVDt1, *DTempDtVDiff1, *DQVapDt1;     /* level 1 of the tendencies (IndexH2OVap for q) */
+    const double *HeatFlux0, *QVapFlux0;                        /* level 0 of xyr_HeatFlux, xyrf_QMixFlux(:,:,0,IndexH2OVap) */
+    const double *ExnerR0, *ExnerZ1, *TempN1, *DSurfTempDt;
+    const double *SnowFrac, *DQVapSatDTempOnLiq, *DQVapSatDTempOnSol;
+    const double *RadLDwFlux0, *RadLUwFlux0, *RadSDwFlux0, *RadSUwFlux0;
+    const double *DelRadLDwFlux00, *DelRadLDwFlux01, *DelRadLUwFlux00, *DelRadLUwFlux01;
+    /* out */
+    double *TauXAtm, *TauYAtm, *SensAtm, *LatentAtm, *LDWRFlxAtm, *LUWRFlxAtm, *SDWRFlxAtm, *SUWRFlxAtm;
+    double *SurfAirTemp, *DSurfLatentFlxDTs, *DSurfHFlxDTs;
+} dccm_atm_sfcflx;
+int dccm_atm_store_surf_flx_device(int64_t n, const dccm_atm_sfcflx *f, double LatentHeat, double CpDry,
+                                   double DelTime, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

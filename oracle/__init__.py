@@ -61,6 +61,10 @@ def lib():
         L.orc_vdiff_get_diag.argtypes = [C.c_void_p, C.c_int, _f64p]
         L.orc_ocn_put_assemble.argtypes = [C.c_int64] + [_f64p] * 5 + [C.c_double, C.c_double, _f64p, _f64p]
         L.orc_ocn_get_assemble.argtypes = [C.c_int64] + [_f64p] * 8 + [C.c_double] + [_f64p] * 6
+        L.orc_avg_accumulate.argtypes = [_f64p, _f64p, C.c_int64, C.c_int]
+        L.orc_avg_finish.argtypes = [_f64p, C.c_int64, C.c_int]
+        L.orc_atm_store_surf_flx.argtypes = [C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                             C.c_double, C.c_double, C.c_double]
         L.orc_num_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -257,6 +261,35 @@ def ocn_get_assemble(ns, sr, dFdT, Snow, Rain, Evap, WSX, WSY, DensFreshWater):
     out = {k: np.full(n, np.nan) for k in names}
     lib().orc_ocn_get_assemble(n, *a, DensFreshWater, *[out[k] for k in names])
     return out
+
+
+ATM_SFCFLX_IN = ("SurfMomFluxX", "SurfMomFluxY", "SurfVelTransCoef", "SurfTempTransCoef", "SurfQVapTransCoef",
+                 "SurfHumidCoef", "DUDt1", "DVDt1", "DTempDtVDiff1", "DQVapDt1", "HeatFlux0", "QVapFlux0", "ExnerR0",
+                 "ExnerZ1", "TempN1", "DSurfTempDt", "SnowFrac", "DQVapSatDTempOnLiq", "DQVapSatDTempOnSol",
+                 "RadLDwFlux0", "RadLUwFlux0", "RadSDwFlux0", "RadSUwFlux0", "DelRadLDwFlux00", "DelRadLDwFlux01",
+                 "DelRadLUwFlux00", "DelRadLUwFlux01")
+ATM_SFCFLX_OUT = ("TauXAtm", "TauYAtm", "SensAtm", "LatentAtm", "LDWRFlxAtm", "LUWRFlxAtm", "SDWRFlxAtm", "SUWRFlxAtm",
+                  "SurfAirTemp", "DSurfLatentFlxDTs", "DSurfHFlxDTs")
+
+
+def atm_store_surf_flx(fields, LatentHeat, CpDry, DelTime):
+    """dcpam_StoreAtmSurfFlxInfo, ref atm/dcpam_main_mod.f90:1068-1112: dict of the 27 inputs -> dict of 11 outputs"""
+    a = [np.ascontiguousarray(fields[k], dtype=np.float64).ravel() for k in ATM_SFCFLX_IN]
+    n = a[0].size
+    out = {k: np.full(n, np.nan) for k in ATM_SFCFLX_OUT}
+    pin = (C.c_void_p * len(a))(*[x.ctypes.data for x in a])
+    pout = (C.c_void_p * len(out))(*[out[k].ctypes.data for k in ATM_SFCFLX_OUT])
+    lib().orc_atm_store_surf_flx(n, pin, pout, LatentHeat, CpDry, DelTime)
+    return out
+
+
+def time_average(puts):
+    """Jcup RECV_MODE='AVG' restated: mean of the fields put during one coupling interval, accumulated in put order"""
+    acc = np.full(np.asarray(puts[0]).size, np.nan)
+    for i, x in enumerate(puts):
+        lib().orc_avg_accumulate(acc, np.ascontiguousarray(x, dtype=np.float64).ravel(), acc.size, int(i == 0))
+    lib().orc_avg_finish(acc, acc.size, len(puts))
+    return acc.reshape(np.asarray(puts[0]).shape)
 
 
 def num_threads():

@@ -1002,3 +1002,45 @@ void orc_ocn_get_assemble(int64_t n, const double *ns, const double *sr, const d
         DSfcHFlxAODTs[c] = dFdT[c];
     }
 }
+
+/* Jcup RECV_MODE='AVG' restated (ref ocn/dccm_ocn_mod.f90:652-672 registers every S->O / S->I variable with it;
+ * Jcup itself is not part of the reference tree): running sum over the puts of an interval, divided by their number. */
+void orc_avg_accumulate(double *acc, const double *x, int64_t n, int first)
+{
+    for (int64_t c = 0; c < n; c++) acc[c] = first ? x[c] : acc[c] + x[c];
+}
+
+void orc_avg_finish(double *acc, int64_t n, int count)
+{
+    for (int64_t c = 0; c < n; c++) acc[c] = acc[c] / (double)count;
+}
+
+/* dcpam_StoreAtmSurfFlxInfo, ref atm/dcpam_main_mod.f90:1068-1112 (array syntax -> one loop; the saturation
+ * derivatives of :1063-1067 come from DCPAM's saturate module and are inputs).  in[] / out[] follow the member
+ * order of dccm_atm_sfcflx in include/dccm_b200.h. */
+void orc_atm_store_surf_flx(int64_t n, const double *const *in, double *const *out,
+                            double LatentHeat, double CpDry, double delta_t)
+{
+    const double *SurfMomFluxX = in[0], *SurfMomFluxY = in[1], *VelTC = in[2], *TempTC = in[3], *QVapTC = in[4],
+                 *HumidCoef = in[5], *DUDt1 = in[6], *DVDt1 = in[7], *DTempDt1 = in[8], *DQVapDt1 = in[9],
+                 *HeatFlux0 = in[10], *QVapFlux0 = in[11], *ExnerR0 = in[12], *ExnerZ1 = in[13], *TempN1 = in[14],
+                 *DSurfTempDt = in[15], *SnowFrac = in[16], *DQOnLiq = in[17], *DQOnSol = in[18],
+                 *RadLDw0 = in[19], *RadLUw0 = in[20], *RadSDw0 = in[21], *RadSUw0 = in[22],
+                 *DelLDw00 = in[23], *DelLDw01 = in[24], *DelLUw00 = in[25], *DelLUw01 = in[26];
+    for (int64_t c = 0; c < n; c++) {
+        const double dqsat = (1.0 - SnowFrac[c]) * DQOnLiq[c] + SnowFrac[c] * DQOnSol[c];
+        out[0][c] = SurfMomFluxX[c] - VelTC[c] * DUDt1[c] * 2.0 * delta_t;
+        out[1][c] = SurfMomFluxY[c] - VelTC[c] * DVDt1[c] * 2.0 * delta_t;
+        out[2][c] = HeatFlux0[c] - CpDry * ExnerR0[c] * TempTC[c]
+                    * (DTempDt1[c] / ExnerZ1[c] - DSurfTempDt[c] / ExnerR0[c]) * 2.0 * delta_t;
+        out[3][c] = LatentHeat * (QVapFlux0[c]
+                    - HumidCoef[c] * QVapTC[c] * (DQVapDt1[c] - dqsat * DSurfTempDt[c]) * 2.0 * delta_t);
+        out[4][c] = RadLDw0[c] + 2.0 * delta_t * (DSurfTempDt[c] * DelLDw00[c] + DTempDt1[c] * DelLDw01[c]);
+        out[5][c] = RadLUw0[c] + 2.0 * delta_t * (DSurfTempDt[c] * DelLUw00[c] + DTempDt1[c] * DelLUw01[c]);
+        out[6][c] = RadSDw0[c];
+        out[7][c] = RadSUw0[c];
+        out[8][c] = ExnerR0[c] / ExnerZ1[c] * TempN1[c];
+        out[9][c] = LatentHeat * HumidCoef[c] * QVapTC[c] * dqsat;
+        out[10][c] = CpDry * TempTC[c] + out[9][c] - DelLDw00[c];
+    }
+}

@@ -112,6 +112,12 @@ void orc_ocn_get_assemble(int64_t n, const double *ns, const double *sr, const d
                           double *FreshWtFlxS0, double *FreshWtFlx0, double *WSXAI, double *WSYAI,
                           double *SfcHFlxAO0, double *DSfcHFlxAODTs);
 
+/* ---- Jcup RECV_MODE='AVG' and dcpam_StoreAtmSurfFlxInfo (ref atm/dcpam_main_mod.f90:1068-1112) ---- */
+void orc_avg_accumulate(double *acc, const double *x, int64_t n, int first);
+void orc_avg_finish(double *acc, int64_t n, int count);
+void orc_atm_store_surf_flx(int64_t n, const double *const *in, double *const *out,
+                            double LatentHeat, double CpDry, double delta_t);
+
 int orc_num_threads(void);
 
 #ifdef __cplusplus

@@ -614,6 +614,47 @@ def test_ocn_glue_kernels_bit_exact(gpu, orc, dccm, S):
         assert np.array_equal(got[k].cpu().numpy(), want[k]), k
 
 
+def _atm_sfcflx_inputs(orc, n, seed=7):
+    rng = np.random.default_rng(seed)
+    f = {k: rng.normal(0.0, 1.0, n) for k in orc.ATM_SFCFLX_IN}
+    f["ExnerR0"] = 1.0 + 0.01 * rng.random(n); f["ExnerZ1"] = 0.99 + 0.01 * rng.random(n)
+    f["TempN1"] = 280.0 + 10.0 * rng.normal(size=n); f["SnowFrac"] = np.clip(rng.normal(0.3, 0.5, n), 0.0, 1.0)
+    for k in ("SurfVelTransCoef", "SurfTempTransCoef", "SurfQVapTransCoef"):
+        f[k] = 0.01 + 0.02 * rng.random(n)
+    f["SurfHumidCoef"] = np.ones(n)
+    return f
+
+
+def test_atm_surface_flux_bookkeeping_bit_exact(gpu, orc, dccm):
+    """dcpam_StoreAtmSurfFlxInfo (ref atm/dcpam_main_mod.f90:1068-1112) on the device."""
+    import torch
+    n = 128 * 64 + 37
+    f = _atm_sfcflx_inputs(orc, n)
+    want = orc.atm_store_surf_flx(f, 2.5e6, 1004.6, 1200.0)
+    got = dccm.dcpam_main_mod.dcpam_StoreAtmSurfFlxInfo({k: torch.as_tensor(v, device=gpu) for k, v in f.items()},
+                                                         2.5e6, 1004.6, 1200.0)
+    for k in want:
+        assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+    with pytest.raises(dccm.DccmError):
+        L = dccm._lib
+        L.check(L.lib().dccm_atm_store_surf_flx_device(n, L.AtmSfcFlx(), 1.0, 1.0, 1.0, None))     # NULL fields
+
+
+def test_time_average_of_surface_puts_bit_exact(gpu, orc, dccm, S):
+    """Jcup RECV_MODE='AVG' of the S->O layers: device accumulate / finish against the oracle, two intervals."""
+    import torch
+    O = dccm.tables.regular_LonLatGrid(72, 36)
+    avg = None
+    for interval, nput in enumerate((3, 1)):
+        puts = [S.generic_fields(np, O, 12) * (1.0 + 0.1 * k + interval) for k in range(nput)]
+        want = orc.time_average(puts)
+        for x in puts:
+            t = torch.as_tensor(np.ascontiguousarray(x), device=gpu)
+            avg = avg or dccm.dccm_ocn_mod.TimeAverage(t)
+            avg.put(t)
+        assert np.array_equal(avg.get().cpu().numpy(), want)
+
+
 @pytest.mark.parametrize("name", ["T21_Pl42", "T42_T42"])
 def test_legacy_two_component_exchange_bit_exact(gpu, orc, dccm, S, name):
     """the legacy A<->O topology the shipped exp/ configs run (12 a2o + 4 o2a layers,

@@ -349,3 +349,38 @@ def test_ocn_glue_known_answers(orc):
     assert o["FreshWtFlxS0"][0] == ((3e-5 + 1e-5) - 2.5e-5) / 1000.0 and o["FreshWtFlx0"][0] == o["FreshWtFlxS0"][0]
     assert o["SfcHFlxAO0"][0] == -150.0 and o["DSfcHFlxAODTs"][0] == 15.0
     assert o["WindStressXAI"][0] == 0.1 and o["WindStressYAI"][0] == -0.2
+
+
+def test_atm_surface_flux_bookkeeping_known_answers(orc):
+    """dcpam_StoreAtmSurfFlxInfo restated (ref atm/dcpam_main_mod.f90:1068-1112): with zero level-1 tendencies and
+    zero surface-temperature tendency every flux equals its explicit value; otherwise the hand-evaluated formulas."""
+    n = 5
+    one = np.ones(n)
+    f = {k: 0.0 * one for k in orc.ATM_SFCFLX_IN}
+    f.update(SurfMomFluxX=0.1 * one, SurfMomFluxY=-0.2 * one, HeatFlux0=15.0 * one, QVapFlux0=2e-5 * one,
+             RadLDwFlux0=300.0 * one, RadLUwFlux0=390.0 * one, RadSDwFlux0=200.0 * one, RadSUwFlux0=20.0 * one,
+             ExnerR0=1.0 * one, ExnerZ1=0.98 * one, TempN1=280.0 * one, SurfHumidCoef=one)
+    o = orc.atm_store_surf_flx(f, 2.5e6, 1004.6, 600.0)
+    assert np.array_equal(o["TauXAtm"], f["SurfMomFluxX"]) and np.array_equal(o["TauYAtm"], f["SurfMomFluxY"])
+    assert np.array_equal(o["SensAtm"], f["HeatFlux0"]) and np.array_equal(o["LatentAtm"], 2.5e6 * f["QVapFlux0"])
+    assert np.array_equal(o["LDWRFlxAtm"], f["RadLDwFlux0"]) and np.array_equal(o["SUWRFlxAtm"], f["RadSUwFlux0"])
+    assert np.array_equal(o["SurfAirTemp"], 1.0 / 0.98 * 280.0 * one)
+    f.update(SurfVelTransCoef=0.02 * one, DUDt1=1e-4 * one, SurfTempTransCoef=0.03 * one, DTempDtVDiff1=2e-4 * one,
+             DSurfTempDt=1e-4 * one, SurfQVapTransCoef=0.025 * one, DQVapDt1=1e-8 * one, SnowFrac=0.25 * one,
+             DQVapSatDTempOnLiq=6e-4 * one, DQVapSatDTempOnSol=7e-4 * one, DelRadLDwFlux00=0.5 * one, DelRadLDwFlux01=4.0 * one)
+    o = orc.atm_store_surf_flx(f, 2.5e6, 1004.6, 600.0)
+    dq = 0.75 * 6e-4 + 0.25 * 7e-4
+    assert o["TauXAtm"][0] == 0.1 - 0.02 * 1e-4 * 2.0 * 600.0
+    assert o["SensAtm"][0] == 15.0 - 1004.6 * 1.0 * 0.03 * (2e-4 / 0.98 - 1e-4 / 1.0) * 2.0 * 600.0
+    assert o["LatentAtm"][0] == 2.5e6 * (2e-5 - 1.0 * 0.025 * (1e-8 - dq * 1e-4) * 2.0 * 600.0)
+    assert o["LDWRFlxAtm"][0] == 300.0 + 2.0 * 600.0 * (1e-4 * 0.5 + 2e-4 * 4.0)
+    assert o["DSurfLatentFlxDTs"][0] == 2.5e6 * 1.0 * 0.025 * dq
+    assert o["DSurfHFlxDTs"][0] == 1004.6 * 0.03 + o["DSurfLatentFlxDTs"][0] - 0.5
+
+
+def test_time_average_is_the_mean_of_the_puts(orc):
+    rng = np.random.default_rng(3)
+    puts = [rng.normal(size=(12, 50)) for _ in range(4)]
+    got = orc.time_average(puts)
+    assert np.array_equal(got, (((puts[0] + puts[1]) + puts[2]) + puts[3]) / 4.0)
+    assert np.array_equal(orc.time_average(puts[:1]), puts[0])
