@@ -2,6 +2,8 @@
 // Replaces DSFCM_Util_SfcBulkFlux_Get (ref sfc/DSFCM_Util_SfcBulkFlux_mod.f90:108-439).
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "dccm_bulkflux.cuh"
 #include "dccm_common.h"
 
@@ -153,35 +155,54 @@ extern "C" int dccm_bulkflux_get_host(int IA, int JA,
     f.ImplCplCoef1 = dC1; f.ImplCplCoef2 = dC2; f.SfcTemp = dTs; f.SfcAlbedo = dAl; f.SIceCon = dIce;
     f.SfcHeight = dH; f.SfcPress = dPs;
 
-    cudaStream_t st = 0;
-    auto h2d = [&](double *dst, const double *src, size_t slots) {
-        return cudaMemcpyAsync(dst, src, sizeof(double) * N2 * slots, cudaMemcpyHostToDevice, st);
-    };
-    DCCM_CUDA_TRY(h2d(dWindU, WindU, 1)); DCCM_CUDA_TRY(h2d(dWindV, WindV, 1));
-    DCCM_CUDA_TRY(h2d(dT1, SfcAirTemp, 1)); DCCM_CUDA_TRY(h2d(dQ1, QVap1, 1));
-    DCCM_CUDA_TRY(h2d(dSDw, SDw, 1)); DCCM_CUDA_TRY(h2d(dLDw, LDw, 1));
-    DCCM_CUDA_TRY(h2d(dC1, Coef1, 4)); DCCM_CUDA_TRY(h2d(dC2, Coef2, 4));
-    DCCM_CUDA_TRY(h2d(dTs, SfcTemp, 3)); DCCM_CUDA_TRY(h2d(dAl, SfcAlbedo, 3));
-    DCCM_CUDA_TRY(h2d(dIce, SIceCon, 1)); DCCM_CUDA_TRY(h2d(dH, SfcHeight, 1)); DCCM_CUDA_TRY(h2d(dPs, SfcPress, 1));
-
+    // Interior rows move in chunks: chunk j+1 on its way in (H2D stream) while the kernel runs on chunk j and
+    // chunk j-1 is on its way out (D2H stream).  Inputs are whole rows of the (IA,JA) slots (contiguous), outputs
+    // the interior columns only -- halo cells of the caller's arrays are never written, as in the reference.
+    static cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
+    for (auto &ps : pipe)
+        if (!ps) DCCM_CUDA_TRY(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+    cudaStream_t sin = pipe[0], sk = pipe[1], sout = pipe[2];
     const int nx = IA - 2, ny = JA - 2;
-    rc = dccm_bulkflux_device(nx, ny, IA, (int64_t)IA + 1, (int64_t)N2, &f, Sig1Info[0], st);
-    if (rc) return rc;
-
-    // interior only, slot by slot
-    auto d2h = [&](double *dst, const double *src, int slot) {
-        const size_t o = (size_t)slot * N2 + IA + 1;
-        return cudaMemcpy2DAsync(dst + o, sizeof(double) * IA, src + o, sizeof(double) * IA,
-                                 sizeof(double) * nx, ny, cudaMemcpyDeviceToHost, st);
-    };
+    const char *env = getenv("DCCM_HOST_CHUNKS");
+    int nchunk = env ? std::max(1, atoi(env)) : ((size_t)nx * ny >= (1u << 19) ? 12 : 1);
+    nchunk = std::min(nchunk, ny);
+    std::vector<cudaEvent_t> ev(2 * (size_t)nchunk, nullptr);
+    struct EvGuard { std::vector<cudaEvent_t> &e; ~EvGuard() { for (auto x : e) if (x) cudaEventDestroy(x); } } guard{ev};
+    for (auto &e : ev) DCCM_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    struct { double *d; const double *h; int slots; } ins[] = {
+        {dWindU, WindU, 1}, {dWindV, WindV, 1}, {dT1, SfcAirTemp, 1}, {dQ1, QVap1, 1}, {dSDw, SDw, 1}, {dLDw, LDw, 1},
+        {dC1, Coef1, 4}, {dC2, Coef2, 4}, {dTs, SfcTemp, 2}, {dAl, SfcAlbedo, 2}, {dIce, SIceCon, 1}, {dH, SfcHeight, 1},
+        {dPs, SfcPress, 1}};
     struct { double *h; const double *d; int first, last; } outs[] = {
         {WSX, f.WindStressX, 0, 2}, {WSY, f.WindStressY, 0, 2}, {SenH, f.SenHFlx, 0, 2}, {QVapM, f.QVapMFlx, 0, 2},
         {LatH, f.LatHFlx, 0, 2}, {VelTC, f.SfcVelTransCoef, 0, 2}, {TempTC, f.SfcTempTransCoef, 0, 2},
         {QVapTC, f.SfcQVapTransCoef, 0, 2}, {Del, f.DelVarImplCPL, 0, 3}, {SUw, f.SUwRFlx, 0, 2}, {LUw, f.LUwRFlx, 0, 2},
         {HFns, f.SfcHFlx_ns, 0, 1}, {HFsr, f.SfcHFlx_sr, 0, 1}, {DHFDTs, f.DSfcHFlxDTs, 0, 1},
         {SfcTemp, f.SfcTemp, 2, 2}, {SfcAlbedo, f.SfcAlbedo, 2, 2}};
-    for (auto &o : outs)
-        for (int s = o.first; s <= o.last; s++) DCCM_CUDA_TRY(d2h(o.h, o.d, s));
-    DCCM_CUDA_TRY(cudaStreamSynchronize(st));
+    const int per = (ny + nchunk - 1) / nchunk;
+    for (int c = 0; c < nchunk; c++) {
+        const int j0 = c * per, j1 = std::min(ny, j0 + per);        // interior rows [j0, j1) = array rows j0+1 .. j1
+        if (j0 >= j1) continue;
+        const size_t row0 = (size_t)(j0 + 1) * IA, nrow = (size_t)(j1 - j0) * IA;
+        for (auto &i : ins)
+            for (int sl = 0; sl < i.slots; sl++)
+                DCCM_CUDA_TRY(cudaMemcpyAsync(i.d + sl * N2 + row0, i.h + sl * N2 + row0, sizeof(double) * nrow,
+                                              cudaMemcpyHostToDevice, sin));
+        DCCM_CUDA_TRY(cudaEventRecord(ev[2 * c], sin));
+        DCCM_CUDA_TRY(cudaStreamWaitEvent(sk, ev[2 * c], 0));
+        rc = dccm_bulkflux_device(nx, j1 - j0, IA, (int64_t)row0 + 1, (int64_t)N2, &f, Sig1Info[0], sk);
+        if (rc) return rc;
+        DCCM_CUDA_TRY(cudaEventRecord(ev[2 * c + 1], sk));
+        DCCM_CUDA_TRY(cudaStreamWaitEvent(sout, ev[2 * c + 1], 0));
+        for (auto &o : outs)
+            for (int sl = o.first; sl <= o.last; sl++) {
+                const size_t at = (size_t)sl * N2 + row0 + 1;
+                DCCM_CUDA_TRY(cudaMemcpy2DAsync(o.h + at, sizeof(double) * IA, o.d + at, sizeof(double) * IA,
+                                                sizeof(double) * nx, j1 - j0, cudaMemcpyDeviceToHost, sout));
+            }
+    }
+    DCCM_CUDA_TRY(cudaStreamSynchronize(sout));
+    DCCM_CUDA_TRY(cudaStreamSynchronize(sk));
+    DCCM_CUDA_TRY(cudaStreamSynchronize(sin));
     return DCCM_OK;
 }

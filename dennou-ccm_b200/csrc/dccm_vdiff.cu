@@ -23,6 +23,8 @@
 // <= a few ulp per level from the reference; verified to the 1e-12 tolerance).
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "dccm_common.h"
 
 using namespace dccm;
@@ -35,6 +37,7 @@ struct dccm_vdiff {
     int64_t coef_stride = 0;                                // 0 = NC
     double *bUV = nullptr, *bT = nullptr, *bQ = nullptr;   // swept diagonals, (NC, kmax)
     DevBuf in_buf, out_buf;                                 // scratch of the host entry points
+    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};     // H2D | kernel | D2H streams of the host entry points
 };
 
 namespace {
@@ -48,6 +51,7 @@ struct FwdArgs {
     double *DU, *DV, *DT, *DQ, *Coef1, *Coef2;
     double *bUV, *bT, *bQ;
     int64_t NC, cstride;          // cstride: slot stride of Coef1/Coef2 (>= NC)
+    int64_t c0, c1;               // columns [c0, c1) of this launch (host entry points pipeline over column chunks)
     int K, iq;
     double Grav, CpDry, GasRDry, DelTime;
 };
@@ -55,9 +59,9 @@ struct FwdArgs {
 template <int NQ, bool FAST>
 __global__ void __launch_bounds__(kThreads) vdiff_forward_kernel(const FwdArgs a)
 {
-    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t c = a.c0 + (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int64_t NC = a.NC;
-    if (c >= NC) return;
+    if (c >= a.c1) return;
     const int K = a.K;
     const double Grav = a.Grav, CpDry = a.CpDry, GasRDry = a.GasRDry;
     const double twodt = 2.0 * a.DelTime;
@@ -221,7 +225,7 @@ struct BwdArgs {
     double *DU, *DV, *DT, *DQ;
     const double *bUV, *bT, *bQ;
     const double *level1;
-    int64_t NC;
+    int64_t NC, c0, c1;           // columns [c0, c1) of this launch
     int K, iq;
     double DelTime;
 };
@@ -229,9 +233,9 @@ struct BwdArgs {
 template <int NQ>
 __global__ void __launch_bounds__(kThreads) vdiff_backward_kernel(const BwdArgs a)
 {
-    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t c = a.c0 + (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int64_t NC = a.NC;
-    if (c >= NC) return;
+    if (c >= a.c1) return;
     const int K = a.K;
     const double twodt = 2.0 * a.DelTime;
     // level 1: the surface-layer increment delivered by the surface component
@@ -338,6 +342,7 @@ extern "C" void dccm_vdiff_destroy(dccm_vdiff *h)
     if (!h) return;
     cudaFree(h->bUV); cudaFree(h->bT); cudaFree(h->bQ);
     h->in_buf.release(); h->out_buf.release();
+    for (cudaStream_t st : h->pipe) if (st) cudaStreamDestroy(st);
     delete h;
 }
 
@@ -356,40 +361,38 @@ extern "C" int dccm_vdiff_set_coef_stride(dccm_vdiff *h, int64_t slot_stride)
     return DCCM_OK;
 }
 
-extern "C" int dccm_vdiff_forward_device(dccm_vdiff *h,
+namespace {
+int forward_range(dccm_vdiff *h,
     const double *FX, const double *FY, const double *FH, const double *FQ,
     const double *Press, const double *zExner, const double *rExner,
     const double *VirTemp, const double *Height,
     const double *DiffV, const double *DiffT, const double *DiffQ,
-    double *DU, double *DV, double *DT, double *DQ, double *Coef1, double *Coef2, void *stream)
+    double *DU, double *DV, double *DT, double *DQ, double *Coef1, double *Coef2,
+    int64_t c0, int64_t c1, cudaStream_t st)
 {
-    if (!h) return fail(DCCM_ERR_ARG, "dccm_vdiff_forward: null handle");
     FwdArgs a;
     a.FX = FX; a.FY = FY; a.FH = FH; a.FQ = FQ; a.Press = Press; a.zExner = zExner; a.rExner = rExner;
     a.VirTemp = VirTemp; a.Height = Height; a.DiffV = DiffV; a.DiffT = DiffT; a.DiffQ = DiffQ;
     a.DU = DU; a.DV = DV; a.DT = DT; a.DQ = DQ; a.Coef1 = Coef1; a.Coef2 = Coef2;
     a.bUV = h->bUV; a.bT = h->bT; a.bQ = h->bQ;
-    a.NC = h->NC; a.K = h->kmax; a.iq = h->iq;
+    a.NC = h->NC; a.K = h->kmax; a.iq = h->iq; a.c0 = c0; a.c1 = c1;
     a.cstride = h->coef_stride > 0 ? h->coef_stride : h->NC;
     a.Grav = h->Grav; a.CpDry = h->CpDry; a.GasRDry = h->GasRDry; a.DelTime = h->DelTime;
-    const unsigned grid = (unsigned)((h->NC + kThreads - 1) / kThreads);
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)((c1 - c0 + kThreads - 1) / kThreads);
     if (h->fast) launch_forward<true>(h->ncmax, a, grid, st);
     else         launch_forward<false>(h->ncmax, a, grid, st);
     DCCM_CUDA_TRY(cudaGetLastError());
     return DCCM_OK;
 }
 
-extern "C" int dccm_vdiff_backward_device(dccm_vdiff *h, double *DU, double *DV, double *DT, double *DQ,
-                                          const double *level1, void *stream)
+int backward_range(dccm_vdiff *h, double *DU, double *DV, double *DT, double *DQ, const double *level1,
+                   int64_t c0, int64_t c1, cudaStream_t st)
 {
-    if (!h) return fail(DCCM_ERR_ARG, "dccm_vdiff_backward: null handle");
     BwdArgs a;
     a.DU = DU; a.DV = DV; a.DT = DT; a.DQ = DQ;
     a.bUV = h->bUV; a.bT = h->bT; a.bQ = h->bQ; a.level1 = level1;
-    a.NC = h->NC; a.K = h->kmax; a.iq = h->iq; a.DelTime = h->DelTime;
-    const unsigned grid = (unsigned)((h->NC + kThreads - 1) / kThreads);
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    a.NC = h->NC; a.K = h->kmax; a.iq = h->iq; a.DelTime = h->DelTime; a.c0 = c0; a.c1 = c1;
+    const unsigned grid = (unsigned)((c1 - c0 + kThreads - 1) / kThreads);
     switch (h->ncmax) {
     case 1: vdiff_backward_kernel<1><<<grid, kThreads, 0, st>>>(a); break;
     case 2: vdiff_backward_kernel<2><<<grid, kThreads, 0, st>>>(a); break;
@@ -402,6 +405,63 @@ extern "C" int dccm_vdiff_backward_device(dccm_vdiff *h, double *DU, double *DV,
     }
     DCCM_CUDA_TRY(cudaGetLastError());
     return DCCM_OK;
+}
+
+// Host entry points move their arguments in column chunks: chunk j+1 is on its way in (H2D stream) while the
+// kernel runs on chunk j (kernel stream) and chunk j-1 is on its way out (D2H stream); arrays keep the
+// reference layout (column fastest, level slowest), so a chunk of an array is a 2-D copy of `levels` rows.
+// PCIe is full duplex: the outputs ride for free under the inputs.  Pinned host arrays overlap; pageable ones
+// are staged by the driver and simply serialise.
+struct Pipe {
+    dccm_vdiff *h;
+    std::vector<cudaEvent_t> ev;
+    int nchunk;
+    int64_t NC;
+    explicit Pipe(dccm_vdiff *hh) : h(hh), NC(hh->NC)
+    {
+        const char *env = getenv("DCCM_HOST_CHUNKS");         // testing knob: force a chunk count on small problems
+        nchunk = env ? std::max(1, atoi(env)) : (NC >= (1 << 19) ? 12 : 1);
+        if ((int64_t)nchunk > (NC + 31) / 32) nchunk = (int)((NC + 31) / 32);
+    }
+    int init()
+    {
+        for (auto &st : h->pipe)
+            if (!st) DCCM_CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        ev.resize(2 * (size_t)nchunk);
+        for (auto &e : ev) DCCM_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        return DCCM_OK;
+    }
+    ~Pipe() { for (auto e : ev) if (e) cudaEventDestroy(e); }
+    void range(int j, int64_t &c0, int64_t &c1) const
+    {
+        const int64_t per = ((NC + nchunk - 1) / nchunk + 31) / 32 * 32;
+        c0 = std::min<int64_t>(NC, per * j); c1 = std::min<int64_t>(NC, per * (j + 1));
+    }
+    cudaError_t copy(double *dst, const double *src, int64_t c0, int64_t c1, size_t rows, cudaMemcpyKind kind, cudaStream_t st) const
+    {
+        return cudaMemcpy2DAsync(dst + c0, sizeof(double) * NC, src + c0, sizeof(double) * NC,
+                                 sizeof(double) * (size_t)(c1 - c0), rows, kind, st);
+    }
+};
+}  // namespace
+
+extern "C" int dccm_vdiff_forward_device(dccm_vdiff *h,
+    const double *FX, const double *FY, const double *FH, const double *FQ,
+    const double *Press, const double *zExner, const double *rExner,
+    const double *VirTemp, const double *Height,
+    const double *DiffV, const double *DiffT, const double *DiffQ,
+    double *DU, double *DV, double *DT, double *DQ, double *Coef1, double *Coef2, void *stream)
+{
+    if (!h) return fail(DCCM_ERR_ARG, "dccm_vdiff_forward: null handle");
+    return forward_range(h, FX, FY, FH, FQ, Press, zExner, rExner, VirTemp, Height, DiffV, DiffT, DiffQ,
+                         DU, DV, DT, DQ, Coef1, Coef2, 0, h->NC, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dccm_vdiff_backward_device(dccm_vdiff *h, double *DU, double *DV, double *DT, double *DQ,
+                                          const double *level1, void *stream)
+{
+    if (!h) return fail(DCCM_ERR_ARG, "dccm_vdiff_backward: null handle");
+    return backward_range(h, DU, DV, DT, DQ, level1, 0, h->NC, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int dccm_vdiff_forward_host(dccm_vdiff *h,
@@ -427,23 +487,35 @@ extern "C" int dccm_vdiff_forward_host(dccm_vdiff *h,
     p = h->out_buf.as<double>();
     double *oDU = take(full), *oDV = take(full), *oDT = take(full), *oDQ = take(full * nc);
     double *oC1 = take(NC * 4), *oC2 = take(NC * 4);
-    cudaStream_t st = 0;
-    auto h2d = [&](double *d, const double *s, size_t n) {
-        return cudaMemcpyAsync(d, s, sizeof(double) * n, cudaMemcpyHostToDevice, st);
-    };
-    DCCM_CUDA_TRY(h2d(dFX, FX, half)); DCCM_CUDA_TRY(h2d(dFY, FY, half)); DCCM_CUDA_TRY(h2d(dFH, FH, half));
-    DCCM_CUDA_TRY(h2d(dFQ, FQ, half * nc)); DCCM_CUDA_TRY(h2d(dP, Press, half)); DCCM_CUDA_TRY(h2d(dzE, zExner, full));
-    DCCM_CUDA_TRY(h2d(drE, rExner, half)); DCCM_CUDA_TRY(h2d(dTv, VirTemp, half)); DCCM_CUDA_TRY(h2d(dH, Height, full));
-    DCCM_CUDA_TRY(h2d(dDV, DiffV, half)); DCCM_CUDA_TRY(h2d(dDT, DiffT, half)); DCCM_CUDA_TRY(h2d(dDQ, DiffQ, half));
-    rc = dccm_vdiff_forward_device(h, dFX, dFY, dFH, dFQ, dP, dzE, drE, dTv, dH, dDV, dDT, dDQ,
-                                   oDU, oDV, oDT, oDQ, oC1, oC2, st);
+    if (h->coef_stride > 0 && h->coef_stride != h->NC)
+        return fail(DCCM_ERR_ARG, "dccm_vdiff_forward_host: a coefficient slot stride is only meaningful for device buffers");
+    Pipe pp(h);
+    rc = pp.init();
     if (rc) return rc;
-    auto d2h = [&](double *d, const double *s, size_t n) {
-        return cudaMemcpyAsync(d, s, sizeof(double) * n, cudaMemcpyDeviceToHost, st);
-    };
-    DCCM_CUDA_TRY(d2h(DU, oDU, full)); DCCM_CUDA_TRY(d2h(DV, oDV, full)); DCCM_CUDA_TRY(d2h(DT, oDT, full));
-    DCCM_CUDA_TRY(d2h(DQ, oDQ, full * nc)); DCCM_CUDA_TRY(d2h(Coef1, oC1, NC * 4)); DCCM_CUDA_TRY(d2h(Coef2, oC2, NC * 4));
-    DCCM_CUDA_TRY(cudaStreamSynchronize(st));
+    cudaStream_t sin = h->pipe[0], sk = h->pipe[1], sout = h->pipe[2];
+    const size_t Kh = K + 1;
+    for (int j = 0; j < pp.nchunk; j++) {
+        int64_t c0, c1;
+        pp.range(j, c0, c1);
+        if (c0 >= c1) continue;
+        auto in = [&](double *d, const double *s, size_t rows) { return pp.copy(d, s, c0, c1, rows, cudaMemcpyHostToDevice, sin); };
+        DCCM_CUDA_TRY(in(dFX, FX, Kh)); DCCM_CUDA_TRY(in(dFY, FY, Kh)); DCCM_CUDA_TRY(in(dFH, FH, Kh));
+        DCCM_CUDA_TRY(in(dFQ, FQ, Kh * nc)); DCCM_CUDA_TRY(in(dP, Press, Kh)); DCCM_CUDA_TRY(in(dzE, zExner, K));
+        DCCM_CUDA_TRY(in(drE, rExner, Kh)); DCCM_CUDA_TRY(in(dTv, VirTemp, Kh)); DCCM_CUDA_TRY(in(dH, Height, K));
+        DCCM_CUDA_TRY(in(dDV, DiffV, Kh)); DCCM_CUDA_TRY(in(dDT, DiffT, Kh)); DCCM_CUDA_TRY(in(dDQ, DiffQ, Kh));
+        DCCM_CUDA_TRY(cudaEventRecord(pp.ev[2 * j], sin));
+        DCCM_CUDA_TRY(cudaStreamWaitEvent(sk, pp.ev[2 * j], 0));
+        rc = forward_range(h, dFX, dFY, dFH, dFQ, dP, dzE, drE, dTv, dH, dDV, dDT, dDQ, oDU, oDV, oDT, oDQ, oC1, oC2, c0, c1, sk);
+        if (rc) return rc;
+        DCCM_CUDA_TRY(cudaEventRecord(pp.ev[2 * j + 1], sk));
+        DCCM_CUDA_TRY(cudaStreamWaitEvent(sout, pp.ev[2 * j + 1], 0));
+        auto out = [&](double *d, const double *s, size_t rows) { return pp.copy(d, s, c0, c1, rows, cudaMemcpyDeviceToHost, sout); };
+        DCCM_CUDA_TRY(out(DU, oDU, K)); DCCM_CUDA_TRY(out(DV, oDV, K)); DCCM_CUDA_TRY(out(DT, oDT, K));
+        DCCM_CUDA_TRY(out(DQ, oDQ, K * nc)); DCCM_CUDA_TRY(out(Coef1, oC1, 4)); DCCM_CUDA_TRY(out(Coef2, oC2, 4));
+    }
+    DCCM_CUDA_TRY(cudaStreamSynchronize(sout));
+    DCCM_CUDA_TRY(cudaStreamSynchronize(sk));
+    DCCM_CUDA_TRY(cudaStreamSynchronize(sin));
     return DCCM_OK;
 }
 
@@ -455,17 +527,31 @@ extern "C" int dccm_vdiff_backward_host(dccm_vdiff *h, double *DU, double *DV, d
     if (rc) return rc;
     double *p = h->out_buf.as<double>();
     double *oDU = p, *oDV = p + full, *oDT = p + 2 * full, *oDQ = p + 3 * full;
-    cudaStream_t st = 0;
-    DCCM_CUDA_TRY(cudaMemcpyAsync(oDU, DU, sizeof(double) * full, cudaMemcpyHostToDevice, st));
-    DCCM_CUDA_TRY(cudaMemcpyAsync(oDV, DV, sizeof(double) * full, cudaMemcpyHostToDevice, st));
-    DCCM_CUDA_TRY(cudaMemcpyAsync(oDT, DT, sizeof(double) * full, cudaMemcpyHostToDevice, st));
-    DCCM_CUDA_TRY(cudaMemcpyAsync(oDQ, DQ, sizeof(double) * full * nc, cudaMemcpyHostToDevice, st));
-    rc = dccm_vdiff_backward_device(h, oDU, oDV, oDT, oDQ, nullptr, st);
+    Pipe pp(h);
+    rc = pp.init();
     if (rc) return rc;
-    DCCM_CUDA_TRY(cudaMemcpyAsync(DU, oDU, sizeof(double) * full, cudaMemcpyDeviceToHost, st));
-    DCCM_CUDA_TRY(cudaMemcpyAsync(DV, oDV, sizeof(double) * full, cudaMemcpyDeviceToHost, st));
-    DCCM_CUDA_TRY(cudaMemcpyAsync(DT, oDT, sizeof(double) * full, cudaMemcpyDeviceToHost, st));
-    DCCM_CUDA_TRY(cudaMemcpyAsync(DQ, oDQ, sizeof(double) * full * nc, cudaMemcpyDeviceToHost, st));
-    DCCM_CUDA_TRY(cudaStreamSynchronize(st));
+    cudaStream_t sin = h->pipe[0], sk = h->pipe[1], sout = h->pipe[2];
+    for (int j = 0; j < pp.nchunk; j++) {
+        int64_t c0, c1;
+        pp.range(j, c0, c1);
+        if (c0 >= c1) continue;
+        DCCM_CUDA_TRY(pp.copy(oDU, DU, c0, c1, K, cudaMemcpyHostToDevice, sin));
+        DCCM_CUDA_TRY(pp.copy(oDV, DV, c0, c1, K, cudaMemcpyHostToDevice, sin));
+        DCCM_CUDA_TRY(pp.copy(oDT, DT, c0, c1, K, cudaMemcpyHostToDevice, sin));
+        DCCM_CUDA_TRY(pp.copy(oDQ, DQ, c0, c1, K * nc, cudaMemcpyHostToDevice, sin));
+        DCCM_CUDA_TRY(cudaEventRecord(pp.ev[2 * j], sin));
+        DCCM_CUDA_TRY(cudaStreamWaitEvent(sk, pp.ev[2 * j], 0));
+        rc = backward_range(h, oDU, oDV, oDT, oDQ, nullptr, c0, c1, sk);
+        if (rc) return rc;
+        DCCM_CUDA_TRY(cudaEventRecord(pp.ev[2 * j + 1], sk));
+        DCCM_CUDA_TRY(cudaStreamWaitEvent(sout, pp.ev[2 * j + 1], 0));
+        DCCM_CUDA_TRY(pp.copy(DU, oDU, c0, c1, K, cudaMemcpyDeviceToHost, sout));
+        DCCM_CUDA_TRY(pp.copy(DV, oDV, c0, c1, K, cudaMemcpyDeviceToHost, sout));
+        DCCM_CUDA_TRY(pp.copy(DT, oDT, c0, c1, K, cudaMemcpyDeviceToHost, sout));
+        DCCM_CUDA_TRY(pp.copy(DQ, oDQ, c0, c1, K * nc, cudaMemcpyDeviceToHost, sout));
+    }
+    DCCM_CUDA_TRY(cudaStreamSynchronize(sout));
+    DCCM_CUDA_TRY(cudaStreamSynchronize(sk));
+    DCCM_CUDA_TRY(cudaStreamSynchronize(sin));
     return DCCM_OK;
 }

@@ -205,7 +205,11 @@ def _check_bulk(got, ref):
         assert e <= RTOL, f"{k}: rel err {e}"
 
 
-def test_bulkflux_vs_oracle_T42(gpu, orc, dccm, S):
+@pytest.mark.parametrize("chunks", [None, 5, 1000])
+def test_bulkflux_vs_oracle_T42(gpu, orc, dccm, S, chunks, monkeypatch):
+    """chunks: the host entry point moves the interior rows in that many pipelined pieces (H2D | kernel | D2H)."""
+    if chunks:
+        monkeypatch.setenv("DCCM_HOST_CHUNKS", str(chunks))
     IA, JA, inp = _bulk_case(S, dccm, 128, 64)
     got = _run_bulk_gpu(dccm, IA, JA, inp)
     ref = orc.bulkflux(IA, JA, inp)
@@ -269,6 +273,31 @@ def test_vdiff_reference_order_mode_is_bit_exact(gpu, orc, dccm, S, im, jm, K, n
     h.VDiffBackward(DU, DV, DT, DQ)
     for a, b, k in zip((DU, DV, DT, DQ), refb, ("DUDt", "DVDt", "DTempDt", "DQMixDt")):
         assert np.array_equal(a, b), f"backward {k}: rel err {relerr(a, b)}"
+
+
+@pytest.mark.parametrize("chunks", [3, 7, 1000])
+def test_vdiff_host_calls_pipelined_over_column_chunks(gpu, orc, dccm, S, chunks, monkeypatch):
+    """The *_host entry points move their arguments in column chunks (H2D | kernel | D2H on three streams, 2-D
+    copies of `levels` rows); forcing 3, 7 (ragged) and more chunks than 32-column groups on a small grid gives
+    the bits of the oracle, for pinned and for pageable host arrays alike."""
+    import torch
+    g, inp = _vdiff_case(S, dccm, 72, 37, 9, 3)
+    args = (g.im, g.jm, 9, 3, 2, S.GRAV, S.CPDRY, S.GASRDRY, S.DELTIME)
+    ref_h = orc.VDiff(*args)
+    ref = ref_h.forward(inp)
+    monkeypatch.setenv("DCCM_HOST_CHUNKS", str(chunks))
+    h = dccm.SfcImplicitCoupling(*args)
+    pinned = {k: torch.as_tensor(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in inp.items()}
+    for host_in in (inp, pinned):
+        got = h.VDiffForward(host_in)
+        for k in ref:
+            assert np.array_equal(got[k], ref[k]), k
+    DU, DV, DT, DQ = (got[k].copy() for k in ("DUDt", "DVDt", "DTempDt", "DQMixDt"))
+    DU[0] = 1e-3; DV[0] = -2e-3; DT[0] = 5e-4; DQ[1, 0] = 1e-7
+    refb = ref_h.backward(DU.copy(), DV.copy(), DT.copy(), DQ.copy())
+    h.VDiffBackward(DU, DV, DT, DQ)
+    for a, b in zip((DU, DV, DT, DQ), refb):
+        assert np.array_equal(a, b)
 
 
 def test_vdiff_fast_mode_within_tolerance(gpu, orc, dccm, S):
