@@ -82,6 +82,10 @@ _SIGS = {
                                               f64p, f64p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
     "dccm_table_gen_bilinear_rows": (C.c_int, [C.c_int, f64p, C.c_int, f64p, C.c_int, f64p, C.c_int, f64p,
                                                C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "dccm_table_gen_jones99_separable": (C.c_int, [C.c_int, f64p, C.c_int, f64p, C.c_int, f64p, C.c_int, f64p,
+                                                   f64p, f64p, C.c_int, C.c_int, C.POINTER(vp)]),
+    "dccm_table_gen_bilinear_separable": (C.c_int, [C.c_int, f64p, C.c_int, f64p, C.c_int, f64p, C.c_int, f64p,
+                                                    C.c_int, C.POINTER(vp)]),
     "dccm_table_write_text": (C.c_int, [vp, C.c_char_p]),
     "dccm_table_read_text": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
     "dccm_table_write_bin": (C.c_int, [vp, C.c_char_p]),
@@ -93,6 +97,10 @@ _SIGS = {
     "dccm_remap_create": (C.c_int, [C.c_int64, i32p, i32p, f64p, C.c_int, C.c_int, C.POINTER(vp)]),
     "dccm_remap_create_lonlat": (C.c_int, [C.c_int64, i32p, i32p, f64p, C.c_int, C.c_int, C.c_int, C.c_int,
                                            C.POINTER(vp)]),
+    "dccm_remap_create_jones99": (C.c_int, [C.c_int, f64p, C.c_int, f64p, C.c_int, f64p, C.c_int, f64p,
+                                            f64p, f64p, C.c_int, C.c_int, C.POINTER(vp)]),
+    "dccm_remap_create_bilinear": (C.c_int, [C.c_int, f64p, C.c_int, f64p, C.c_int, f64p, C.c_int, f64p,
+                                             C.c_int, C.POINTER(vp)]),
     "dccm_remap_classify": (C.c_int, [C.c_int64, i32p, i32p, f64p, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "dccm_remap_destroy": (None, [vp]),

@@ -36,6 +36,8 @@
 
 using namespace dccm;
 
+SepTab sep_of(const dccm_remap *h);        // dccm_remap.cu
+
 namespace {
 
 constexpr int kThreads = 128;
@@ -48,6 +50,7 @@ struct Csr {                       // one table: CSR (kind 0) or zonal stencil (
 
 struct SfcArgs {
     Csr as_bil, as_cons, os_bil, os_cons;
+    SepTab os_bil_sep, os_cons_sep;                           // used when the table's kind is 2 (separable)
     SrcSeg a2s_bil, a2s_cons, o2s_bil, o2s_cons;             // (13M, nA) (4M, nA) (2M, nO) (3M, nO)
     double *s2a, *s2o;                                        // (9M, nS) (12M, nS)
     dccm_sfc_fields full;                                     // optional API-complete outputs, slot stride M*nS
@@ -115,6 +118,80 @@ __device__ __forceinline__ void gather(const Csr &t, int r, const SrcSeg &src, i
             }
         }
     }
+}
+
+// One destination cell of a separable (kind 2) table, D layers: the column's x-list and the row's y-list are a few
+// L1-resident entries; every (m, n) pair is rebuilt as the generator emitted it (order, product, 1e-14 drop test).
+template <int D, bool SEG>
+__device__ __forceinline__ void gather_sep(const SepTab &t, int r, const SrcSeg &src, int64_t n_src, int M, int m,
+                                           double (&acc)[D])
+{
+#pragma unroll
+    for (int d = 0; d < D; d++) acc[d] = 0.0;
+    const int64_t o0 = (int64_t)m * n_src, lstride = (int64_t)M * n_src;
+    const int jD = r / t.nxd, iD = r - jD * t.nxd;
+    const int x0 = __ldg(&t.xptr[iD]), x1 = __ldg(&t.xptr[iD + 1]);
+    const int y0 = __ldg(&t.yptr[jD]), y1 = __ldg(&t.yptr[jD + 1]);
+    if (t.mode == 1) {                         // bilinear: (m0,n0) (m1,n0) (m1,n1) (m0,n1), nothing dropped
+        const int i0 = __ldg(&t.xi[x0]), i1 = __ldg(&t.xi[x0 + 1]);
+        const double a0 = __ldg(&t.xw[x0]), a1 = __ldg(&t.xw[x0 + 1]);
+        const int j0 = __ldg(&t.yj[y0]) * t.nxs, j1 = __ldg(&t.yj[y0 + 1]) * t.nxs;
+        const double b0 = __ldg(&t.yw[y0]), b1 = __ldg(&t.yw[y0 + 1]);
+        const int c[4] = {j0 + i0, j0 + i1, j1 + i1, j1 + i0};
+        const double w[4] = {__dmul_rn(a0, b0), __dmul_rn(a1, b0), __dmul_rn(a1, b1), __dmul_rn(a0, b1)};
+        double v[4][D];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const double *p = cell<SEG>(src, c[j]) + o0;
+#pragma unroll
+            for (int d = 0; d < D; d++) v[j][d] = __ldg(p + d * lstride);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int d = 0; d < D; d++) acc[d] = __dadd_rn(acc[d], __dmul_rn(v[j][d], w[j]));
+        return;
+    }
+    for (int mm = x0; mm < x1; mm++) {
+        const int i = __ldg(&t.xi[mm]);
+        const double a = __ldg(&t.xw[mm]);
+        for (int nb = y0; nb < y1; nb += 3) {
+            int c[3];
+            double w[3], v[3][D];
+            bool on[3];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                on[j] = nb + j < y1;
+                c[j] = on[j] ? __ldg(&t.yj[nb + j]) * t.nxs + i : 0;
+                w[j] = on[j] ? __dmul_rn(a, __ldg(&t.yw[nb + j])) : 0.0;
+                on[j] = on[j] && fabs(w[j]) > 1e-14;
+            }
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                if (on[j]) {
+                    const double *p = cell<SEG>(src, c[j]) + o0;
+#pragma unroll
+                    for (int d = 0; d < D; d++) v[j][d] = __ldg(p + d * lstride);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                if (on[j]) {
+#pragma unroll
+                    for (int d = 0; d < D; d++) acc[d] = __dadd_rn(acc[d], __dmul_rn(v[j][d], w[j]));
+                }
+            }
+        }
+    }
+}
+
+// any kind: CSR / zonal stencil through gather<>, separable through gather_sep<>
+template <int D, int CH, bool SEG>
+__device__ __forceinline__ void gather_any(const Csr &t, const SepTab &ts, int r, const SrcSeg &src, int64_t n_src,
+                                           int M, int m, double (&acc)[D])
+{
+    if (t.kind == 2) gather_sep<D, SEG>(ts, r, src, n_src, M, m, acc);
+    else gather<D, CH, SEG>(t, r, src, n_src, M, m, acc);
 }
 
 // The two ocean-side tables of one cell (CSR: ocean and exchange-grid longitudes differ), software-pipelined.
@@ -265,8 +342,8 @@ __device__ __forceinline__ void direct_cell(const SfcArgs &a, int m, int r)
     double ab[13], ac[4], ob[2], oc[3];
     gather<13, 2, SEG>(a.as_bil, r, a.a2s_bil, a.nA, M, m, ab);
     gather<4, 4, SEG>(a.as_cons, r, a.a2s_cons, a.nA, M, m, ac);
-    gather<2, 4, SEG>(a.os_bil, r, a.o2s_bil, a.nO, M, m, ob);
-    gather<3, 4, SEG>(a.os_cons, r, a.o2s_cons, a.nO, M, m, oc);
+    gather_any<2, 4, SEG>(a.os_bil, a.os_bil_sep, r, a.o2s_bil, a.nO, M, m, ob);
+    gather_any<3, 4, SEG>(a.os_cons, a.os_cons_sep, r, a.o2s_cons, a.nO, M, m, oc);
 
     BulkIn in;
     in.WindU = ab[0]; in.WindV = ab[1]; in.SfcAirTemp = ab[2]; in.QVap1 = ab[3]; in.SfcPress = ab[4];
@@ -467,8 +544,8 @@ __global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_staged_kernel(con
             og.pairs(a.os_bil, a.os_cons);
             og.finish(a.os_bil, a.os_cons, a.o2s_bil, a.o2s_cons, a.nO, M, m, ob, oc);
         } else {
-            gather<2, 4, SEG>(a.os_bil, r, a.o2s_bil, a.nO, M, m, ob);
-            gather<3, 4, SEG>(a.os_cons, r, a.o2s_cons, a.nO, M, m, oc);
+            gather_any<2, 4, SEG>(a.os_bil, a.os_bil_sep, r, a.o2s_bil, a.nO, M, m, ob);
+            gather_any<3, 4, SEG>(a.os_cons, a.os_cons_sep, r, a.o2s_cons, a.nO, M, m, oc);
         }
     }
     __syncthreads();                       // stencil records + barrier initialisation visible to every warp
@@ -500,6 +577,7 @@ __global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_staged_kernel(con
 
 Csr csr_of(const dccm_remap *h)
 {
+    if (h->kind == 2) return Csr{nullptr, nullptr, nullptr, 2, h->nxs, h->nxd};
     if (h->kind == 1) return Csr{h->d_zptr, h->d_zdj, h->d_zw, 1, h->nxs, h->nxd};
     return Csr{h->d_rowptr, h->d_col, h->d_w, 0, 0, 0};
 }
@@ -557,6 +635,10 @@ extern "C" int dccm_sfc_exchange_seg_device(const dccm_remap *as_bil, const dccm
         return fail(DCCM_ERR_ARG, "dccm_sfc_exchange: the four tables do not describe the same grid triple");
     SfcArgs a;
     a.as_bil = csr_of(as_bil); a.as_cons = csr_of(as_cons); a.os_bil = csr_of(os_bil); a.os_cons = csr_of(os_cons);
+    a.os_bil_sep = sep_of(os_bil); a.os_cons_sep = sep_of(os_cons);
+    if (as_bil->kind == 2 || as_cons->kind == 2)
+        return fail(DCCM_ERR_UNSUPPORTED, "dccm_sfc_exchange: separable A->S tables are not supported (the exchange grid has the "
+                                          "atmosphere's longitudes: those tables are zonal stencils)");
     a.a2s_bil = seg_of(sa2s_bil); a.a2s_cons = seg_of(sa2s_cons); a.o2s_bil = seg_of(so2s_bil); a.o2s_cons = seg_of(so2s_cons);
     a.s2a = s2a; a.s2o = s2o;
     a.redo = as_bil->d_redo; a.redo_cap = dccm_remap::kRedoCap;

@@ -23,6 +23,9 @@
 using namespace dccm;
 
 #include "dccm_remap_internal.h"
+#include "dccm_sep.h"
+
+SepTab sep_of(const dccm_remap *h);
 
 namespace {
 
@@ -119,6 +122,70 @@ remap_zonal_kernel(const int32_t *__restrict__ zptr, const int32_t *__restrict__
 #pragma unroll
                 for (int d = 0; d < FB; d++)
                     if (d < nf) acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(sp + (int64_t)d * sn1), ww));
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < FB; d++)
+            if (d < nf) recv[r + (int64_t)(d0 + d) * rn1] = acc[d];
+    }
+}
+
+// kind 2: separable generated table, one thread per destination cell.  The x-list of the cell's column and the
+// y-list of its row are a few L1-resident entries; each (m, n) pair is rebuilt exactly as the generator emitted it
+// (order, product, drop test), three latitude entries at a time so their source loads are in flight together.
+template <int FB, bool SEG>
+__global__ void __launch_bounds__(kThreads)
+remap_sep_kernel(const SepTab t, const SrcSeg send, int64_t sn1, double *__restrict__ recv, int64_t rn1,
+                 int n_recv, int nfield, int fields_per_y)
+{
+    const int r = blockIdx.x * kThreads + threadIdx.x;
+    if (r >= n_recv) return;
+    const int jD = r / t.nxd, iD = r - jD * t.nxd;
+    const int x0 = __ldg(&t.xptr[iD]), x1 = __ldg(&t.xptr[iD + 1]);
+    const int y0 = __ldg(&t.yptr[jD]), y1 = __ldg(&t.yptr[jD + 1]);
+    const int d_begin = blockIdx.y * fields_per_y;
+    const int d_end = min(nfield, d_begin + fields_per_y);
+    for (int d0 = d_begin; d0 < d_end; d0 += FB) {
+        double acc[FB];
+#pragma unroll
+        for (int d = 0; d < FB; d++) acc[d] = 0.0;
+        const int64_t o0 = (int64_t)d0 * sn1;
+        const int nf = min(FB, d_end - d0);
+        auto add = [&](int c, double w) {
+            const double *sp = cell<SEG>(send, c) + o0;
+            if (nf == FB) {
+#pragma unroll
+                for (int d = 0; d < FB; d++) acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(sp + (int64_t)d * sn1), w));
+            } else {
+#pragma unroll
+                for (int d = 0; d < FB; d++)
+                    if (d < nf) acc[d] = __dadd_rn(acc[d], __dmul_rn(__ldg(sp + (int64_t)d * sn1), w));
+            }
+        };
+        if (t.mode == 1) {                         // bilinear: (m0,n0) (m1,n0) (m1,n1) (m0,n1), nothing dropped
+            const int i0 = __ldg(&t.xi[x0]), i1 = __ldg(&t.xi[x0 + 1]);
+            const double a0 = __ldg(&t.xw[x0]), a1 = __ldg(&t.xw[x0 + 1]);
+            const int j0 = __ldg(&t.yj[y0]) * t.nxs, j1 = __ldg(&t.yj[y0 + 1]) * t.nxs;
+            const double b0 = __ldg(&t.yw[y0]), b1 = __ldg(&t.yw[y0 + 1]);
+            add(j0 + i0, __dmul_rn(a0, b0)); add(j0 + i1, __dmul_rn(a1, b0));
+            add(j1 + i1, __dmul_rn(a1, b1)); add(j1 + i0, __dmul_rn(a0, b1));
+        } else {
+            for (int m = x0; m < x1; m++) {
+                const int i = __ldg(&t.xi[m]);
+                const double a = __ldg(&t.xw[m]);
+                for (int nb = y0; nb < y1; nb += 3) {
+                    int c[3];
+                    double w[3];
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        const bool on = nb + j < y1;
+                        c[j] = on ? __ldg(&t.yj[nb + j]) * t.nxs + i : 0;
+                        w[j] = on ? __dmul_rn(a, __ldg(&t.yw[nb + j])) : 0.0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 3; j++)
+                        if (nb + j < y1 && fabs(w[j]) > 1e-14) add(c[j], w[j]);
+                }
             }
         }
 #pragma unroll
@@ -298,6 +365,109 @@ extern "C" int dccm_remap_create_lonlat(int64_t nops, const int32_t *send_index,
     return DCCM_OK;
 }
 
+SepTab sep_of(const dccm_remap *h)
+{
+    return SepTab{h->d_xptr, h->d_xi, h->d_yptr, h->d_yj, h->d_xw, h->d_yw, h->sep_mode, h->nxs, h->nxd};
+}
+
+namespace {
+template <class T> cudaError_t upload(T *&d, const std::vector<T> &v)
+{
+    cudaError_t e = cudaMalloc(&d, sizeof(T) * std::max<size_t>(2, v.size()));
+    if (e == cudaSuccess && !v.empty()) e = cudaMemcpy(d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice);
+    return e;
+}
+
+// kind-2 handle from the factors; nnz = entries the expanded table would hold (mode 0 applies the drop test)
+int create_separable(const SepFactors &f, dccm_remap **out)
+{
+    int rc = ensure_device();
+    if (rc) return rc;
+    dccm_remap *h = new dccm_remap();
+    h->kind = 2; h->sep_mode = f.mode; h->nxs = f.nxs; h->nxd = f.nxd; h->nyd = f.nyd;
+    h->n_send = f.nxs * f.nys; h->n_recv = f.nxd * f.nyd;
+    int64_t nnz = 0;
+    int maxrow = 0;
+    if (f.mode == 1) { nnz = 4 * (int64_t)h->n_recv; maxrow = 4; }
+    else {
+        // count per (x-entry, y-entry) pair once: the kept pairs of column iD and row jD multiply out
+        std::vector<int64_t> kept_x(f.nxd, 0);
+        for (int jD = 0; jD < f.nyd; jD++) {
+            for (int iD = 0; iD < f.nxd; iD++) {
+                int k = 0;
+                for (int m = f.xptr[iD]; m < f.xptr[iD + 1]; m++)
+                    for (int n = f.yptr[jD]; n < f.yptr[jD + 1]; n++)
+                        k += std::fabs(f.xw[m] * f.yw[n]) > 1e-14;
+                nnz += k; maxrow = std::max(maxrow, k);
+            }
+        }
+    }
+    h->nnz = nnz; h->max_row_nnz = maxrow;
+    cudaError_t e = cudaMalloc(&h->d_redo, sizeof(int) * (2 + 2 * (size_t)dccm_remap::kRedoCap));
+    if (e == cudaSuccess) e = cudaMemset(h->d_redo, 0, sizeof(int) * 2);
+    if (e == cudaSuccess) e = upload(h->d_xptr, f.xptr);
+    if (e == cudaSuccess) e = upload(h->d_xi, f.xi);
+    if (e == cudaSuccess) e = upload(h->d_xw, f.xw);
+    if (e == cudaSuccess) e = upload(h->d_yptr, f.yptr);
+    if (e == cudaSuccess) e = upload(h->d_yj, f.yj);
+    if (e == cudaSuccess) e = upload(h->d_yw, f.yw);
+    if (e != cudaSuccess) {
+        dccm_remap_destroy(h);
+        return fail(DCCM_ERR_CUDA, "dccm_remap_create (separable): %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return DCCM_OK;
+}
+
+// expanded-table route for the pairs the separable form does not take (zonal stencils, 2nd order)
+int create_from_table(dccm_table *t, int nxs, int nys, int nxd, int nyd, dccm_remap **out)
+{
+    const int64_t n = dccm_table_size(t);
+    std::vector<int32_t> si((size_t)n), ri((size_t)n);
+    std::vector<double> cf((size_t)n);
+    int rc = dccm_table_index(t, nxs, nxd, si.data(), ri.data(), cf.data());
+    dccm_table_free(t);
+    if (rc) return rc;
+    return dccm_remap_create_lonlat(n, si.data(), ri.data(), cf.data(), nxs * nys, nxd * nyd, nxs, nxd, out);
+}
+}  // namespace
+
+extern "C" int dccm_remap_create_jones99(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                                         int nxd, const double *x_LonD, int nyd, const double *y_LatD,
+                                         const double *y_LatIntWtS, const double *y_LatIntWtD,
+                                         int accuracy_order, int lon_mode, dccm_remap **out)
+{
+    *out = nullptr;
+    SepFactors f;
+    int rc = jones99_factors(nxs, x_LonS, nys, y_LatS, nxd, x_LonD, nyd, y_LatD, y_LatIntWtS, y_LatIntWtD,
+                             accuracy_order, lon_mode, f);
+    if (rc) return rc;
+    if (f.ok) return create_separable(f, out);
+    dccm_table *t = nullptr;
+    rc = dccm_table_gen_jones99(nxs, x_LonS, nys, y_LatS, nxd, x_LonD, nyd, y_LatD, y_LatIntWtS, y_LatIntWtD,
+                                accuracy_order, lon_mode, &t);
+    if (rc) return rc;
+    return create_from_table(t, nxs, nys, nxd, nyd, out);
+}
+
+extern "C" int dccm_remap_create_bilinear(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                                          int nxr, const double *x_LonR, int nyr, const double *y_LatR,
+                                          int lon_mode, dccm_remap **out)
+{
+    *out = nullptr;
+    SepFactors f;
+    bool same = nxs == nxr;
+    if (same) for (int i = 0; i < nxs; i++) if (x_LonS[i] != x_LonR[i]) { same = false; break; }
+    int rc = DCCM_OK;
+    if (!same) rc = bilinear_factors(nxs, x_LonS, nys, y_LatS, nxr, x_LonR, nyr, y_LatR, lon_mode, f);   // equal longitudes: zonal stencil
+    if (rc) return rc;
+    if (f.ok) return create_separable(f, out);
+    dccm_table *t = nullptr;
+    rc = dccm_table_gen_bilinear(nxs, x_LonS, nys, y_LatS, nxr, x_LonR, nyr, y_LatR, lon_mode, &t);
+    if (rc) return rc;
+    return create_from_table(t, nxs, nys, nxr, nyr, out);
+}
+
 extern "C" void dccm_remap_destroy(dccm_remap *h)
 {
     if (!h) return;
@@ -308,6 +478,7 @@ extern "C" void dccm_remap_destroy(dccm_remap *h)
     }
     cudaFree(h->d_rowptr); cudaFree(h->d_col); cudaFree(h->d_w);
     cudaFree(h->d_zptr); cudaFree(h->d_zdj); cudaFree(h->d_zw); cudaFree(h->d_redo);
+    cudaFree(h->d_xptr); cudaFree(h->d_xi); cudaFree(h->d_yptr); cudaFree(h->d_yj); cudaFree(h->d_xw); cudaFree(h->d_yw);
     h->send_buf.release(); h->recv_buf.release();
     delete h;
 }
@@ -356,7 +527,10 @@ extern "C" int dccm_remap_apply_seg_device(dccm_remap *h, const dccm_src_seg *se
     dim3 grid(gx, gy);
 #define DCCM_REMAP_LAUNCH(F, S)                                                                                   \
     do {                                                                                                          \
-        if (h->kind == 1)                                                                                         \
+        if (h->kind == 2)                                                                                         \
+            remap_sep_kernel<F, S><<<grid, kThreads, 0, st>>>(sep_of(h), d_send, sn1, d_recv, rn1, h->n_recv,      \
+                                                             num_of_data, fields_per_y);                         \
+        else if (h->kind == 1)                                                                                    \
             remap_zonal_kernel<F, S><<<grid, kThreads, 0, st>>>(h->d_zptr, h->d_zdj, h->d_zw, h->nxs, h->nxd,     \
                                                                d_send, sn1, d_recv, rn1, h->n_recv, num_of_data, \
                                                                fields_per_y);                                    \

@@ -19,6 +19,13 @@ struct SrcSeg {
 inline SrcSeg seg_of(const double *p) { return SrcSeg{p, p, p, 0, INT64_MAX}; }
 inline SrcSeg seg_of(const dccm_src_seg *s) { return SrcSeg{s->lo, s->own, s->hi, s->b0, s->b1}; }
 
+// kind-2 table as the kernels see it
+struct SepTab {
+    const int32_t *xptr, *xi, *yptr, *yj;
+    const double *xw, *yw;
+    int mode, nxs, nxd;
+};
+
 struct dccm_remap {
     int n_send = 0, n_recv = 0;
     int64_t nnz = 0;
@@ -43,6 +50,12 @@ struct dccm_remap {
     // surface kernel): longest stencil, most distinct source rows in one stencil, and the range of
     // the longitude offsets taken as signed shifts (di > nxs/2 is a westward neighbour)
     int z_max_len = 0, z_max_rows = 0, z_dmin = 0, z_dmax = 0;
+    // kind 2: separable form of a generated table (dccm_sep.h): per destination column a list of (source column,
+    // longitude factor), per destination row a list of (source row, latitude factor); the kernels rebuild each
+    // entry as the generator did (weight = xw * yw, mode 0 drops |w| <= 1e-14).  nxs / nxd / nyd as for kind 1.
+    int sep_mode = 0;
+    int32_t *d_xptr = nullptr, *d_xi = nullptr, *d_yptr = nullptr, *d_yj = nullptr;
+    double *d_xw = nullptr, *d_yw = nullptr;
     // fused surface kernel: cells to re-evaluate with plain IEEE operators (csrc/dccm_exchange.cu); the list of
     // the A->S bilinear handle is the one used.  Allocated at creation (never inside a stream capture).
     static constexpr int kRedoCap = 16384;

@@ -11,6 +11,7 @@
 #include <algorithm>
 
 #include "dccm_common.h"
+#include "dccm_sep.h"
 
 struct dccm_table {
     std::vector<int32_t> iD, jD, iS, jS;
@@ -167,14 +168,16 @@ extern "C" int dccm_table_gen_jones99(int nxs, const double *x_LonS, int nys, co
                                        accuracy_order, lon_mode, 1, nyd, out);
 }
 
-extern "C" int dccm_table_gen_jones99_rows(int nxs, const double *x_LonS, int nys, const double *y_LatS,
-                                           int nxd, const double *x_LonD, int nyd, const double *y_LatD,
-                                           const double *y_LatIntWtS, const double *y_LatIntWtD,
-                                           int accuracy_order, int lon_mode, int jd_first, int jd_last,
-                                           dccm_table **out)
+// sep != nullptr: return the separable factors instead of the expanded table (sep->ok stays false when the
+// pair is not handled in that form: equal longitudes / nx == 1 -- those tables are zonal stencils -- or 2nd order)
+static int jones99_impl(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                        int nxd, const double *x_LonD, int nyd, const double *y_LatD,
+                        const double *y_LatIntWtS, const double *y_LatIntWtD,
+                        int accuracy_order, int lon_mode, int jd_first, int jd_last,
+                        dccm_table **out, SepFactors *sep)
 {
     (void)y_LatD;
-    *out = nullptr;
+    if (out) *out = nullptr;
     if (nxs < 1 || nys < 1 || nxd < 1 || nyd < 1) return fail(DCCM_ERR_ARG, "jones99: bad grid sizes");
     if (jd_first < 1 || jd_last > nyd || jd_first > jd_last + 1) return fail(DCCM_ERR_ARG, "jones99: bad destination row range");
     std::vector<double> uS = lon_edges(nxs, x_LonS), uD = lon_edges(nxd, x_LonD);
@@ -259,6 +262,23 @@ extern "C" int dccm_table_gen_jones99_rows(int nxs, const double *x_LonS, int ny
         }
     }
 
+    if (sep) {
+        if (!general || accuracy_order > 1) return DCCM_OK;
+        sep->mode = 0; sep->nxs = nxs; sep->nys = nys; sep->nxd = nxd; sep->nyd = nyd;
+        sep->xptr.assign(gptr.begin(), gptr.end());
+        sep->xi.resize(gidx.size());
+        for (size_t k = 0; k < gidx.size(); k++) sep->xi[k] = gidx[k] - 1;
+        sep->xw = gw;
+        sep->yptr.assign(nyd + 1, 0);
+        for (int jD = 1; jD <= nyd; jD++) {
+            const LatRow &R = rows[jD];
+            for (int n = 1; n <= R.nyr; n++) { sep->yj.push_back(R.ry1 + n - 2); sep->yw.push_back(R.w1[n]); }
+            sep->yptr[jD] = (int32_t)sep->yj.size();
+        }
+        sep->ok = true;
+        return DCCM_OK;
+    }
+
     // ---- emit in table-file order (ref :230-275) ----
     dccm_table *t = new dccm_table();
     for (int jD = jd_first; jD <= jd_last; jD++) {
@@ -290,6 +310,26 @@ extern "C" int dccm_table_gen_jones99_rows(int nxs, const double *x_LonS, int ny
     return DCCM_OK;
 }
 
+extern "C" int dccm_table_gen_jones99_rows(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                                           int nxd, const double *x_LonD, int nyd, const double *y_LatD,
+                                           const double *y_LatIntWtS, const double *y_LatIntWtD,
+                                           int accuracy_order, int lon_mode, int jd_first, int jd_last,
+                                           dccm_table **out)
+{
+    return jones99_impl(nxs, x_LonS, nys, y_LatS, nxd, x_LonD, nyd, y_LatD, y_LatIntWtS, y_LatIntWtD,
+                        accuracy_order, lon_mode, jd_first, jd_last, out, nullptr);
+}
+
+int dccm::jones99_factors(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                          int nxd, const double *x_LonD, int nyd, const double *y_LatD,
+                          const double *y_LatIntWtS, const double *y_LatIntWtD,
+                          int accuracy_order, int lon_mode, SepFactors &f)
+{
+    f = SepFactors();
+    return jones99_impl(nxs, x_LonS, nys, y_LatS, nxd, x_LonD, nyd, y_LatD, y_LatIntWtS, y_LatIntWtD,
+                        accuracy_order, lon_mode, 1, nyd, nullptr, &f);
+}
+
 extern "C" int dccm_table_gen_bilinear(int nxs, const double *x_LonS, int nys, const double *y_LatS,
                                        int nxr, const double *x_LonR, int nyr, const double *y_LatR,
                                        int lon_mode, dccm_table **out)
@@ -297,16 +337,16 @@ extern "C" int dccm_table_gen_bilinear(int nxs, const double *x_LonS, int nys, c
     return dccm_table_gen_bilinear_rows(nxs, x_LonS, nys, y_LatS, nxr, x_LonR, nyr, y_LatR, lon_mode, 1, nyr, out);
 }
 
-extern "C" int dccm_table_gen_bilinear_rows(int nxs, const double *x_LonS, int nys, const double *y_LatS,
-                                            int nxr, const double *x_LonR, int nyr, const double *y_LatR,
-                                            int lon_mode, int jr_first, int jr_last, dccm_table **out)
+static int bilinear_impl(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                         int nxr, const double *x_LonR, int nyr, const double *y_LatR,
+                         int lon_mode, int jr_first, int jr_last, dccm_table **out, SepFactors *sep)
 {
-    *out = nullptr;
+    if (out) *out = nullptr;
     if (nxs < 1 || nys < 2 || nxr < 1 || nyr < 1) return fail(DCCM_ERR_ARG, "bilinear: bad grid sizes");
     if (jr_first < 1 || jr_last > nyr || jr_first > jr_last + 1) return fail(DCCM_ERR_ARG, "bilinear: bad destination row range");
     const double dlon_r = 360.0 / (double)nxr, dlon_s = 360.0 / (double)nxs;   // ref :78-79
     dccm_table *t = new dccm_table();
-    t->reserve((size_t)nxr * (jr_last - jr_first + 1) * ((nxr == 1) ? 2 * nxs : (nxs == 1 ? 2 : 4)));
+    if (!sep) t->reserve((size_t)nxr * (jr_last - jr_first + 1) * ((nxr == 1) ? 2 * nxs : (nxs == 1 ? 2 : 4)));
     // longitude part is the same for every row: hoist (ref :116-119, cal_coef :154-165)
     std::vector<int> is1(nxr), is2(nxr);
     std::vector<double> a1(nxr), a2(nxr);
@@ -320,6 +360,17 @@ extern "C" int dccm_table_gen_bilinear_rows(int nxs, const double *x_LonS, int n
             a1[ir - 1] = (xc - x1) / (x3 - x1);
             a2[ir - 1] = 1.0 - a1[ir - 1];
         }
+    }
+    if (sep) {
+        if (nxr == 1 || nxs == 1) { delete t; return DCCM_OK; }     // axisymmetric side: a zonal stencil, not handled here
+        sep->mode = 1; sep->nxs = nxs; sep->nys = nys; sep->nxd = nxr; sep->nyd = nyr;
+        sep->xptr.resize(nxr + 1); sep->yptr.resize(nyr + 1);
+        for (int ir = 0; ir < nxr; ir++) {
+            sep->xptr[ir] = 2 * ir;
+            sep->xi.push_back(is1[ir] - 1); sep->xw.push_back(a2[ir]);       // m0: (is,  a2)
+            sep->xi.push_back(is2[ir] - 1); sep->xw.push_back(a1[ir]);       // m1: (is+1, a1)
+        }
+        sep->xptr[nxr] = 2 * nxr;
     }
     for (int jr = jr_first; jr <= jr_last; jr++) {
         double latR = y_LatR[jr - 1];
@@ -355,6 +406,12 @@ extern "C" int dccm_table_gen_bilinear_rows(int nxs, const double *x_LonS, int n
             int jhi_out = (js == nys) ? jhi : (js % nys + 1);
             double y1 = y_LatS[jlo - 1], y3 = y_LatS[jhi - 1];
             double b1 = (latR - y1) / (y3 - y1), b2 = 1.0 - b1;
+            if (sep) {
+                sep->yptr[jr - 1] = 2 * (jr - 1);
+                sep->yj.push_back(jlo - 1);     sep->yw.push_back(b2);      // n0: (jlo, b2)
+                sep->yj.push_back(jhi_out - 1); sep->yw.push_back(b1);      // n1: (jhi, b1)
+                continue;
+            }
             for (int ir = 0; ir < nxr; ir++) {
                 t->push(ir + 1, jr, is1[ir], jlo,     a2[ir] * b2);
                 t->push(ir + 1, jr, is2[ir], jlo,     a1[ir] * b2);
@@ -363,8 +420,77 @@ extern "C" int dccm_table_gen_bilinear_rows(int nxs, const double *x_LonS, int n
             }
         }
     }
+    if (sep) {
+        sep->yptr[nyr] = 2 * nyr;
+        sep->ok = true;
+        delete t;
+        return DCCM_OK;
+    }
     *out = t;
     return DCCM_OK;
+}
+
+extern "C" int dccm_table_gen_bilinear_rows(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                                            int nxr, const double *x_LonR, int nyr, const double *y_LatR,
+                                            int lon_mode, int jr_first, int jr_last, dccm_table **out)
+{
+    return bilinear_impl(nxs, x_LonS, nys, y_LatS, nxr, x_LonR, nyr, y_LatR, lon_mode, jr_first, jr_last, out, nullptr);
+}
+
+int dccm::bilinear_factors(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                           int nxr, const double *x_LonR, int nyr, const double *y_LatR, int lon_mode, SepFactors &f)
+{
+    f = SepFactors();
+    return bilinear_impl(nxs, x_LonS, nys, y_LatS, nxr, x_LonR, nyr, y_LatR, lon_mode, 1, nyr, nullptr, &f);
+}
+
+// Host-side expansion of the separable factors into a table, entry by entry as the kernels do it (kind 2):
+// lets the CPU test-suite check factors + expansion order against the generators index for index.
+static int expand_factors(const SepFactors &f, dccm_table **out)
+{
+    if (!f.ok) return fail(DCCM_ERR_UNSUPPORTED, "this grid pair is not handled in separable form (equal longitudes, nx == 1 or 2nd order)");
+    dccm_table *t = new dccm_table();
+    for (int jD = 0; jD < f.nyd; jD++) {
+        const int y0 = f.yptr[jD], y1 = f.yptr[jD + 1];
+        for (int iD = 0; iD < f.nxd; iD++) {
+            const int x0 = f.xptr[iD], x1 = f.xptr[iD + 1];
+            if (f.mode == 1) {
+                const int mm[4] = {x0, x0 + 1, x0 + 1, x0}, nn[4] = {y0, y0, y0 + 1, y0 + 1};
+                for (int k = 0; k < 4; k++)
+                    t->push(iD + 1, jD + 1, f.xi[mm[k]] + 1, f.yj[nn[k]] + 1, f.xw[mm[k]] * f.yw[nn[k]]);
+            } else {
+                for (int m = x0; m < x1; m++)
+                    for (int n = y0; n < y1; n++) {
+                        const double w = f.xw[m] * f.yw[n];
+                        if (std::fabs(w) > 1e-14) t->push(iD + 1, jD + 1, f.xi[m] + 1, f.yj[n] + 1, w);
+                    }
+            }
+        }
+    }
+    *out = t;
+    return DCCM_OK;
+}
+
+extern "C" int dccm_table_gen_jones99_separable(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                                                int nxd, const double *x_LonD, int nyd, const double *y_LatD,
+                                                const double *y_LatIntWtS, const double *y_LatIntWtD,
+                                                int accuracy_order, int lon_mode, dccm_table **out)
+{
+    *out = nullptr;
+    SepFactors f;
+    int rc = jones99_factors(nxs, x_LonS, nys, y_LatS, nxd, x_LonD, nyd, y_LatD, y_LatIntWtS, y_LatIntWtD,
+                             accuracy_order, lon_mode, f);
+    return rc ? rc : expand_factors(f, out);
+}
+
+extern "C" int dccm_table_gen_bilinear_separable(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                                                 int nxr, const double *x_LonR, int nyr, const double *y_LatR,
+                                                 int lon_mode, dccm_table **out)
+{
+    *out = nullptr;
+    SepFactors f;
+    int rc = bilinear_factors(nxs, x_LonS, nys, y_LatS, nxr, x_LonR, nyr, y_LatR, lon_mode, f);
+    return rc ? rc : expand_factors(f, out);
 }
 
 extern "C" int dccm_table_write_text(const dccm_table *t, const char *filename)

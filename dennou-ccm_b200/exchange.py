@@ -67,19 +67,28 @@ class SurfaceExchange:
         self.Grav = c.get("Grav", syn.GRAV); self.CpDry = c.get("CpDry", syn.CPDRY)
         self.GasRDry = c.get("GasRDry", syn.GASRDRY); self.DelTime = c.get("DelTime", syn.DELTIME)
         self.sig1 = c.get("Sig1", syn.SIG1)
-        tabs = tabs or build_tables(A, O, S)
         layout = layout or {"A": (A.n, A.n, 0), "S": (S.n, S.n, 0), "O": (O.n, O.n, 0)}
         self.layout = layout
         self.sharded = any(ext != own for own, ext, off in layout.values())
         assert not (self.sharded and members > 1), "ensembles shard by member, not by latitude band"
         self.ops = {}
         self.nnz = {}
-        for key, (send_i, recv_i, coef) in tabs.items():
-            s, d = key[0].upper(), key[1].upper()
-            gx = {"A": A.im, "S": S.im, "O": O.im}
-            self.ops[key] = RemapOperator(send_i, recv_i, coef, layout[s][1], layout[d][0],
-                                          gnxs=gx[s] if structured else 0, gnxr=gx[d] if structured else 0)
-            self.nnz[key] = len(coef)
+        if tabs is None and not self.sharded and structured:
+            # straight from the grids (dccm_remap_create_jones99 / _bilinear): no table is built on the host;
+            # the ocean-side pairs with different longitudes come back in separable form (kind 2)
+            g = {"a": A, "s": S, "o": O}
+            for key in ("as", "sa", "os", "so"):
+                for kind in ("cons", "bil"):
+                    self.ops[f"{key}_{kind}"] = RemapOperator.from_grids(g[key[0]], g[key[1]], kind == "cons", 1, 1)
+            self.nnz = {k: op.nnz for k, op in self.ops.items()}
+        else:
+            tabs = tabs or build_tables(A, O, S)
+            for key, (send_i, recv_i, coef) in tabs.items():
+                s, d = key[0].upper(), key[1].upper()
+                gx = {"A": A.im, "S": S.im, "O": O.im}
+                self.ops[key] = RemapOperator(send_i, recv_i, coef, layout[s][1], layout[d][0],
+                                              gnxs=gx[s] if structured else 0, gnxr=gx[d] if structured else 0)
+                self.nnz[key] = len(coef)
         nA, nS, nO, M = A.n, S.n, O.n, members
         nAx, nSx, nOx = layout["A"][1], layout["S"][1], layout["O"][1]
         self.offA, self.offS, self.offO = layout["A"][2], layout["S"][2], layout["O"][2]

@@ -29,6 +29,25 @@ class RemapOperator:
                                                  self.n_send, self.n_recv, int(gnxs), int(gnxr), C.byref(h)))
         self._h = h
 
+    @classmethod
+    def from_grids(cls, src, dst, conservative, accuracy_order=1, lon_mode=1):
+        """Generate-and-create in one step (dccm_remap_create_jones99 / _bilinear): the table is never built.
+        Different longitudes give the separable form (kind 2); equal longitudes a zonal stencil (kind 1)."""
+        self = cls.__new__(cls)
+        self.n_send, self.n_recv = src.n, dst.n
+        h = C.c_void_p()
+        if conservative:
+            L.check(L.lib().dccm_remap_create_jones99(src.im, L.dp(src.x_Lon), src.jm, L.dp(src.y_Lat),
+                                                      dst.im, L.dp(dst.x_Lon), dst.jm, L.dp(dst.y_Lat),
+                                                      L.dp(src.y_LatWt), L.dp(dst.y_LatWt),
+                                                      accuracy_order, lon_mode, C.byref(h)))
+        else:
+            L.check(L.lib().dccm_remap_create_bilinear(src.im, L.dp(src.x_Lon), src.jm, L.dp(src.y_Lat),
+                                                       dst.im, L.dp(dst.x_Lon), dst.jm, L.dp(dst.y_Lat),
+                                                       lon_mode, C.byref(h)))
+        self._h = h
+        return self
+
     @property
     def kind(self):
         return int(L.lib().dccm_remap_kind(self._h))

@@ -104,3 +104,18 @@ def gen_table_bilinear(src, dst, lon_mode=0, rows=None):
                                                  dst.im, L.dp(dst.x_Lon), dst.jm, L.dp(dst.y_Lat),
                                                  lon_mode, j0 + 1, j1, C.byref(h)))
     return MappingTable(h)
+
+
+def gen_table_separable(src, dst, conservative, accuracy_order=1, lon_mode=1):
+    """The table multiplied out from its separable factors, as the kind-2 kernels do (host check of that form)."""
+    h = C.c_void_p()
+    if conservative:
+        L.check(L.lib().dccm_table_gen_jones99_separable(src.im, L.dp(src.x_Lon), src.jm, L.dp(src.y_Lat),
+                                                         dst.im, L.dp(dst.x_Lon), dst.jm, L.dp(dst.y_Lat),
+                                                         L.dp(src.y_LatWt), L.dp(dst.y_LatWt),
+                                                         accuracy_order, lon_mode, C.byref(h)))
+    else:
+        L.check(L.lib().dccm_table_gen_bilinear_separable(src.im, L.dp(src.x_Lon), src.jm, L.dp(src.y_Lat),
+                                                          dst.im, L.dp(dst.x_Lon), dst.jm, L.dp(dst.y_Lat),
+                                                          lon_mode, C.byref(h)))
+    return MappingTable(h)

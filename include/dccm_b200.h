@@ -75,6 +75,17 @@ int dccm_table_gen_jones99_rows(int nxs, const double *x_LonS, int nys, const do
 int dccm_table_gen_bilinear_rows(int nxs, const double *x_LonS, int nys, const double *y_LatS,
                                  int nxr, const double *x_LonR, int nyr, const double *y_LatR,
                                  int lon_mode, int jr_first, int jr_last, dccm_table **out);
+/* The same tables produced by multiplying out the separable factors (longitude list per destination column x
+ * latitude list per destination row) the way the kind-2 kernels do: identical to the generators' output entry for
+ * entry wherever the separable form applies (Jones99: different longitudes, 1st order; bilinear: nx > 1 on both
+ * sides), DCCM_ERR_UNSUPPORTED otherwise.  Host only. */
+int dccm_table_gen_jones99_separable(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                                     int nxd, const double *x_LonD, int nyd, const double *y_LatD,
+                                     const double *y_LatIntWtS, const double *y_LatIntWtD,
+                                     int accuracy_order, int lon_mode, dccm_table **out);
+int dccm_table_gen_bilinear_separable(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                                      int nxr, const double *x_LonR, int nyr, const double *y_LatR,
+                                      int lon_mode, dccm_table **out);
 /* The reference's on-disk format: one entry per line "iD jD iS jS coef", list-directed
  * (ref common/grid_mapping_util_jones99.f90:246-247, :479-504). */
 int dccm_table_write_text(const dccm_table *t, const char *filename);
@@ -108,13 +119,27 @@ int dccm_remap_create(int64_t nops, const int32_t *send_index, const int32_t *re
 int dccm_remap_create_lonlat(int64_t nops, const int32_t *send_index, const int32_t *recv_index,
                              const double *coef, int n_send, int n_recv, int gnxs, int gnxr,
                              dccm_remap **out);
+/* Generate-and-create in one step: same arguments as the generators above, the operator comes
+ * back without the table ever being built.  Grid pairs with different longitudes (lon_mode 1) give a SEPARABLE
+ * operator (dccm_remap_kind() == 2): per-column longitude factors and per-row latitude factors, O(nx + ny) numbers
+ * that the kernels multiply out exactly as the generator would have (same order, same product, same 1e-14 drop
+ * test) -- bit-identical results, no O(nx*ny) table in memory or in the kernels' traffic.  Equal longitudes,
+ * nx == 1 and 2nd order go through the generator and dccm_remap_create_lonlat (kind 1 or 0). */
+int dccm_remap_create_jones99(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                              int nxd, const double *x_LonD, int nyd, const double *y_LatD,
+                              const double *y_LatIntWtS, const double *y_LatIntWtD,
+                              int accuracy_order, int lon_mode, dccm_remap **out);
+int dccm_remap_create_bilinear(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                               int nxr, const double *x_LonR, int nyr, const double *y_LatR,
+                               int lon_mode, dccm_remap **out);
 /* host-only: the storage form dccm_remap_create_lonlat would choose (kind, entries kept) */
 int dccm_remap_classify(int64_t nops, const int32_t *send_index, const int32_t *recv_index,
                         const double *coef, int n_send, int n_recv, int gnxs, int gnxr,
                         int *kind, int64_t *stored_entries);
 void dccm_remap_destroy(dccm_remap *h);
 int64_t dccm_remap_nnz(const dccm_remap *h);
-/* 0 = general destination-row CSR, 1 = zonal stencil (one stencil per destination latitude row) */
+/* 0 = general destination-row CSR, 1 = zonal stencil (one stencil per destination latitude row),
+ * 2 = separable (longitude factors x latitude factors, dccm_remap_create_jones99 / _bilinear) */
 int dccm_remap_kind(const dccm_remap *h);
 /* recv_data(:,:) = 0 ; recv(r_i,d) += send(s_i,d)*coef(i), d = 1..num_of_data  (ref :293-302) */
 int dccm_remap_apply_host(dccm_remap *h, const double *send, int sn1, int sn2,

@@ -167,3 +167,24 @@ def test_zonal_stencil_detection_is_exact(dccm, orc):
     k, n = C.c_int(), C.c_int64()
     L.check(L.lib().dccm_remap_classify(len(c2), L.ip(s), L.ip(r), L.dp(c2), S.n, A.n, S.im, A.im, C.byref(k), C.byref(n)))
     assert k.value == 0
+
+
+@pytest.mark.parametrize("name", ["T21_1deg", "T106_1deg"])
+def test_separable_factors_multiply_out_to_the_generated_tables(dccm, name):
+    """for grid pairs with different longitudes the kind-2 operator keeps per-column longitude
+    factors and per-row latitude factors only; multiplied out in the kernels' order (with the generator's 1e-14
+    drop test) they give the generators' tables entry for entry, bit for bit.  Equal longitudes are refused
+    (those tables are zonal stencils)."""
+    from util import pair
+    T = dccm.tables
+    A, O, S = pair(None, dccm, name)
+    for src, dst in ((O, S), (S, O), (A, O), (O, A)):
+        for cons in (True, False):
+            want = (T.gen_table_jones99(src, dst, 1, 1) if cons else T.gen_table_bilinear(src, dst, 1)).entries()
+            got = T.gen_table_separable(src, dst, cons).entries()
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b), (name, src.im, dst.im, cons)
+    with pytest.raises(dccm.DccmError):              # equal longitudes, conservative: a zonal stencil, not this form
+        T.gen_table_separable(A, S, True)
+    for a, b in zip(T.gen_table_separable(A, S, False).entries(), T.gen_table_bilinear(A, S, 1).entries()):
+        assert np.array_equal(a, b)                  # the 4-point bilinear form is separable for any longitudes

@@ -71,6 +71,30 @@ def test_remap_zonal_stencil_form_bit_exact(gpu, orc, dccm, S, name):
     assert 1 in kinds, kinds
 
 
+@pytest.mark.parametrize("name", ["T21_1deg", "T106_1deg"])
+def test_remap_separable_form_bit_exact(gpu, orc, dccm, S, name):
+    """operators created straight from the grids (dccm_remap_create_jones99 / _bilinear).  Pairs with
+    different longitudes come back in separable form (kind 2: longitude factors x latitude factors, multiplied out
+    in the kernel); their results have the bits of the CSR operator built from the generated table, and nnz counts
+    the entries that table holds.  Equal longitudes come back as zonal stencils (kind 1)."""
+    import torch
+    T = dccm.tables
+    A, O, Sx = pair(orc, dccm, name)
+    for label, s, d in (("O->S", O, Sx), ("S->O", Sx, O), ("A->O", A, O), ("O->A", O, A), ("A->S", A, Sx)):
+        for cons in (True, False):
+            tab = T.gen_table_jones99(s, d, 1, 1) if cons else T.gen_table_bilinear(s, d, 1)
+            si, ri, cf = tab.index(s.im, d.im)
+            csr = dccm.RemapOperator(si, ri, cf, s.n, d.n)                        # kind 0
+            op = dccm.RemapOperator.from_grids(s, d, cons)
+            assert csr.kind == 0 and op.kind == (1 if s.im == d.im else 2), (label, cons, op.kind)
+            assert op.nnz == len(cf), (label, cons)
+            for D in (1, 3, 10, 13):
+                x = torch.as_tensor(S.generic_fields(np, s, D), device=gpu).contiguous()
+                assert torch.equal(op.apply(x), csr.apply(x)), (label, cons, D)
+            x = S.generic_fields(np, s, 4)
+            assert np.array_equal(op.apply_host(x), orc.remap_apply(si, ri, cf, x, d.n)), (label, cons, "host")
+
+
 @pytest.mark.parametrize("D", [1, 5, 8, 17, 43])
 def test_remap_field_counts_and_zero_fill(gpu, orc, dccm, S, D):
     """recv_data(:,:) = 0 covers ALL rn2 columns and rows beyond the table
@@ -535,6 +559,46 @@ def test_fused_surface_kernel_redo_list_for_out_of_range_operands(gpu, orc, dccm
                 ex.sfc_fused()
                 torch.cuda.synchronize()
                 assert same(ex.s2a, want[0]) and same(ex.s2o, want[1]), (how, staged, inputs is clean)
+    finally:
+        L.check(L.lib().dccm_sfc_exchange_config(1, 5))
+
+
+@pytest.mark.parametrize("name,members", [("T21_1deg", 1), ("T106_1deg", 2), ("T42_T42", 1)])
+def test_exchange_from_grids_equals_exchange_from_tables(gpu, orc, dccm, S, name, members):
+    """SurfaceExchange built straight from the grids (no table on the host; ocean-side operators separable where the
+    longitudes differ) against the same exchange built from the generated tables: every output bit for bit, fused
+    (staged and direct form) and unfused."""
+    import torch
+    X = importlib.import_module("dennou-ccm_b200.exchange")
+    L = dccm._lib
+    A, O, Sx = pair(orc, dccm, name)
+    M, K = members, 9
+    tt = lambda d: {k: torch.as_tensor(v, device=gpu).contiguous() for k, v in d.items()}
+    cols = [tt(S.column_inputs(np, A, K, 1, member=m)) for m in range(M)]
+    atms = [tt(S.atm_surface_fields(np, A, member=m)) for m in range(M)]
+    ocns = [tt(S.ocn_surface_fields(np, O, member=m)) for m in range(M)]
+    inputs = ({k: torch.cat([c[k] for c in cols], dim=-1).contiguous() for k in cols[0]},
+              {k: torch.stack([a[k] for a in atms]) for k in atms[0]},
+              {k: torch.stack([o[k] for o in ocns]) for k in ocns[0]})
+    ref = X.SurfaceExchange(A, O, Sx, K, 1, 1, tabs=X.build_tables(A, O, Sx), members=M, device=gpu)
+    ref.set_inputs(*inputs)
+    ref.step(fused=False)
+    ex = X.SurfaceExchange(A, O, Sx, K, 1, 1, members=M, device=gpu)
+    want_kind = 2 if O.im != Sx.im else 1
+    assert {ex.ops[k].kind for k in ("os_cons", "os_bil", "so_cons", "so_bil")} == {want_kind}
+    assert ex.nnz == ref.nnz
+    ex.set_inputs(*inputs)
+    try:
+        for fused, staged in ((False, 1), (True, 1), (True, 0)):
+            L.check(L.lib().dccm_sfc_exchange_config(staged, 5))
+            for t in (ex.s2a, ex.s2o, ex.a_recv, ex.o_recv):
+                t.fill_(float("nan"))
+            ex.step(fused=fused)
+            torch.cuda.synchronize()
+            for k in ("s2a", "s2o", "a_recv", "o_recv"):
+                assert torch.equal(getattr(ex, k), getattr(ref, k)), (k, fused, staged)
+            for k in ex.tend:
+                assert torch.equal(ex.tend[k], ref.tend[k]), (k, fused, staged)
     finally:
         L.check(L.lib().dccm_sfc_exchange_config(1, 5))
 
