@@ -121,17 +121,16 @@ __device__ __forceinline__ void gather(const Csr &t, int r, const SrcSeg &src, i
 }
 
 // One destination cell of a separable (kind 2) table, D layers: the column's x-list and the row's y-list are a few
-// L1-resident entries; every (m, n) pair is rebuilt as the generator emitted it (order, product, 1e-14 drop test).
+// L1-resident entries at fixed offsets (no pointer load); every (m, n) pair is rebuilt as the generator emitted it
+// (order, product, 1e-14 drop test).
 template <int D, bool SEG>
-__device__ __forceinline__ void gather_sep(const SepTab &t, int r, const SrcSeg &src, int64_t n_src, int M, int m,
+__device__ __forceinline__ void gather_sep(const SepTab &t, int iD, int jD, const SrcSeg &src, int64_t n_src, int M, int m,
                                            double (&acc)[D])
 {
 #pragma unroll
     for (int d = 0; d < D; d++) acc[d] = 0.0;
     const int64_t o0 = (int64_t)m * n_src, lstride = (int64_t)M * n_src;
-    const int jD = r / t.nxd, iD = r - jD * t.nxd;
-    const int x0 = __ldg(&t.xptr[iD]), x1 = __ldg(&t.xptr[iD + 1]);
-    const int y0 = __ldg(&t.yptr[jD]), y1 = __ldg(&t.yptr[jD + 1]);
+    const int x0 = iD * t.wx, y0 = jD * t.wy, y1 = y0 + t.wy;
     if (t.mode == 1) {                         // bilinear: (m0,n0) (m1,n0) (m1,n1) (m0,n1), nothing dropped
         const int i0 = __ldg(&t.xi[x0]), i1 = __ldg(&t.xi[x0 + 1]);
         const double a0 = __ldg(&t.xw[x0]), a1 = __ldg(&t.xw[x0 + 1]);
@@ -152,7 +151,7 @@ __device__ __forceinline__ void gather_sep(const SepTab &t, int r, const SrcSeg 
             for (int d = 0; d < D; d++) acc[d] = __dadd_rn(acc[d], __dmul_rn(v[j][d], w[j]));
         return;
     }
-    for (int mm = x0; mm < x1; mm++) {
+    for (int mm = x0; mm < x0 + t.wx; mm++) {
         const int i = __ldg(&t.xi[mm]);
         const double a = __ldg(&t.xw[mm]);
         for (int nb = y0; nb < y1; nb += 3) {
@@ -164,7 +163,7 @@ __device__ __forceinline__ void gather_sep(const SepTab &t, int r, const SrcSeg 
                 on[j] = nb + j < y1;
                 c[j] = on[j] ? __ldg(&t.yj[nb + j]) * t.nxs + i : 0;
                 w[j] = on[j] ? __dmul_rn(a, __ldg(&t.yw[nb + j])) : 0.0;
-                on[j] = on[j] && fabs(w[j]) > 1e-14;
+                on[j] = fabs(w[j]) > 1e-14;
             }
 #pragma unroll
             for (int j = 0; j < 3; j++) {
@@ -190,8 +189,12 @@ template <int D, int CH, bool SEG>
 __device__ __forceinline__ void gather_any(const Csr &t, const SepTab &ts, int r, const SrcSeg &src, int64_t n_src,
                                            int M, int m, double (&acc)[D])
 {
-    if (t.kind == 2) gather_sep<D, SEG>(ts, r, src, n_src, M, m, acc);
-    else gather<D, CH, SEG>(t, r, src, n_src, M, m, acc);
+    if (t.kind == 2) {
+        const int jD = r / ts.nxd;
+        gather_sep<D, SEG>(ts, r - jD * ts.nxd, jD, src, n_src, M, m, acc);
+    } else {
+        gather<D, CH, SEG>(t, r, src, n_src, M, m, acc);
+    }
 }
 
 // The two ocean-side tables of one cell (CSR: ocean and exchange-grid longitudes differ), software-pipelined.
@@ -543,6 +546,9 @@ __global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_staged_kernel(con
         if (ocsr) {
             og.pairs(a.os_bil, a.os_cons);
             og.finish(a.os_bil, a.os_cons, a.o2s_bil, a.o2s_cons, a.nO, M, m, ob, oc);
+        } else if (a.os_bil.kind == 2 && a.os_cons.kind == 2) {
+            gather_sep<2, SEG>(a.os_bil_sep, i0 + tid, jD, a.o2s_bil, a.nO, M, m, ob);
+            gather_sep<3, SEG>(a.os_cons_sep, i0 + tid, jD, a.o2s_cons, a.nO, M, m, oc);
         } else {
             gather_any<2, 4, SEG>(a.os_bil, a.os_bil_sep, r, a.o2s_bil, a.nO, M, m, ob);
             gather_any<3, 4, SEG>(a.os_cons, a.os_cons_sep, r, a.o2s_cons, a.nO, M, m, oc);

@@ -131,8 +131,9 @@ remap_zonal_kernel(const int32_t *__restrict__ zptr, const int32_t *__restrict__
 }
 
 // kind 2: separable generated table, one thread per destination cell.  The x-list of the cell's column and the
-// y-list of its row are a few L1-resident entries; each (m, n) pair is rebuilt exactly as the generator emitted it
-// (order, product, drop test), three latitude entries at a time so their source loads are in flight together.
+// y-list of its row are a few L1-resident entries at fixed offsets; each (m, n) pair is rebuilt exactly as the
+// generator emitted it (order, product, drop test), three latitude entries at a time so their source loads are in
+// flight together.
 template <int FB, bool SEG>
 __global__ void __launch_bounds__(kThreads)
 remap_sep_kernel(const SepTab t, const SrcSeg send, int64_t sn1, double *__restrict__ recv, int64_t rn1,
@@ -141,8 +142,7 @@ remap_sep_kernel(const SepTab t, const SrcSeg send, int64_t sn1, double *__restr
     const int r = blockIdx.x * kThreads + threadIdx.x;
     if (r >= n_recv) return;
     const int jD = r / t.nxd, iD = r - jD * t.nxd;
-    const int x0 = __ldg(&t.xptr[iD]), x1 = __ldg(&t.xptr[iD + 1]);
-    const int y0 = __ldg(&t.yptr[jD]), y1 = __ldg(&t.yptr[jD + 1]);
+    const int x0 = iD * t.wx, y0 = jD * t.wy, y1 = y0 + t.wy;
     const int d_begin = blockIdx.y * fields_per_y;
     const int d_end = min(nfield, d_begin + fields_per_y);
     for (int d0 = d_begin; d0 < d_end; d0 += FB) {
@@ -170,7 +170,7 @@ remap_sep_kernel(const SepTab t, const SrcSeg send, int64_t sn1, double *__restr
             add(j0 + i0, __dmul_rn(a0, b0)); add(j0 + i1, __dmul_rn(a1, b0));
             add(j1 + i1, __dmul_rn(a1, b1)); add(j1 + i0, __dmul_rn(a0, b1));
         } else {
-            for (int m = x0; m < x1; m++) {
+            for (int m = x0; m < x0 + t.wx; m++) {
                 const int i = __ldg(&t.xi[m]);
                 const double a = __ldg(&t.xw[m]);
                 for (int nb = y0; nb < y1; nb += 3) {
@@ -184,7 +184,7 @@ remap_sep_kernel(const SepTab t, const SrcSeg send, int64_t sn1, double *__restr
                     }
 #pragma unroll
                     for (int j = 0; j < 3; j++)
-                        if (nb + j < y1 && fabs(w[j]) > 1e-14) add(c[j], w[j]);
+                        if (fabs(w[j]) > 1e-14) add(c[j], w[j]);
                 }
             }
         }
@@ -367,7 +367,7 @@ extern "C" int dccm_remap_create_lonlat(int64_t nops, const int32_t *send_index,
 
 SepTab sep_of(const dccm_remap *h)
 {
-    return SepTab{h->d_xptr, h->d_xi, h->d_yptr, h->d_yj, h->d_xw, h->d_yw, h->sep_mode, h->nxs, h->nxd};
+    return SepTab{h->d_xi, h->d_yj, h->d_xw, h->d_yw, h->sep_mode, h->nxs, h->nxd, h->sep_wx, h->sep_wy};
 }
 
 namespace {
@@ -391,7 +391,6 @@ int create_separable(const SepFactors &f, dccm_remap **out)
     if (f.mode == 1) { nnz = 4 * (int64_t)h->n_recv; maxrow = 4; }
     else {
         // count per (x-entry, y-entry) pair once: the kept pairs of column iD and row jD multiply out
-        std::vector<int64_t> kept_x(f.nxd, 0);
         for (int jD = 0; jD < f.nyd; jD++) {
             for (int iD = 0; iD < f.nxd; iD++) {
                 int k = 0;
@@ -403,14 +402,29 @@ int create_separable(const SepFactors &f, dccm_remap **out)
         }
     }
     h->nnz = nnz; h->max_row_nnz = maxrow;
+    // fixed-width lists: pad with (index 0, weight 0.0)
+    auto pad = [](const std::vector<int32_t> &ptr, const std::vector<int32_t> &idx, const std::vector<double> &w, int n,
+                  int &width, std::vector<int32_t> &pidx, std::vector<double> &pw) {
+        width = 1;
+        for (int k = 0; k < n; k++) width = std::max(width, ptr[k + 1] - ptr[k]);
+        pidx.assign((size_t)n * width, 0);
+        pw.assign((size_t)n * width, 0.0);
+        for (int k = 0; k < n; k++)
+            for (int e = ptr[k]; e < ptr[k + 1]; e++) {
+                pidx[(size_t)k * width + (e - ptr[k])] = idx[e];
+                pw[(size_t)k * width + (e - ptr[k])] = w[e];
+            }
+    };
+    std::vector<int32_t> pxi, pyj;
+    std::vector<double> pxw, pyw;
+    pad(f.xptr, f.xi, f.xw, f.nxd, h->sep_wx, pxi, pxw);
+    pad(f.yptr, f.yj, f.yw, f.nyd, h->sep_wy, pyj, pyw);
     cudaError_t e = cudaMalloc(&h->d_redo, sizeof(int) * (2 + 2 * (size_t)dccm_remap::kRedoCap));
     if (e == cudaSuccess) e = cudaMemset(h->d_redo, 0, sizeof(int) * 2);
-    if (e == cudaSuccess) e = upload(h->d_xptr, f.xptr);
-    if (e == cudaSuccess) e = upload(h->d_xi, f.xi);
-    if (e == cudaSuccess) e = upload(h->d_xw, f.xw);
-    if (e == cudaSuccess) e = upload(h->d_yptr, f.yptr);
-    if (e == cudaSuccess) e = upload(h->d_yj, f.yj);
-    if (e == cudaSuccess) e = upload(h->d_yw, f.yw);
+    if (e == cudaSuccess) e = upload(h->d_xi, pxi);
+    if (e == cudaSuccess) e = upload(h->d_xw, pxw);
+    if (e == cudaSuccess) e = upload(h->d_yj, pyj);
+    if (e == cudaSuccess) e = upload(h->d_yw, pyw);
     if (e != cudaSuccess) {
         dccm_remap_destroy(h);
         return fail(DCCM_ERR_CUDA, "dccm_remap_create (separable): %s", cudaGetErrorString(e));
@@ -478,7 +492,7 @@ extern "C" void dccm_remap_destroy(dccm_remap *h)
     }
     cudaFree(h->d_rowptr); cudaFree(h->d_col); cudaFree(h->d_w);
     cudaFree(h->d_zptr); cudaFree(h->d_zdj); cudaFree(h->d_zw); cudaFree(h->d_redo);
-    cudaFree(h->d_xptr); cudaFree(h->d_xi); cudaFree(h->d_yptr); cudaFree(h->d_yj); cudaFree(h->d_xw); cudaFree(h->d_yw);
+    cudaFree(h->d_xi); cudaFree(h->d_yj); cudaFree(h->d_xw); cudaFree(h->d_yw);
     h->send_buf.release(); h->recv_buf.release();
     delete h;
 }

@@ -19,11 +19,14 @@ struct SrcSeg {
 inline SrcSeg seg_of(const double *p) { return SrcSeg{p, p, p, 0, INT64_MAX}; }
 inline SrcSeg seg_of(const dccm_src_seg *s) { return SrcSeg{s->lo, s->own, s->hi, s->b0, s->b1}; }
 
-// kind-2 table as the kernels see it
+// kind-2 table as the kernels see it: fixed-width lists, wx entries per destination column and wy per destination
+// row (shorter lists are padded with weight 0, which the mode-0 drop test |w| > 1e-14 discards like the generator
+// discards any other negligible entry; mode 1 lists are exactly 2 wide), so a cell finds its entries at
+// iD*wx / jD*wy without a pointer load.
 struct SepTab {
-    const int32_t *xptr, *xi, *yptr, *yj;
+    const int32_t *xi, *yj;
     const double *xw, *yw;
-    int mode, nxs, nxd;
+    int mode, nxs, nxd, wx, wy;
 };
 
 struct dccm_remap {
@@ -53,8 +56,8 @@ struct dccm_remap {
     // kind 2: separable form of a generated table (dccm_sep.h): per destination column a list of (source column,
     // longitude factor), per destination row a list of (source row, latitude factor); the kernels rebuild each
     // entry as the generator did (weight = xw * yw, mode 0 drops |w| <= 1e-14).  nxs / nxd / nyd as for kind 1.
-    int sep_mode = 0;
-    int32_t *d_xptr = nullptr, *d_xi = nullptr, *d_yptr = nullptr, *d_yj = nullptr;
+    int sep_mode = 0, sep_wx = 0, sep_wy = 0;
+    int32_t *d_xi = nullptr, *d_yj = nullptr;
     double *d_xw = nullptr, *d_yw = nullptr;
     // fused surface kernel: cells to re-evaluate with plain IEEE operators (csrc/dccm_exchange.cu); the list of
     // the A->S bilinear handle is the one used.  Allocated at creation (never inside a stream capture).
