@@ -533,9 +533,18 @@ extern "C" int dccm_remap_apply_seg_device(dccm_remap *h, const dccm_src_seg *se
     int FB = 13;
     for (int f : kFB) if (num_of_data <= f) { FB = f; break; }
     const int want = 4 * num_sms();
-    if (gx < want && num_of_data > 2) FB = 2;
+    if (gx < want) {          // few rows: the largest block that still leaves enough field groups to fill the machine
+        const int groups = (want + gx - 1) / gx;
+        FB = 2;
+        for (int f : kFB) if (f <= num_of_data && (num_of_data + f - 1) / f >= groups) FB = f;
+    }
+    // separable operators re-derive their entries from L1-resident factors, so splitting the fields over more
+    // threads costs no table traffic and buys occupancy: blocks of at most kSepFB fields, one block per grid.y
+    static const int kSepFB = getenv("DCCM_SEP_FB") ? atoi(getenv("DCCM_SEP_FB")) : 13;
+    const bool split_sep = h->kind == 2 && num_of_data > kSepFB;
+    if (split_sep) { FB = 2; for (int f : kFB) if (f <= kSepFB) FB = f; }
     int nfb = (num_of_data + FB - 1) / FB;
-    int gy = std::min(nfb, std::max(1, (want + gx - 1) / gx));
+    int gy = split_sep ? nfb : std::min(nfb, std::max(1, (want + gx - 1) / gx));
     int fields_per_y = ((nfb + gy - 1) / gy) * FB;
     gy = (num_of_data + fields_per_y - 1) / fields_per_y;
     dim3 grid(gx, gy);
