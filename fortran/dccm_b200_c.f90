@@ -79,6 +79,26 @@ module dccm_b200_c
        real(c_double) :: DUDt(*), DVDt(*), DTempDt(*), DQMixDt(*)
        integer(c_int) :: rc
      end function
+     !> operator straight from the axis arrays gmapgen hands to gen_gridmapfile_lonlat2lonlat
+     !! (ref common/grid_mapping_util_jones99.f90:35-54): no table file, separable form for different longitudes
+     function dccm_remap_create_jones99(nxs, x_LonS, nys, y_LatS, nxd, x_LonD, nyd, y_LatD, &
+          & y_LatIntWtS, y_LatIntWtD, accuracy_order, lon_mode, handle) &
+          & bind(C, name="dccm_remap_create_jones99") result(rc)
+       import
+       integer(c_int), value :: nxs, nys, nxd, nyd, accuracy_order, lon_mode
+       real(c_double), intent(in) :: x_LonS(nxs), y_LatS(nys), x_LonD(nxd), y_LatD(nyd), y_LatIntWtS(nys), y_LatIntWtD(nyd)
+       type(c_ptr), intent(out) :: handle
+       integer(c_int) :: rc
+     end function
+     !> same for the bilinear generator (ref common/grid_mapping_util.f90:32-48)
+     function dccm_remap_create_bilinear(nxs, x_LonS, nys, y_LatS, nxr, x_LonR, nyr, y_LatR, lon_mode, handle) &
+          & bind(C, name="dccm_remap_create_bilinear") result(rc)
+       import
+       integer(c_int), value :: nxs, nys, nxr, nyr, lon_mode
+       real(c_double), intent(in) :: x_LonS(nxs), y_LatS(nys), x_LonR(nxr), y_LatR(nyr)
+       type(c_ptr), intent(out) :: handle
+       integer(c_int) :: rc
+     end function
   end interface
 
 contains
