@@ -71,6 +71,8 @@ _SIGS = {
     "dccm_init": (C.c_int, [C.c_int]),
     "dccm_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "dccm_sync": (C.c_int, [vp]),
+    "dccm_host_register": (C.c_int, [vp, C.c_int64]),
+    "dccm_host_unregister": (C.c_int, [vp]),
     "dccm_grid_gauss": (C.c_int, [C.c_int, C.c_int, f64p, f64p, f64p, f64p]),
     "dccm_grid_regular": (C.c_int, [C.c_int, C.c_int, f64p, f64p, f64p, f64p]),
     "dccm_grid_exchange": (C.c_int, [C.c_int, f64p, f64p, C.c_int, f64p, C.POINTER(C.c_int), f64p, f64p]),

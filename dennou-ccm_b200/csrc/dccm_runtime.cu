@@ -111,3 +111,21 @@ extern "C" int dccm_sync(void *stream)
     DCCM_CUDA_TRY(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
     return DCCM_OK;
 }
+
+// Page-lock a caller-owned host array (cudaHostRegister) so that the *_host entry points can overlap their
+// H2D / kernel / D2H chunks; pageable arrays work too, the copies then serialise through the driver's staging.
+extern "C" int dccm_host_register(void *ptr, int64_t bytes)
+{
+    if (!ptr || bytes <= 0) return fail(DCCM_ERR_ARG, "dccm_host_register: bad arguments");
+    int rc = ensure_device();
+    if (rc) return rc;
+    DCCM_CUDA_TRY(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    return DCCM_OK;
+}
+
+extern "C" int dccm_host_unregister(void *ptr)
+{
+    if (!ptr) return fail(DCCM_ERR_ARG, "dccm_host_unregister: null pointer");
+    DCCM_CUDA_TRY(cudaHostUnregister(ptr));
+    return DCCM_OK;
+}

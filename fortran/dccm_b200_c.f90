@@ -10,6 +10,10 @@ module dccm_b200_c
      function dccm_init(device) bind(C, name="dccm_init") result(rc)
        import; integer(c_int), value :: device; integer(c_int) :: rc
      end function
+     !> page-lock a module array once at init (c_loc(array), bytes): lets the *_host calls overlap their copies
+     function dccm_host_register(ptr, bytes) bind(C, name="dccm_host_register") result(rc)
+       import; type(c_ptr), value :: ptr; integer(c_int64_t), value :: bytes; integer(c_int) :: rc
+     end function
      function dccm_last_error() bind(C, name="dccm_last_error") result(msg)
        import; type(c_ptr) :: msg
      end function

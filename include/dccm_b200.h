@@ -38,6 +38,12 @@ int dccm_init(int device);                 /* cudaSetDevice + capability check (
 int dccm_device_count(int *count);
 int dccm_sync(void *stream);               /* cudaStreamSynchronize */
 
+/* Page-lock / release a caller-owned host array (e.g. the module arrays of DSFCM_Admin_Variable_mod or DCPAM's
+ * tendency arrays, once at init).  The *_host entry points move their arguments in chunks with H2D, kernel and D2H
+ * overlapped on three streams; that overlap needs page-locked memory (pageable arrays still work, serialised). */
+int dccm_host_register(void *ptr, int64_t bytes);
+int dccm_host_unregister(void *ptr);
+
 /* ------------------------------------------------------------------ grids
  * Stand-ins for the SPML w_module axes gmapgen uses (ref tool/gmapgen/gmapgen_main.f90:256-307). */
 int dccm_grid_gauss(int im, int jm, double *x_Lon, double *y_Lat, double *x_LonWt, double *y_LatWt);

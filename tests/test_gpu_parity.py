@@ -324,6 +324,24 @@ def test_vdiff_host_calls_pipelined_over_column_chunks(gpu, orc, dccm, S, chunks
         assert np.array_equal(a, b)
 
 
+def test_host_register_pins_caller_arrays(gpu, dccm):
+    """dccm_host_register / _unregister: page-lock a caller-owned array (what a Fortran component does once at init
+    for its module arrays) -- the array is then usable by the pipelined *_host entry points like any other."""
+    import torch
+    L = dccm._lib
+    a = np.arange(1 << 16, dtype=np.float64)
+    L.check(L.lib().dccm_host_register(a.ctypes.data, a.nbytes))
+    try:
+        t = torch.empty(a.size, dtype=torch.float64, device=gpu)
+        t.copy_(torch.from_numpy(a), non_blocking=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(t.cpu().numpy(), a)
+    finally:
+        L.check(L.lib().dccm_host_unregister(a.ctypes.data))
+    with pytest.raises(dccm.DccmError):
+        L.check(L.lib().dccm_host_register(None, 8))
+
+
 def test_vdiff_fast_mode_within_tolerance(gpu, orc, dccm, S):
     g, inp = _vdiff_case(S, dccm, 128, 64, 26, 2)
     args = (g.im, g.jm, 26, 2, 1, S.GRAV, S.CPDRY, S.GASRDRY, S.DELTIME)
