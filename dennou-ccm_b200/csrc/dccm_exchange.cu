@@ -441,38 +441,23 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 
 struct StagePlan { int a, b, nslots; };
 
-// One lane's share of a row's stencil: lane l < n holds entry l (loaded by stage_fetch, resolved by stage_plan).
-struct StageEntry { int n, di, js; double w; };
-
-// Warp 0, all lanes, step 1: the stencil row's extent (both tables' extents are requested before either is used).
-__device__ __forceinline__ void stage_extent(const Csr &t, int jD, int &e0, int &n)
-{
-    e0 = __ldg(&t.rowptr[jD]);
-    n = __ldg(&t.rowptr[jD + 1]);
-}
-// step 2: the entries (again for both tables before either is resolved)
-__device__ __forceinline__ StageEntry stage_fetch(const Csr &t, int e0, int e1, int lane)
-{
-    StageEntry s;
-    s.n = e1 - e0; s.di = 0; s.js = -1 - lane; s.w = 0.0;     // idle lanes: distinct keys, never a row
-    if (lane < s.n) {
-        s.di = __ldg(&t.col[2 * (e0 + lane)]);
-        s.js = __ldg(&t.col[2 * (e0 + lane) + 1]);
-        s.w = __ldg(&t.w[e0 + lane]);
-    }
-    return s;
-}
-// step 3: resolve the stencil of destination row jD into shared-memory offsets and decide which source rows go
-// to which tile slot.  The tile of a slot holds logical source columns [a, b) (both even, so every copy is
-// 16-byte aligned), wrapped into [0, nxs) piece by piece when issued.
+// Warp 0, all lanes: resolve the stencil of destination row jD into shared-memory offsets and decide
+// which source rows go to which tile slot.  The tile of a slot holds logical source columns [a, b)
+// (both even, so every copy is 16-byte aligned), wrapped into [0, nxs) piece by piece when issued.
 template <int D>
-__device__ __forceinline__ StagePlan stage_plan(const Csr &t, int dmin, int dmax, StageEntry s, int i0, int nact,
+__device__ __forceinline__ StagePlan stage_plan(const Csr &t, int dmin, int dmax, int jD, int i0, int nact,
                                                 ZStage &zs, int lane)
 {
-    const int n = s.n;
-    int di = s.di;
-    const int js = s.js;
-    if (lane < n && di > t.nxs / 2) di -= t.nxs;  // westward neighbour
+    const int e0 = __ldg(&t.rowptr[jD]);
+    const int n = __ldg(&t.rowptr[jD + 1]) - e0;
+    int di = 0, js = -1 - lane;                   // idle lanes: distinct keys, never a row
+    double w = 0.0;
+    if (lane < n) {
+        di = __ldg(&t.col[2 * (e0 + lane)]);
+        js = __ldg(&t.col[2 * (e0 + lane) + 1]);
+        w = __ldg(&t.w[e0 + lane]);
+        if (di > t.nxs / 2) di -= t.nxs;          // westward neighbour
+    }
     const unsigned same = __match_any_sync(0xffffffffu, js);
     const int leader = __ffs(same) - 1;
     const bool first = leader == lane && lane < n;
@@ -482,7 +467,7 @@ __device__ __forceinline__ StagePlan stage_plan(const Csr &t, int dmin, int dmax
     p.a = (i0 + dmin) & ~1;
     p.b = (i0 + nact + dmax + 1) & ~1;
     p.nslots = __popc(firsts);
-    if (lane < n) { zs.soff[lane] = slot * (D * kTileW) + (di + i0 - p.a); zs.w[lane] = s.w; }
+    if (lane < n) { zs.soff[lane] = slot * (D * kTileW) + (di + i0 - p.a); zs.w[lane] = w; }
     if (first) zs.row_of_slot[slot] = js;
     if (lane == 0) zs.n = n;
     return p;
@@ -539,15 +524,26 @@ __global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_staged_kernel(con
     const int nact = min(kThreads, g.nxd - i0);
     const int M = a.M;
 
-    // Ocean / sea-ice side (direct gathers) and atmosphere side (tiles) overlap: warps 1-3 gather while warp 0 plans and
-    // issues the tiles; warp 0 gathers its own cells AFTER the CTA barrier, while its tiles are in flight -- so nobody
-    // waits at the barrier for warp 0 to do both (that wait was 21 % of the kernel's stall samples).
+    // ocean / sea-ice side: in flight while the atmosphere tiles are planned, issued and land
     const int r = jD * g.nxd + i0 + tid;
+    const bool ocsr = a.os_bil.kind == 0 && a.os_cons.kind == 0;
+    OceanGather<SEG> og;
+    if (ocsr && tid < nact) og.rows(a.os_bil, a.os_cons, r);
+
+    if (tid < 32) {
+        if (tid == 0) mbar_init(mbar, 1);
+        const StagePlan pb = stage_plan<13>(a.as_bil, g.dmin_bil, g.dmax_bil, jD, i0, nact, zs[0], tid);
+        const StagePlan pc = stage_plan<4>(a.as_cons, g.dmin_cons, g.dmax_cons, jD, i0, nact, zs[1], tid);
+        if (tid == 0)
+            mbar_arrive_expect_tx(mbar, 8u * (uint32_t)(pb.nslots * 13 * (pb.b - pb.a) + pc.nslots * 4 * (pc.b - pc.a)));
+        __syncwarp();
+        stage_issue<13, SEG>(a.as_bil, pb, zs[0], a.a2s_bil, a.nA, M, m, tile_bil, mbar, tid);
+        stage_issue<4, SEG>(a.as_cons, pc, zs[1], a.a2s_cons, a.nA, M, m, tile_cons, mbar, tid);
+    }
+
     double ob[2], oc[3];
-    auto ocean_side = [&]() {
-        if (a.os_bil.kind == 0 && a.os_cons.kind == 0) {
-            OceanGather<SEG> og;
-            og.rows(a.os_bil, a.os_cons, r);
+    if (tid < nact) {
+        if (ocsr) {
             og.pairs(a.os_bil, a.os_cons);
             og.finish(a.os_bil, a.os_cons, a.o2s_bil, a.o2s_cons, a.nO, M, m, ob, oc);
         } else if (a.os_bil.kind == 2 && a.os_cons.kind == 2) {
@@ -557,25 +553,8 @@ __global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_staged_kernel(con
             gather_any<2, 4, SEG>(a.os_bil, a.os_bil_sep, r, a.o2s_bil, a.nO, M, m, ob);
             gather_any<3, 4, SEG>(a.os_cons, a.os_cons_sep, r, a.o2s_cons, a.nO, M, m, oc);
         }
-    };
-    if (tid < 32) {
-        if (tid == 0) mbar_init(mbar, 1);
-        int eb, nb, ec, nc;
-        stage_extent(a.as_bil, jD, eb, nb);
-        stage_extent(a.as_cons, jD, ec, nc);
-        const StageEntry sb = stage_fetch(a.as_bil, eb, nb, tid), sc = stage_fetch(a.as_cons, ec, nc, tid);
-        const StagePlan pb = stage_plan<13>(a.as_bil, g.dmin_bil, g.dmax_bil, sb, i0, nact, zs[0], tid);
-        const StagePlan pc = stage_plan<4>(a.as_cons, g.dmin_cons, g.dmax_cons, sc, i0, nact, zs[1], tid);
-        if (tid == 0)
-            mbar_arrive_expect_tx(mbar, 8u * (uint32_t)(pb.nslots * 13 * (pb.b - pb.a) + pc.nslots * 4 * (pc.b - pc.a)));
-        __syncwarp();
-        stage_issue<13, SEG>(a.as_bil, pb, zs[0], a.a2s_bil, a.nA, M, m, tile_bil, mbar, tid);
-        stage_issue<4, SEG>(a.as_cons, pc, zs[1], a.a2s_cons, a.nA, M, m, tile_cons, mbar, tid);
-    } else if (tid < nact) {
-        ocean_side();
     }
     __syncthreads();                       // stencil records + barrier initialisation visible to every warp
-    if (tid < 32 && tid < nact) ocean_side();
     mbar_wait(mbar, 0);                    // tiles complete (every thread waits: no copy outlives the CTA)
     if (tid >= nact) return;
 
