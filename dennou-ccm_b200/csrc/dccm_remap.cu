@@ -268,6 +268,41 @@ int build_csr(int64_t nops, const int32_t *send_index, const int32_t *recv_index
 }
 }  // namespace
 
+namespace {
+// kind-1 storage of a handle: upload the per-row stencils and note what a CTA that stages source tiles in shared
+// memory must provision (longest stencil, most distinct source rows in one stencil, range of the signed shifts)
+int finish_zonal(dccm_remap *h, int nxs, int nxd, int nyd, const std::vector<int32_t> &zptr,
+                 const std::vector<int32_t> &zdi, const std::vector<int32_t> &zjs, const std::vector<double> &zw)
+{
+    h->kind = 1; h->nxs = nxs; h->nxd = nxd; h->nyd = nyd; h->znnz = (int64_t)zw.size();
+    h->z_dmin = INT32_MAX; h->z_dmax = INT32_MIN;
+    for (int jD = 0; jD < nyd; jD++) {
+        const int e0 = zptr[jD], e1 = zptr[jD + 1];
+        h->z_max_len = std::max(h->z_max_len, e1 - e0);
+        int rows = 0;
+        for (int e = e0; e < e1; e++) {
+            bool first = true;
+            for (int f = e0; f < e; f++) first = first && zjs[f] != zjs[e];
+            rows += first;
+            const int sd = zdi[e] > nxs / 2 ? zdi[e] - nxs : zdi[e];
+            h->z_dmin = std::min(h->z_dmin, sd); h->z_dmax = std::max(h->z_dmax, sd);
+        }
+        h->z_max_rows = std::max(h->z_max_rows, rows);
+    }
+    if (zw.empty()) h->z_dmin = h->z_dmax = 0;
+    std::vector<int32_t> zdj(2 * zdi.size());
+    for (size_t k = 0; k < zdi.size(); k++) { zdj[2 * k] = zdi[k]; zdj[2 * k + 1] = zjs[k]; }
+    cudaError_t e = cudaMalloc(&h->d_zptr, sizeof(int32_t) * zptr.size());
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_zdj, sizeof(int32_t) * std::max<size_t>(2, zdj.size()));
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_zw, sizeof(double) * std::max<size_t>(1, zw.size()));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_zptr, zptr.data(), sizeof(int32_t) * zptr.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_zdj, zdj.data(), sizeof(int32_t) * zdj.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_zw, zw.data(), sizeof(double) * zw.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail(DCCM_ERR_CUDA, "dccm_remap_create: %s", cudaGetErrorString(e));
+    return DCCM_OK;
+}
+}  // namespace
+
 // Host-only: which storage form would dccm_remap_create_lonlat pick (no GPU needed).
 extern "C" int dccm_remap_classify(int64_t nops, const int32_t *send_index, const int32_t *recv_index,
                                    const double *coef, int n_send, int n_recv, int gnxs, int gnxr,
@@ -319,34 +354,8 @@ extern "C" int dccm_remap_create_lonlat(int64_t nops, const int32_t *send_index,
         std::vector<int32_t> zptr, zdi, zjs;
         std::vector<double> zw;
         if (detect_zonal(rowptr, col, w, gnxs, gnxr, n_recv / gnxr, zptr, zdi, zjs, zw)) {
-            h->kind = 1; h->nxs = gnxs; h->nxd = gnxr; h->nyd = n_recv / gnxr; h->znnz = (int64_t)zw.size();
-            h->z_dmin = INT32_MAX; h->z_dmax = INT32_MIN;
-            for (int jD = 0; jD < h->nyd; jD++) {
-                const int e0 = zptr[jD], e1 = zptr[jD + 1];
-                h->z_max_len = std::max(h->z_max_len, e1 - e0);
-                int rows = 0;
-                for (int e = e0; e < e1; e++) {
-                    bool first = true;
-                    for (int f = e0; f < e; f++) first = first && zjs[f] != zjs[e];
-                    rows += first;
-                    const int sd = zdi[e] > gnxs / 2 ? zdi[e] - gnxs : zdi[e];
-                    h->z_dmin = std::min(h->z_dmin, sd); h->z_dmax = std::max(h->z_dmax, sd);
-                }
-                h->z_max_rows = std::max(h->z_max_rows, rows);
-            }
-            if (zw.empty()) h->z_dmin = h->z_dmax = 0;
-            std::vector<int32_t> zdj(2 * zdi.size());
-            for (size_t k = 0; k < zdi.size(); k++) { zdj[2 * k] = zdi[k]; zdj[2 * k + 1] = zjs[k]; }
-            e = cudaMalloc(&h->d_zptr, sizeof(int32_t) * zptr.size());
-            if (e == cudaSuccess) e = cudaMalloc(&h->d_zdj, sizeof(int32_t) * std::max<size_t>(2, zdj.size()));
-            if (e == cudaSuccess) e = cudaMalloc(&h->d_zw, sizeof(double) * std::max<size_t>(1, zw.size()));
-            if (e == cudaSuccess) e = cudaMemcpy(h->d_zptr, zptr.data(), sizeof(int32_t) * zptr.size(), cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) e = cudaMemcpy(h->d_zdj, zdj.data(), sizeof(int32_t) * zdj.size(), cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) e = cudaMemcpy(h->d_zw, zw.data(), sizeof(double) * zw.size(), cudaMemcpyHostToDevice);
-            if (e != cudaSuccess) {
-                dccm_remap_destroy(h);
-                return fail(DCCM_ERR_CUDA, "dccm_remap_create: %s", cudaGetErrorString(e));
-            }
+            rc = finish_zonal(h, gnxs, gnxr, n_recv / gnxr, zptr, zdi, zjs, zw);
+            if (rc) { dccm_remap_destroy(h); return rc; }
             *out = h;
             return DCCM_OK;
         }
@@ -433,6 +442,34 @@ int create_separable(const SepFactors &f, dccm_remap **out)
     return DCCM_OK;
 }
 
+// kind-1 handle straight from the per-row stencils of the generator (equal longitudes / axisymmetric source): the
+// O(nx*ny) table is never generated.  Same limits as the detection of dccm_remap_create_lonlat (at least two
+// destination columns, stencils of at most 64 entries); anything else goes through the table.
+bool zonal_ok(const SepFactors &f)
+{
+    if (!f.zonal || f.nxd < 2 || !(f.nxs == f.nxd || f.nxs == 1)) return false;
+    for (int jD = 0; jD < f.nyd; jD++)
+        if (f.zptr[jD + 1] - f.zptr[jD] > 64) return false;
+    return true;
+}
+
+int create_zonal(const SepFactors &f, dccm_remap **out)
+{
+    int rc = ensure_device();
+    if (rc) return rc;
+    dccm_remap *h = new dccm_remap();
+    h->n_send = f.nxs * f.nys; h->n_recv = f.nxd * f.nyd;
+    h->nnz = (int64_t)f.zw.size() * f.nxd;
+    for (int jD = 0; jD < f.nyd; jD++) h->max_row_nnz = std::max(h->max_row_nnz, f.zptr[jD + 1] - f.zptr[jD]);
+    cudaError_t e = cudaMalloc(&h->d_redo, sizeof(int) * (2 + 2 * (size_t)dccm_remap::kRedoCap));
+    if (e == cudaSuccess) e = cudaMemset(h->d_redo, 0, sizeof(int) * 2);
+    if (e != cudaSuccess) { dccm_remap_destroy(h); return fail(DCCM_ERR_CUDA, "dccm_remap_create (zonal): %s", cudaGetErrorString(e)); }
+    rc = finish_zonal(h, f.nxs, f.nxd, f.nyd, f.zptr, f.zdi, f.zjs, f.zw);
+    if (rc) { dccm_remap_destroy(h); return rc; }
+    *out = h;
+    return DCCM_OK;
+}
+
 // expanded-table route for the pairs the separable form does not take (zonal stencils, 2nd order)
 int create_from_table(dccm_table *t, int nxs, int nys, int nxd, int nyd, dccm_remap **out)
 {
@@ -456,6 +493,7 @@ extern "C" int dccm_remap_create_jones99(int nxs, const double *x_LonS, int nys,
     int rc = jones99_factors(nxs, x_LonS, nys, y_LatS, nxd, x_LonD, nyd, y_LatD, y_LatIntWtS, y_LatIntWtD,
                              accuracy_order, lon_mode, f);
     if (rc) return rc;
+    if (zonal_ok(f)) return create_zonal(f, out);
     if (f.ok) return create_separable(f, out);
     dccm_table *t = nullptr;
     rc = dccm_table_gen_jones99(nxs, x_LonS, nys, y_LatS, nxd, x_LonD, nyd, y_LatD, y_LatIntWtS, y_LatIntWtD,
@@ -470,11 +508,9 @@ extern "C" int dccm_remap_create_bilinear(int nxs, const double *x_LonS, int nys
 {
     *out = nullptr;
     SepFactors f;
-    bool same = nxs == nxr;
-    if (same) for (int i = 0; i < nxs; i++) if (x_LonS[i] != x_LonR[i]) { same = false; break; }
-    int rc = DCCM_OK;
-    if (!same) rc = bilinear_factors(nxs, x_LonS, nys, y_LatS, nxr, x_LonR, nyr, y_LatR, lon_mode, f);   // equal longitudes: zonal stencil
+    int rc = bilinear_factors(nxs, x_LonS, nys, y_LatS, nxr, x_LonR, nyr, y_LatR, lon_mode, f);
     if (rc) return rc;
+    if (zonal_ok(f)) return create_zonal(f, out);         // equal longitudes: one stencil per destination row
     if (f.ok) return create_separable(f, out);
     dccm_table *t = nullptr;
     rc = dccm_table_gen_bilinear(nxs, x_LonS, nys, y_LatS, nxr, x_LonR, nyr, y_LatR, lon_mode, &t);

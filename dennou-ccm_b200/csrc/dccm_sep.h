@@ -21,6 +21,12 @@ struct SepFactors {
     int nxs = 0, nys = 0, nxd = 0, nyd = 0;
     std::vector<int32_t> xptr, xi, yptr, yj;   // CSR lists per destination column / row, 0-based source indices
     std::vector<double> xw, yw;
+    // Equal longitudes (or an axisymmetric side): the table repeats one ordered stencil (longitude shift di,
+    // source row jS, weight) along each destination row -- the zonal form (kind 1), described here directly so that
+    // the O(nx*ny) table need not be generated just to be recognised as a stencil afterwards.
+    bool zonal = false;
+    std::vector<int32_t> zptr, zdi, zjs;       // per destination row; source column = (iD + di) mod nxs
+    std::vector<double> zw;
 };
 
 int jones99_factors(int nxs, const double *x_LonS, int nys, const double *y_LatS,

@@ -262,8 +262,39 @@ static int jones99_impl(int nxs, const double *x_LonS, int nys, const double *y_
         }
     }
 
+    if (sep && !general) {
+        // every destination column must see the same longitude shift(s): true for equal longitudes and nx == 1
+        sep->nxs = nxs; sep->nys = nys; sep->nxd = nxd; sep->nyd = nyd;
+        for (int iD = 2; iD <= nxd; iD++)
+            if (lxn[iD] != lxn[1] || (nxs > 1 && (lx1[iD] - iD - (lx1[1] - 1)) % nxs != 0)) return DCCM_OK;
+        sep->zptr.assign(nyd + 1, 0);
+        for (int jD = 1; jD <= nyd; jD++) {
+            const LatRow &R = rows[jD];
+            for (int m = 1; m <= lxn[1]; m++) {
+                const int di = (lx1[1] + m - 2) % nxs;                  // column 1 (0-based 0): shift = source column
+                for (int n = 1; n <= R.nyr; n++) {
+                    const int jS = R.ry1 + n - 1;
+                    if (std::fabs(R.w1[n]) > 1e-14) { sep->zdi.push_back(di); sep->zjs.push_back(jS - 1); sep->zw.push_back(R.w1[n]); }
+                    if (accuracy_order > 1) {
+                        int j1, j2;
+                        if (jS == 1)        { j1 = jS;     j2 = jS + 1; }
+                        else if (jS == nys) { j1 = jS - 1; j2 = jS; }
+                        else                { j1 = jS - 1; j2 = jS + 1; }
+                        const double DLat = y_LatS[j2 - 1] - y_LatS[j1 - 1];
+                        if (std::fabs(R.w2[n]) > 1e-14) {
+                            sep->zdi.push_back(di); sep->zjs.push_back(j1 - 1); sep->zw.push_back(-R.w2[n] / DLat);
+                            sep->zdi.push_back(di); sep->zjs.push_back(j2 - 1); sep->zw.push_back(+R.w2[n] / DLat);
+                        }
+                    }
+                }
+            }
+            sep->zptr[jD] = (int32_t)sep->zw.size();
+        }
+        sep->zonal = true;
+        return DCCM_OK;
+    }
     if (sep) {
-        if (!general || accuracy_order > 1) return DCCM_OK;
+        if (accuracy_order > 1) return DCCM_OK;
         sep->mode = 0; sep->nxs = nxs; sep->nys = nys; sep->nxd = nxd; sep->nyd = nyd;
         sep->xptr.assign(gptr.begin(), gptr.end());
         sep->xi.resize(gidx.size());
@@ -361,8 +392,15 @@ static int bilinear_impl(int nxs, const double *x_LonS, int nys, const double *y
             a2[ir - 1] = 1.0 - a1[ir - 1];
         }
     }
+    bool zon = false;
+    if (sep && nxr != 1 && nxs != 1 && nxr == nxs) {
+        zon = true;                                   // same shifts and value-equal coefficients in every column?
+        for (int ir = 1; ir < nxr && zon; ir++)
+            zon = (is1[ir] - 1 - ir + nxs) % nxs == (is1[0] - 1) % nxs && (is2[ir] - 1 - ir + nxs) % nxs == (is2[0] - 1) % nxs &&
+                  a1[ir] == a1[0] && a2[ir] == a2[0];
+    }
     if (sep) {
-        if (nxr == 1 || nxs == 1) { delete t; return DCCM_OK; }     // axisymmetric side: a zonal stencil, not handled here
+        if (nxr == 1 || nxs == 1) { delete t; return DCCM_OK; }     // axisymmetric side: goes through the table
         sep->mode = 1; sep->nxs = nxs; sep->nys = nys; sep->nxd = nxr; sep->nyd = nyr;
         sep->xptr.resize(nxr + 1); sep->yptr.resize(nyr + 1);
         for (int ir = 0; ir < nxr; ir++) {
@@ -410,6 +448,12 @@ static int bilinear_impl(int nxs, const double *x_LonS, int nys, const double *y
                 sep->yptr[jr - 1] = 2 * (jr - 1);
                 sep->yj.push_back(jlo - 1);     sep->yw.push_back(b2);      // n0: (jlo, b2)
                 sep->yj.push_back(jhi_out - 1); sep->yw.push_back(b1);      // n1: (jhi, b1)
+                if (zon) {                                                  // the row's stencil, in table order
+                    const int d1 = (is1[0] - 1) % nxs, d2 = (is2[0] - 1) % nxs;
+                    const int dd[4] = {d1, d2, d2, d1}, jj[4] = {jlo - 1, jlo - 1, jhi_out - 1, jhi_out - 1};
+                    const double ww[4] = {a2[0] * b2, a1[0] * b2, a1[0] * b1, a2[0] * b1};
+                    for (int k = 0; k < 4; k++) { sep->zdi.push_back(dd[k]); sep->zjs.push_back(jj[k]); sep->zw.push_back(ww[k]); }
+                }
                 continue;
             }
             for (int ir = 0; ir < nxr; ir++) {
@@ -423,6 +467,11 @@ static int bilinear_impl(int nxs, const double *x_LonS, int nys, const double *y
     if (sep) {
         sep->yptr[nyr] = 2 * nyr;
         sep->ok = true;
+        if (zon) {
+            sep->zptr.resize(nyr + 1);
+            for (int jr = 0; jr <= nyr; jr++) sep->zptr[jr] = 4 * jr;
+            sep->zonal = true;
+        }
         delete t;
         return DCCM_OK;
     }
@@ -446,8 +495,20 @@ int dccm::bilinear_factors(int nxs, const double *x_LonS, int nys, const double 
 
 // Host-side expansion of the separable factors into a table, entry by entry as the kernels do it (kind 2):
 // lets the CPU test-suite check factors + expansion order against the generators index for index.
+static int expand_zonal(const SepFactors &f, dccm_table **out)
+{
+    dccm_table *t = new dccm_table();
+    for (int jD = 0; jD < f.nyd; jD++)
+        for (int iD = 0; iD < f.nxd; iD++)
+            for (int e = f.zptr[jD]; e < f.zptr[jD + 1]; e++)
+                t->push(iD + 1, jD + 1, (f.nxs == 1 ? 0 : (iD + f.zdi[e]) % f.nxs) + 1, f.zjs[e] + 1, f.zw[e]);
+    *out = t;
+    return DCCM_OK;
+}
+
 static int expand_factors(const SepFactors &f, dccm_table **out)
 {
+    if (f.zonal) return expand_zonal(f, out);
     if (!f.ok) return fail(DCCM_ERR_UNSUPPORTED, "this grid pair is not handled in separable form (equal longitudes, nx == 1 or 2nd order)");
     dccm_table *t = new dccm_table();
     for (int jD = 0; jD < f.nyd; jD++) {

@@ -107,7 +107,8 @@ def gen_table_bilinear(src, dst, lon_mode=0, rows=None):
 
 
 def gen_table_separable(src, dst, conservative, accuracy_order=1, lon_mode=1):
-    """The table multiplied out from its separable factors, as the kind-2 kernels do (host check of that form)."""
+    """The table multiplied out from its separable factors (different longitudes, kind 2) or from its per-row stencil
+    (equal longitudes / nx == 1, kind 1), as the kernels do: host check of the forms dccm_remap_create_* build."""
     h = C.c_void_p()
     if conservative:
         L.check(L.lib().dccm_table_gen_jones99_separable(src.im, L.dp(src.x_Lon), src.jm, L.dp(src.y_Lat),

@@ -184,7 +184,24 @@ def test_separable_factors_multiply_out_to_the_generated_tables(dccm, name):
             got = T.gen_table_separable(src, dst, cons).entries()
             for a, b in zip(got, want):
                 assert np.array_equal(a, b), (name, src.im, dst.im, cons)
-    with pytest.raises(dccm.DccmError):              # equal longitudes, conservative: a zonal stencil, not this form
-        T.gen_table_separable(A, S, True)
-    for a, b in zip(T.gen_table_separable(A, S, False).entries(), T.gen_table_bilinear(A, S, 1).entries()):
-        assert np.array_equal(a, b)                  # the 4-point bilinear form is separable for any longitudes
+    # equal longitudes: described directly as one stencil per destination row (kind 1), multiplied out the same way
+    for src, dst in ((A, S), (S, A)):
+        for order in (1, 2):
+            for a, b in zip(T.gen_table_separable(src, dst, True, order).entries(), T.gen_table_jones99(src, dst, order, 1).entries()):
+                assert np.array_equal(a, b), (name, order)
+        for a, b in zip(T.gen_table_separable(src, dst, False).entries(), T.gen_table_bilinear(src, dst, 1).entries()):
+            assert np.array_equal(a, b), name
+
+
+def test_zonal_description_of_axisymmetric_pairs(dccm):
+    """nx == 1 on either side (the shipped APEI07Couple ocean): the conservative generator's table is one stencil per
+    destination row; its direct description multiplies out to the generated table."""
+    from util import pair
+    T = dccm.tables
+    A, O, S = pair(None, dccm, "T21_Pl42")
+    assert O.im == 1
+    for src, dst in ((O, S), (S, O), (A, O), (O, A)):
+        for a, b in zip(T.gen_table_separable(src, dst, True).entries(), T.gen_table_jones99(src, dst, 1, 0).entries()):
+            assert np.array_equal(a, b), (src.im, dst.im)
+    with pytest.raises(dccm.DccmError):              # bilinear with an axisymmetric side: through the table only
+        T.gen_table_separable(O, S, False)
