@@ -129,8 +129,10 @@ int dccm_remap_create_lonlat(int64_t nops, const int32_t *send_index, const int3
  * back without the table ever being built.  Grid pairs with different longitudes (lon_mode 1) give a SEPARABLE
  * operator (dccm_remap_kind() == 2): per-column longitude factors and per-row latitude factors, O(nx + ny) numbers
  * that the kernels multiply out exactly as the generator would have (same order, same product, same 1e-14 drop
- * test) -- bit-identical results, no O(nx*ny) table in memory or in the kernels' traffic.  Equal longitudes,
- * nx == 1 and 2nd order go through the generator and dccm_remap_create_lonlat (kind 1 or 0). */
+ * test) -- bit-identical results, no O(nx*ny) table in memory or in the kernels' traffic.  Equal longitudes and an
+ * axisymmetric source (any accuracy order) come back directly as one stencil per destination row (kind 1), again without
+ * a table; what is left (axisymmetric destination, very long stencils) goes through the generator and
+ * dccm_remap_create_lonlat. */
 int dccm_remap_create_jones99(int nxs, const double *x_LonS, int nys, const double *y_LatS,
                               int nxd, const double *x_LonD, int nyd, const double *y_LatD,
                               const double *y_LatIntWtS, const double *y_LatIntWtD,
