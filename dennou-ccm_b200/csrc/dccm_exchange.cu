@@ -42,7 +42,7 @@ namespace {
 
 constexpr int kThreads = 128;
 
-struct Csr {                       // one table: CSR (kind 0) or zonal stencil (kind 1)
+struct Csr {                       // one table: CSR (kind 0) or zonal stencil (kind 1); kind 2 (separable) uses SepTab
     const int32_t *rowptr, *col;
     const double *w;
     int kind, nxs, nxd;
@@ -62,12 +62,13 @@ struct SfcArgs {
     int redo_cap;
 };
 
-// One destination row of one table, D layers.  The row's (col, w) pairs are fetched CH at a
-// time BEFORE any of the dependent source loads is issued, so a thread has up to CH*D gathers in
-// flight instead of D (rows of these tables hold 1-4 entries); accumulation stays in table order.
+// source cell c of a send buffer; SEG: the buffer's boundary rows live in the neighbouring ranks' memory
 template <bool SEG>
 __device__ __forceinline__ const double *cell(const SrcSeg &s, int64_t c) { return SEG ? s.at(c) : s.own + c; }
 
+// One destination row of one table, D layers.  The row's (col, w) pairs are fetched CH at a
+// time BEFORE any of the dependent source loads is issued, so a thread has up to CH*D gathers in
+// flight instead of D (rows of these tables hold 1-4 entries); accumulation stays in table order.
 template <int D, int CH, bool SEG>
 __device__ __forceinline__ void gather(const Csr &t, int r, const SrcSeg &src, int64_t n_src,
                                        int M, int m, double (&acc)[D])
