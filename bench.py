@@ -619,7 +619,7 @@ def run_e2e_dropin(torch, dccm, ex, A, O, S, K, nc, col_in, atm_sfc, ocn_sfc, st
     return {"value": 1.0 / dt, "unit": "exchanges/s", "ms_per_step": 1e3 * dt, "steps": steps,
             "matches_resident_path_bitwise": same,
             "note": "reference interfaces only (forward_host, interpolate_data x8, bulkflux_get_host, backward_host), "
-                    "pinned host arrays, every call moves its arguments in and out (solves and bulk flux in chunks, H2D | kernel | D2H overlapped inside the call); host pack/unpack in numpy/torch-cpu"}
+                    "pinned host arrays, every call moves its arguments in and out in chunks (H2D | kernel | D2H overlapped inside the call); host pack/unpack in numpy/torch-cpu"}
 
 
 def main():

@@ -612,20 +612,51 @@ extern "C" int dccm_remap_apply_seg_device(dccm_remap *h, const dccm_src_seg *se
     return DCCM_OK;
 }
 
+// Host form.  Large calls move their fields in groups: group g+1 on its way in (H2D stream) while the kernel runs on
+// group g and group g-1 is on its way out (D2H stream) -- fields are independent, so a group is just a call with
+// fewer fields on offset pointers.  The zero fill of recv_data(:, num_of_data+1:) (ref :293) is done once up front.
 extern "C" int dccm_remap_apply_host(dccm_remap *h, const double *send, int sn1, int sn2,
                                      double *recv, int rn1, int rn2, int num_of_data)
 {
     if (!h) return fail(DCCM_ERR_ARG, "dccm_remap_apply: null handle");
     if (num_of_data > sn2) return fail(DCCM_ERR_ARG, "dccm_remap_apply: num_of_data=%d exceeds sn2=%d", num_of_data, sn2);
+    if (num_of_data < 0 || num_of_data > rn2)
+        return fail(DCCM_ERR_ARG, "dccm_remap_apply: num_of_data=%d exceeds rn2=%d", num_of_data, rn2);
     int rc = h->send_buf.reserve(sizeof(double) * (size_t)sn1 * std::max(1, num_of_data));
     if (rc) return rc;
     rc = h->recv_buf.reserve(sizeof(double) * (size_t)rn1 * std::max(1, rn2));
     if (rc) return rc;
-    DCCM_CUDA_TRY(cudaMemcpyAsync(h->send_buf.p, send, sizeof(double) * (size_t)sn1 * num_of_data, cudaMemcpyHostToDevice, 0));
-    rc = dccm_remap_apply_device(h, h->send_buf.as<double>(), sn1, h->recv_buf.as<double>(), rn1, rn2, num_of_data, nullptr);
-    if (rc) return rc;
-    DCCM_CUDA_TRY(cudaMemcpyAsync(recv, h->recv_buf.p, sizeof(double) * (size_t)rn1 * rn2, cudaMemcpyDeviceToHost, 0));
-    DCCM_CUDA_TRY(cudaStreamSynchronize(0));
+    static cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
+    for (auto &ps : pipe)
+        if (!ps) DCCM_CUDA_TRY(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+    cudaStream_t sin = pipe[0], sk = pipe[1], sout = pipe[2];
+    const char *env = getenv("DCCM_HOST_CHUNKS");
+    const bool big = (size_t)(sn1 + rn1) * (size_t)std::max(1, num_of_data) >= ((size_t)1 << 22);
+    int ngroup = env ? std::max(1, atoi(env)) : (big ? 4 : 1);
+    ngroup = std::max(1, std::min(ngroup, num_of_data));
+    double *d_send = h->send_buf.as<double>(), *d_recv = h->recv_buf.as<double>();
+    // rows the kernel does not write: recv_data(:,:) = 0 (ref :293) -- set on the host, nothing to copy back
+    if (rn2 > num_of_data) memset(recv + (size_t)num_of_data * rn1, 0, sizeof(double) * (size_t)(rn2 - num_of_data) * rn1);
+    std::vector<cudaEvent_t> ev(2 * (size_t)ngroup, nullptr);
+    struct EvGuard { std::vector<cudaEvent_t> &e; ~EvGuard() { for (auto x : e) if (x) cudaEventDestroy(x); } } guard{ev};
+    for (auto &e : ev) DCCM_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    const int per = num_of_data > 0 ? (num_of_data + ngroup - 1) / ngroup : 0;
+    for (int g = 0; g < ngroup && num_of_data > 0; g++) {
+        const int f0 = g * per, f1 = std::min(num_of_data, f0 + per);
+        if (f0 >= f1) continue;
+        const size_t so = (size_t)f0 * sn1, ro = (size_t)f0 * rn1;
+        DCCM_CUDA_TRY(cudaMemcpyAsync(d_send + so, send + so, sizeof(double) * (size_t)sn1 * (f1 - f0), cudaMemcpyHostToDevice, sin));
+        DCCM_CUDA_TRY(cudaEventRecord(ev[2 * g], sin));
+        DCCM_CUDA_TRY(cudaStreamWaitEvent(sk, ev[2 * g], 0));
+        rc = dccm_remap_apply_device(h, d_send + so, sn1, d_recv + ro, rn1, f1 - f0, f1 - f0, sk);
+        if (rc) return rc;
+        DCCM_CUDA_TRY(cudaEventRecord(ev[2 * g + 1], sk));
+        DCCM_CUDA_TRY(cudaStreamWaitEvent(sout, ev[2 * g + 1], 0));
+        DCCM_CUDA_TRY(cudaMemcpyAsync(recv + ro, d_recv + ro, sizeof(double) * (size_t)rn1 * (f1 - f0), cudaMemcpyDeviceToHost, sout));
+    }
+    DCCM_CUDA_TRY(cudaStreamSynchronize(sout));
+    DCCM_CUDA_TRY(cudaStreamSynchronize(sk));
+    DCCM_CUDA_TRY(cudaStreamSynchronize(sin));
     return DCCM_OK;
 }
 

@@ -95,10 +95,14 @@ def test_remap_separable_form_bit_exact(gpu, orc, dccm, S, name):
             assert np.array_equal(op.apply_host(x), orc.remap_apply(si, ri, cf, x, d.n)), (label, cons, "host")
 
 
+@pytest.mark.parametrize("groups", [None, 3, 100])
 @pytest.mark.parametrize("D", [1, 5, 8, 17, 43])
-def test_remap_field_counts_and_zero_fill(gpu, orc, dccm, S, D):
+def test_remap_field_counts_and_zero_fill(gpu, orc, dccm, S, D, groups, monkeypatch):
     """recv_data(:,:) = 0 covers ALL rn2 columns and rows beyond the table
-    (ref common/interpolation_data_latlon_mod.f90:293)."""
+    (ref common/interpolation_data_latlon_mod.f90:293).  groups: the host form moves its fields in that many
+    pipelined groups (H2D | kernel | D2H)."""
+    if groups:
+        monkeypatch.setenv("DCCM_HOST_CHUNKS", str(groups))
     A, O, Sx = pair(orc, dccm, "T21_Pl42")
     tab = dccm.tables.gen_table_jones99(A, Sx, 2)
     send_i, recv_i, coef = tab.index(A.im, Sx.im)
