@@ -65,6 +65,19 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+DRIVER_PATH = os.path.join(_HERE, "..", "examples", "exchange_driver")
+
+
+def build_driver():
+    """examples/exchange_driver: one exchange through the C ABI from compiled host code (plain g++)."""
+    build()
+    r = subprocess.run(["make", "-C", CSRC, "driver"], capture_output=True, text=True)
+    if r.returncode != 0:
+        print(r.stdout[-2000:], r.stderr[-2000:])
+        raise DccmError("building examples/exchange_driver failed")
+    return os.path.abspath(DRIVER_PATH)
+
+
 _SIGS = {
     "dccm_last_error": (C.c_char_p, []),
     "dccm_build_info": (C.c_char_p, []),

@@ -789,3 +789,45 @@ def test_legacy_two_component_exchange_bit_exact(gpu, orc, dccm, S, name):
     # conservative A->O keeps the global integral (area weights of the destination / source rows)
     wo, wa = np.repeat(O.y_LatWt, O.im) / O.im, np.repeat(A.y_LatWt, A.im) / A.im
     assert abs((want_o[2] * wo).sum() / (a2o[2] * wa).sum() - 1.0) <= 1e-11
+
+
+def test_compiled_host_driver_through_the_c_abi_equals_resident_path(gpu, dccm, tmp_path):
+    """examples/exchange_driver.cpp: one exchange from compiled host code through the C ABI only (operators built from
+    the grid axes, interpolate_data x8, DSFCM_Util_SfcBulkFlux_Get on (IA,JA) halo arrays, VDiffForward / Backward with
+    host arrays), in the call order of the reference's component drivers.  Its dumped outputs equal, bit for bit, the
+    device-resident SurfaceExchange run on the dumped inputs."""
+    import subprocess
+    import json
+    import torch
+    X = importlib.import_module("dennou-ccm_b200.exchange")
+    exe = dccm.build_driver()
+    ima, jma, imo, jmo, K = 64, 32, 72, 36, 8
+    r = subprocess.run([exe, str(ima), str(jma), str(imo), str(jmo), str(K), str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    assert info["kinds"] == [1, 1, 2, 2, 1, 1, 2, 2]          # A<->S zonal stencils, O<->S separable (bil, cons per pair)
+    load = lambda name, *shape: torch.as_tensor(np.fromfile(tmp_path / f"{name}.f64").reshape(shape), device=gpu)
+    T = dccm.tables
+    A, O = T.get_LonLatGrid(ima, jma), T.regular_LonLatGrid(imo, jmo)
+    Sx = T.generate_surface_exchange_grid(A, O)
+    assert [Sx.im, Sx.jm] == info["sfc"]
+    nA, nO, nS = A.n, O.n, Sx.n
+    ex = X.SurfaceExchange(A, O, Sx, K, 1, 1, fast=False, device=gpu,
+                           consts=dict(Grav=9.8, CpDry=1004.6, GasRDry=287.04, DelTime=1200.0, Sig1=0.995))
+    col = {k: load(k, K + 1, nA) for k in ("MomFluxX", "MomFluxY", "HeatFlux", "Press", "rExner", "VirTemp",
+                                            "VelDiffCoef", "TempDiffCoef", "QMixDiffCoef")}
+    col["QMixFlux"] = load("QMixFlux", 1, K + 1, nA)
+    col["zExner"], col["Height"] = load("zExner", K, nA), load("Height", K, nA)
+    ab, ac, ob, oc = load("a2s_bil", 13, nA), load("a2s_cons", 4, nA), load("o2s_bil", 2, nO), load("o2s_cons", 3, nO)
+    ex.set_inputs(col, {"WindU": ab[0:1], "WindV": ab[1:2], "SfcAirTemp": ab[2:3], "QVap1": ab[3:4], "SfcPress": ab[4:5],
+                        "LDwRFlx": ac[0:1], "SDwRFlx": ac[1:2], "RainFall": ac[2:3], "SnowFall": ac[3:4]},
+                  {"SfcTempO": ob[0:1], "SfcTempI": ob[1:2], "SIceCon": oc[0:1], "SfcAlbedoO": oc[1:2], "SfcAlbedoI": oc[2:3]})
+    ex.step()
+    torch.cuda.synchronize()
+    assert torch.equal(ex.a2s_bil, ab)                        # the forward solve's coefficients, layers 5..12
+    for name, got in (("s2a", ex.s2a), ("s2o", ex.s2o), ("a_recv", ex.a_recv), ("o_recv", ex.o_recv)):
+        assert torch.equal(got, load(name, *got.shape)), name
+    for name in ("DUDt", "DVDt", "DTempDt"):
+        assert torch.equal(ex.tend[name], load(name, K, nA)), name
+    assert torch.equal(ex.tend["DQMixDt"], load("DQMixDt", 1, K, nA))
+    assert bool(torch.isfinite(ex.o_recv).all()) and float(ex.o_recv.abs().max()) > 0.0
