@@ -56,8 +56,10 @@ struct FwdArgs {
     double Grav, CpDry, GasRDry, DelTime;
 };
 
-template <int NQ, bool FAST>
-__global__ void __launch_bounds__(kThreads) vdiff_forward_kernel(const FwdArgs a)
+// 5 CTAs (20 warps) per SM for one or two tracers: 95 registers and 56 B of spills instead of 104 registers and 4 CTAs
+// -- more loads in flight, 4.83 -> 4.61 ms at config 5 (6 CTAs / 80 registers spills too much: 4.80 ms)
+template <int NQ, bool FAST, int MINB = (NQ <= 2 ? 5 : 1)>
+__global__ void __launch_bounds__(kThreads, MINB) vdiff_forward_kernel(const FwdArgs a)
 {
     const int64_t c = a.c0 + (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int64_t NC = a.NC;
