@@ -101,6 +101,7 @@ _SIGS = {
                                                    f64p, f64p, C.c_int, C.c_int, C.POINTER(vp)]),
     "dccm_table_gen_bilinear_separable": (C.c_int, [C.c_int, f64p, C.c_int, f64p, C.c_int, f64p, C.c_int, f64p,
                                                     C.c_int, C.POINTER(vp)]),
+    "dccm_table_gen_make_mapping_table": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
     "dccm_table_write_text": (C.c_int, [vp, C.c_char_p]),
     "dccm_table_read_text": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
     "dccm_table_write_bin": (C.c_int, [vp, C.c_char_p]),

@@ -486,6 +486,49 @@ extern "C" int dccm_table_gen_bilinear_rows(int nxs, const double *x_LonS, int n
     return bilinear_impl(nxs, x_LonS, nys, y_LatS, nxr, x_LonR, nyr, y_LatR, lon_mode, jr_first, jr_last, out, nullptr);
 }
 
+// make_mapping_table, ref common/cal_mappingtable.f90:10-49 (+ cal_coef :59-76): the stand-alone bilinear generator on
+// regular grids given by their sizes only (degrees; longitudes from 0 in steps of 360/nx, latitudes from one pole to
+// the other in steps of 180/(ny-1)).  The west source column and its weight pair depend only on the destination
+// column, the south source row and its pair only on the destination row, so both are tabulated once (the reference
+// recomputes them per cell); a cell then emits the four products in the reference order, keeping those > 0.
+extern "C" int dccm_table_gen_make_mapping_table(int nx_r, int ny_r, int nx_s, int ny_s, dccm_table **out)
+{
+    if (!out) return fail(DCCM_ERR_ARG, "make_mapping_table: out is NULL");
+    *out = nullptr;
+    if (nx_r < 1 || nx_s < 1 || ny_r < 2 || ny_s < 2)
+        return fail(DCCM_ERR_ARG, "make_mapping_table: need nx >= 1 and ny >= 2 on both sides (got %d x %d <- %d x %d)",
+                    nx_r, ny_r, nx_s, ny_s);
+    struct Axis { int lo, hi; double w_hi, w_lo; };          // source index pair (1-based) and weights (a1 | a2)
+    auto tabulate = [](int n_r, double d_r, int n_s, double d_s) {
+        std::vector<Axis> ax(n_r);
+        for (int k = 0; k < n_r; k++) {
+            const double c = d_r * k;
+            const int lo = (int)(c / d_s) + 1;
+            const double c1 = (lo - 1) * d_s, c3 = c1 + d_s;
+            const double t = (c - c1) / (c3 - c1);
+            ax[k] = {lo, lo % n_s + 1, t, 1.0 - t};
+        }
+        return ax;
+    };
+    const std::vector<Axis> X = tabulate(nx_r, 360.0 / nx_r, nx_s, 360.0 / nx_s);
+    const std::vector<Axis> Y = tabulate(ny_r, 180.0 / (ny_r - 1), ny_s, 180.0 / (ny_s - 1));
+    auto *t = new dccm_table;
+    t->reserve((size_t)4 * nx_r * ny_r);
+    for (int j = 0; j < ny_r; j++) {
+        const Axis &y = Y[j];
+        for (int i = 0; i < nx_r; i++) {
+            const Axis &x = X[i];
+            const double sw = x.w_lo * y.w_lo, se = x.w_hi * y.w_lo, ne = x.w_hi * y.w_hi, nw = x.w_lo * y.w_hi;
+            if (sw > 0.0) t->push(i + 1, j + 1, x.lo, y.lo, sw);
+            if (se > 0.0) t->push(i + 1, j + 1, x.hi, y.lo, se);
+            if (ne > 0.0) t->push(i + 1, j + 1, x.hi, y.hi, ne);
+            if (nw > 0.0) t->push(i + 1, j + 1, x.lo, y.hi, nw);
+        }
+    }
+    *out = t;
+    return DCCM_OK;
+}
+
 int dccm::bilinear_factors(int nxs, const double *x_LonS, int nys, const double *y_LatS,
                            int nxr, const double *x_LonR, int nyr, const double *y_LatR, int lon_mode, SepFactors &f)
 {

@@ -106,6 +106,13 @@ def gen_table_bilinear(src, dst, lon_mode=0, rows=None):
     return MappingTable(h)
 
 
+def make_mapping_table(nx_r, ny_r, nx_s, ny_s):
+    """ref common/cal_mappingtable.f90:10-49 -- regular grids in degrees, given by their sizes; receiver <- sender."""
+    h = C.c_void_p()
+    L.check(L.lib().dccm_table_gen_make_mapping_table(nx_r, ny_r, nx_s, ny_s, C.byref(h)))
+    return MappingTable(h)
+
+
 def gen_table_separable(src, dst, conservative, accuracy_order=1, lon_mode=1):
     """The table multiplied out from its separable factors (different longitudes, kind 2) or from its per-row stencil
     (equal longitudes / nx == 1, kind 1), as the kernels do: host check of the forms dccm_remap_create_* build."""

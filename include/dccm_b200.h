@@ -70,6 +70,11 @@ int dccm_table_gen_jones99(int nxs, const double *x_LonS, int nys, const double 
 int dccm_table_gen_bilinear(int nxs, const double *x_LonS, int nys, const double *y_LatS,
                             int nxr, const double *x_LonR, int nyr, const double *y_LatR,
                             int lon_mode, dccm_table **out);
+/* make_mapping_table of the older stand-alone bilinear generator, ref common/cal_mappingtable.f90:10-49 (cal_coef
+ * :59-76): REGULAR grids given by their sizes (degrees: longitudes 0, 360/nx, ...; latitudes pole to pole in steps of
+ * 180/(ny-1)), receiver (nx_r, ny_r) <- sender (nx_s, ny_s).  Entries with coefficient > 0 only, in the order
+ * (is,js) (is+1,js) (is+1,js+1) (is,js+1) with mod wrap, as the reference writes them (:40-43).  Host only. */
+int dccm_table_gen_make_mapping_table(int nx_r, int ny_r, int nx_s, int ny_s, dccm_table **out);
 /* Same generators restricted to destination rows jd_first..jd_last (1-based, inclusive): the
  * entries a rank owning that latitude band needs (row-block sharding).  Entries are
  * identical to the corresponding slice of the full table. */

@@ -46,6 +46,7 @@ def lib():
                                       _f64p, _f64p, C.c_int, C.c_int, C.c_void_p]
         L.orc_gen_bilinear.argtypes = [C.c_int, _f64p, C.c_int, _f64p, C.c_int, _f64p, C.c_int, _f64p,
                                        C.c_int, C.c_void_p]
+        L.orc_make_mapping_table.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orc_exchange_grid.argtypes = [C.c_int, _f64p, _f64p, C.c_int, _f64p,
                                         C.POINTER(C.c_int), _f64p, _f64p]
         L.orc_table_write_text.argtypes = [C.c_void_p, C.c_char_p]
@@ -144,6 +145,16 @@ def gen_bilinear(src, dst, lon_mode=0):
     if rc != 0:
         lib().orc_table_free(t)
         raise RuntimeError(f"orc_gen_bilinear failed rc={rc}")
+    return _take(t)
+
+
+def make_mapping_table(nx_r, ny_r, nx_s, ny_s):
+    """ref common/cal_mappingtable.f90:10-49 (regular grids in degrees, entries with coef > 0 only)"""
+    t = lib().orc_table_new()
+    rc = lib().orc_make_mapping_table(nx_r, ny_r, nx_s, ny_s, t)
+    if rc != 0:
+        lib().orc_table_free(t)
+        raise RuntimeError(f"orc_make_mapping_table failed rc={rc}")
     return _take(t)
 
 

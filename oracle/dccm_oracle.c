@@ -379,6 +379,43 @@ int orc_gen_bilinear(int nxs, const double *x_LonS, int nys, const double *y_Lat
 
 /* ------------------------------------------------------------------ exchange grid */
 
+/* ref common/cal_mappingtable.f90:10-49 (make_mapping_table) with cal_coef :59-76: the older stand-alone
+ * bilinear generator on REGULAR grids in degrees -- longitudes 360/nx apart starting at 0, latitudes
+ * 180/(ny-1) apart from pole to pole.  An entry is written only when its coefficient is > 0 (:40-43), in the
+ * order coef(1..4) = (a2*b2, a1*b2, a1*b1, a2*b1); the east / north neighbours wrap with mod (:41-43).
+ * The program around it (:81-109) refers to undefined names and is not built by the reference. */
+int orc_make_mapping_table(int nx_r, int ny_r, int nx_s, int ny_s, orc_table *out)
+{
+    if (nx_r < 1 || nx_s < 1 || ny_r < 2 || ny_s < 2) return 1;
+    double dx_r = 360.0 / nx_r;                 /* :20 */
+    double dy_r = 180.0 / (ny_r - 1);           /* :21 */
+    double dx_s = 360.0 / nx_s;                 /* :22 */
+    double dy_s = 180.0 / (ny_s - 1);           /* :23 */
+    for (int j = 1; j <= ny_r; j++) {           /* :25 */
+        double yr = dy_r * (j - 1);
+        int js = (int)(yr / dy_s) + 1;          /* :27 int() truncates */
+        double ys1 = (js - 1) * dy_s;
+        double ys3 = ys1 + dy_s;
+        for (int i = 1; i <= nx_r; i++) {       /* :31 */
+            double xr = dx_r * (i - 1);
+            int is = (int)(xr / dx_s) + 1;      /* :34 */
+            double xs1 = (is - 1) * dx_s;
+            double xs3 = xs1 + dx_s;
+            /* cal_coef(xr, yr, xs1, ys1, xs3, ys3, coef) :66-74 */
+            double alpha1 = (xr - xs1) / (xs3 - xs1);
+            double alpha2 = 1.0 - alpha1;
+            double beta1 = (yr - ys1) / (ys3 - ys1);
+            double beta2 = 1.0 - beta1;
+            double c1 = alpha2 * beta2, c2 = alpha1 * beta2, c3 = alpha1 * beta1, c4 = alpha2 * beta1;
+            if (c1 > 0.0) table_push(out, i, j, is, js, c1);                               /* :40 */
+            if (c2 > 0.0) table_push(out, i, j, is % nx_s + 1, js, c2);                    /* :41 */
+            if (c3 > 0.0) table_push(out, i, j, is % nx_s + 1, js % ny_s + 1, c3);         /* :42 */
+            if (c4 > 0.0) table_push(out, i, j, is, js % ny_s + 1, c4);                    /* :43 */
+        }
+    }
+    return 0;
+}
+
 /* ref tool/gmapgen/gmapgen_main.f90:336-405 (generate_surface_exchage_grid) + sort :407-426.
  * Longitudes of the exchange grid are those of the atmosphere (:349-352) and are not returned.
  * y_LatS / y_IntWtLatS must have room for jma + jmo - 1 entries. */

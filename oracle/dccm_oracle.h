@@ -50,6 +50,8 @@ int orc_gen_jones99(int nxs, const double *x_LonS, int nys, const double *y_LatS
 int orc_gen_bilinear(int nxs, const double *x_LonS, int nys, const double *y_LatS,
                      int nxr, const double *x_LonR, int nyr, const double *y_LatR,
                      int lon_mode, orc_table *out);
+/* make_mapping_table of the stand-alone regular-grid generator, ref common/cal_mappingtable.f90:10-49 */
+int orc_make_mapping_table(int nx_r, int ny_r, int nx_s, int ny_s, orc_table *out);
 int orc_exchange_grid(int jma, const double *y_LatA, const double *y_IntWtLatA,
                       int jmo, const double *y_IntWtLatO,
                       int *jms, double *y_LatS, double *y_IntWtLatS);

@@ -70,6 +70,27 @@ def test_generators_match_oracle_index_for_index(orc, dccm, name):
                 assert np.array_equal(x, y)
 
 
+@pytest.mark.parametrize("sizes", [(8, 5, 4, 3), (360, 181, 128, 65), (128, 65, 360, 181), (7, 4, 7, 4),
+                                   (1, 2, 5, 3), (5, 3, 1, 2), (96, 49, 100, 37)])
+def test_make_mapping_table_matches_oracle_entry_for_entry(orc, dccm, sizes, tmp_path):
+    """ref common/cal_mappingtable.f90:10-49: same entries, same order, bit-identical weights; and the file the
+    mirror module writes reads back to the same 1-D indices."""
+    o = orc.make_mapping_table(*sizes)
+    t = dccm.tables.make_mapping_table(*sizes)
+    for x, y in zip(t.entries(), (o.iD, o.jD, o.iS, o.jS, o.coef)):
+        assert np.array_equal(x, y)
+    f = str(tmp_path / "mapping_table.txt")
+    dccm.cal_mappingtable.make_mapping_table(f, *sizes)
+    back = orc.read_table(f)
+    for x, y in zip(o.to_index(sizes[2], sizes[0]), back.to_index(sizes[2], sizes[0])):
+        assert np.array_equal(x, y)
+
+
+def test_make_mapping_table_rejects_degenerate_grids(dccm):
+    with pytest.raises(dccm.DccmError, match="ny >= 2"):
+        dccm.tables.make_mapping_table(8, 1, 4, 3)
+
+
 def test_unsupported_grid_pair_fails_like_the_reference(dccm, orc):
     A, O, S = pair(orc, dccm, "T21_1deg")
     with pytest.raises(dccm.DccmError, match="lon_mode=1"):

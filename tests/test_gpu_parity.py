@@ -134,6 +134,16 @@ def test_remap_ragged_empty_and_duplicate_rows(gpu, orc, dccm):
         op.apply_host(x, rn1=n_recv - 1)
 
 
+@pytest.mark.parametrize("sizes", [(360, 181, 128, 65), (128, 65, 360, 181)])
+def test_remap_with_the_standalone_regular_grid_table(gpu, orc, dccm, sizes):
+    """Tables of common/cal_mappingtable.f90:10-49 (make_mapping_table) through the remap apply, bit-exact."""
+    nx_r, ny_r, nx_s, ny_s = sizes
+    send_i, recv_i, coef = dccm.tables.make_mapping_table(*sizes).index(nx_s, nx_r)
+    x = np.random.default_rng(11).standard_normal((3, nx_s * ny_s))
+    op = dccm.RemapOperator(send_i, recv_i, coef, nx_s * ny_s, nx_r * ny_r)
+    assert np.array_equal(op.apply_host(x), orc.remap_apply(send_i, recv_i, coef, x, nx_r * ny_r))
+
+
 def test_interpolate_data_callback_interface(gpu, orc, dccm, S):
     """The (recv_model, send_model, mapping_tag)-keyed path Jcup drives
     (ref common/interpolate_data.f90:1-17, interpolation_data_latlon_mod.f90:116-154,219-270)."""

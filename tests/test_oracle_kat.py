@@ -90,6 +90,30 @@ def test_kat3_bilinear_coefficients_by_hand(orc):
     np.testing.assert_allclose(t.coef[4:], [(1 - a1) * (1 - b1), a1 * (1 - b1), a1 * b1, (1 - a1) * b1], rtol=0, atol=1e-16)
 
 
+def test_make_mapping_table_known_answers(orc):
+    """ref common/cal_mappingtable.f90:10-49: regular grids in degrees; 8x5 receiver <- 4x3 sender by hand."""
+    t = orc.make_mapping_table(8, 5, 4, 3)
+    cell = lambda i, j: [(int(a), int(b), float(c)) for a, b, c, x, y in zip(t.iS, t.jS, t.coef, t.iD, t.jD) if (x, y) == (i, j)]
+    # (1,1): xr = yr = 0 coincide with source node (1,1): alpha1 = beta1 = 0, only coef(1) = 1 survives the > 0 test
+    assert cell(1, 1) == [(1, 1, 1.0)]
+    # (2,2): xr = 45 of dx_s = 90 -> is = 1, alpha1 = 0.5; yr = 45 of dy_s = 90 -> js = 1, beta1 = 0.5
+    assert cell(2, 2) == [(1, 1, 0.25), (2, 1, 0.25), (2, 2, 0.25), (1, 2, 0.25)]
+    # (8,2): xr = 315 -> is = 4, the east neighbour wraps to mod(4,4)+1 = 1 (:41-42)
+    assert cell(8, 2) == [(4, 1, 0.25), (1, 1, 0.25), (1, 2, 0.25), (4, 2, 0.25)]
+    # (3,5): north pole row, yr = 180 -> js = 3 = ny_s, beta1 = 0: the wrapped row mod(3,3)+1 = 1 is never written
+    assert cell(3, 5) == [(2, 3, 1.0)]
+    assert t.coef.min() > 0.0
+    # destination-major, i fastest (:25, :31), and every destination's weights sum to one
+    key = (t.jD.astype(np.int64) - 1) * 8 + (t.iD - 1)
+    assert np.all(np.diff(key) >= 0)
+    np.testing.assert_allclose(np.bincount(key, weights=t.coef, minlength=40), 1.0, rtol=0, atol=4e-16)
+    # a linear function of latitude is reproduced exactly by the two-point latitude weights (away from the lon wrap)
+    send, recv, coef = t.to_index(4, 8)
+    f = np.repeat(np.arange(3.0) * 90.0, 4)[None, :]          # value = source latitude in degrees from the pole
+    y = orc.remap_apply(send, recv, coef, f, 40).reshape(5, 8)
+    np.testing.assert_allclose(y, np.repeat((np.arange(5.0) * 45.0)[:, None], 8, axis=1), rtol=0, atol=1e-12)
+
+
 def test_table_order_is_dst_major_lon_outer_lat_inner(orc, dccm):
     """ref common/grid_mapping_util_jones99.f90:230-272"""
     A, O, Sx = [as_orc_grid(orc, g) for g in pair(orc, dccm, "T21_1deg")]
