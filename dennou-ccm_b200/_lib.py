@@ -78,6 +78,19 @@ def build_driver():
     return os.path.abspath(DRIVER_PATH)
 
 
+GMAPGEN_PATH = os.path.join(_HERE, "..", "tool", "gmapgen", "gmapgen_main")
+
+
+def build_gmapgen():
+    """tool/gmapgen/gmapgen_main: the reference's table-file generator program over the C ABI (plain g++)."""
+    build()
+    r = subprocess.run(["make", "-C", CSRC, "gmapgen"], capture_output=True, text=True)
+    if r.returncode != 0:
+        print(r.stdout[-2000:], r.stderr[-2000:])
+        raise DccmError("building tool/gmapgen/gmapgen_main failed")
+    return os.path.abspath(GMAPGEN_PATH)
+
+
 _SIGS = {
     "dccm_last_error": (C.c_char_p, []),
     "dccm_build_info": (C.c_char_p, []),
