@@ -141,6 +141,10 @@ _SIGS = {
     "dccm_interp_register": (C.c_int, [C.c_int, C.c_int, C.c_int, vp]),
     "dccm_interpolate_data": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f64p,
                                         C.c_int, C.c_int, f64p, C.c_int]),
+    "dccm_interp_set_model_name": (C.c_int, [C.c_int, C.c_char_p]),
+    "dccm_interpolate_data_named": (C.c_int, [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_int, C.c_int, C.c_int, f64p,
+                                              C.c_int, C.c_int, f64p, C.c_int]),
+    "dccm_f77_set_error_handler": (None, [vp]),
     "dccm_bulkflux_get_host": (C.c_int, [C.c_int, C.c_int] + [f64p] * 28),
     "dccm_bulkflux_device": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
                                        C.POINTER(SfcFields), C.c_double, vp]),
@@ -182,6 +186,18 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+F77_INTERPOLATE_DATA = ("interpolate_data_", None, [C.c_char_p, C.c_char_p] + [i32p] * 3 + [f64p] + [i32p] * 2 + [f64p]
+                        + [i32p] * 3 + [C.c_size_t, C.c_size_t])
+
+
+def f77_interpolate_data():
+    """the bare Fortran external `interpolate_data_` the library exports for Jcup (every argument by reference,
+    CHARACTER lengths appended by value)"""
+    fn = getattr(lib(), F77_INTERPOLATE_DATA[0])
+    fn.restype, fn.argtypes = F77_INTERPOLATE_DATA[1], F77_INTERPOLATE_DATA[2]
+    return fn
 
 
 def declared_symbols():

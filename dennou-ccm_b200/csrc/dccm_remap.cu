@@ -234,6 +234,17 @@ bool detect_zonal(const std::vector<int32_t> &rowptr, const std::vector<int32_t>
 
 std::mutex g_reg_mutex;
 std::map<std::tuple<int, int, int>, dccm_remap *> g_registry;
+std::map<std::string, int> g_model_ids;          // component name -> Jcup component number (guarded by g_reg_mutex)
+
+// Fortran CHARACTER(*) argument -> std::string: `len` characters, trailing blanks (and a stray NUL) dropped.
+std::string fortran_name(const char *s, int64_t len)
+{
+    if (!s || len <= 0) return std::string();
+    size_t n = (size_t)len;
+    if (const void *z = memchr(s, 0, n)) n = (size_t)((const char *)z - s);
+    while (n > 0 && s[n - 1] == ' ') n--;
+    return std::string(s, n);
+}
 
 }  // namespace
 
@@ -681,4 +692,63 @@ extern "C" int dccm_interpolate_data(int recv_model, int send_model, int mapping
         return fail(DCCM_ERR_ARG, "interpolate_data: no operation index registered for (recv=%d, send=%d, tag=%d)",
                     recv_model, send_model, mapping_tag);
     return dccm_remap_apply_host(h, send_data, sn1, sn2, recv_data, rn1, rn2, num_of_data);
+}
+
+// ---------------------------------------------------------------- the coupler's callback, without a Fortran shim
+
+extern "C" int dccm_interp_set_model_name(int model_id, const char *name)
+{
+    if (!name || !*name || model_id < 1) return fail(DCCM_ERR_ARG, "dccm_interp_set_model_name: bad arguments");
+    std::lock_guard<std::mutex> lk(g_reg_mutex);
+    g_model_ids[fortran_name(name, (int64_t)strlen(name))] = model_id;
+    return DCCM_OK;
+}
+
+extern "C" int dccm_interpolate_data_named(const char *recv_model, int64_t recv_len,
+                                           const char *send_model, int64_t send_len, int mapping_tag,
+                                           int sn1, int sn2, const double *send_data,
+                                           int rn1, int rn2, double *recv_data, int num_of_data)
+{
+    const std::string r = fortran_name(recv_model, recv_len), s = fortran_name(send_model, send_len);
+    int ir = 0, is = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_reg_mutex);
+        auto a = g_model_ids.find(r), b = g_model_ids.find(s);
+        if (a != g_model_ids.end()) ir = a->second;
+        if (b != g_model_ids.end()) is = b->second;
+    }
+    if (!ir || !is)
+        return fail(DCCM_ERR_ARG, "interpolate_data: unknown component name '%s' (dccm_interp_set_model_name)",
+                    (!ir ? r : s).c_str());
+    return dccm_interpolate_data(ir, is, mapping_tag, sn1, sn2, send_data, rn1, rn2, recv_data, num_of_data);
+}
+
+namespace {
+void default_f77_error(const char *msg)
+{
+    fprintf(stderr, "interpolate_data: %s\n", msg);
+    exit(1);                                       // the reference leaves through jcup_error, which aborts the run
+}
+void (*g_f77_error)(const char *) = default_f77_error;
+}  // namespace
+
+extern "C" void dccm_f77_set_error_handler(void (*handler)(const char *))
+{
+    g_f77_error = handler ? handler : default_f77_error;
+}
+
+// The external procedure itself under its Fortran link name (gfortran / ifort / nvfortran on x86-64 and aarch64:
+// lower case + underscore, every argument by reference, the CHARACTER lengths appended by value).  Lengths are
+// size_t with gfortran >= 8 and 32-bit int before that; only the low 32 bits are looked at, so both work.
+extern "C" void interpolate_data_(const char *recv_model, const char *send_model, const int32_t *mapping_tag,
+                                  const int32_t *sn1, const int32_t *sn2, const double *send_data,
+                                  const int32_t *rn1, const int32_t *rn2, double *recv_data,
+                                  const int32_t *num_of_data, const int32_t *tn, const int32_t *exchange_tag,
+                                  size_t recv_model_len, size_t send_model_len)
+{
+    (void)tn; (void)exchange_tag;                  // unused by the reference as well (ref common/interpolate_data.f90:15)
+    int rc = dccm_interpolate_data_named(recv_model, (int64_t)(recv_model_len & 0xffffffffu),
+                                         send_model, (int64_t)(send_model_len & 0xffffffffu), *mapping_tag,
+                                         *sn1, *sn2, send_data, *rn1, *rn2, recv_data, *num_of_data);
+    if (rc != DCCM_OK) g_f77_error(dccm_last_error());
 }

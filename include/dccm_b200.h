@@ -18,6 +18,7 @@
  */
 #ifndef DCCM_B200_H
 #define DCCM_B200_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -176,6 +177,26 @@ int dccm_interp_register(int recv_model, int send_model, int mapping_tag, dccm_r
 int dccm_interpolate_data(int recv_model, int send_model, int mapping_tag,
                           int sn1, int sn2, const double *send_data,
                           int rn1, int rn2, double *recv_data, int num_of_data);
+
+/* The coupler's callback WITHOUT a Fortran shim.  Jcup resolves the bare external symbol `interpolate_data_`
+ * (ref common/interpolate_data.f90:1-17; linked as a lone object, Mkinclude:167).  The library exports that symbol
+ * itself with the Fortran calling convention of gfortran / ifort / nvfortran on 64-bit Linux -- every argument by
+ * reference, the two CHARACTER(*) lengths appended by value -- so leaving interpolate_data.o out of the link line
+ * and adding -ldccm_b200 is enough.  Component names are translated through a table the host fills once with
+ * what jcup_get_comp_num_from_name returns (ref common/interpolation_data_latlon_mod.f90:289).  The subroutine has
+ * no status argument: a failure goes to the error handler (default: message to stderr and exit(1), the behaviour of
+ * the reference's jcup_error); dccm_interpolate_data_named is the same call with a status for C callers. */
+int dccm_interp_set_model_name(int model_id, const char *name);
+int dccm_interpolate_data_named(const char *recv_model, int64_t recv_len,
+                                const char *send_model, int64_t send_len, int mapping_tag,
+                                int sn1, int sn2, const double *send_data,
+                                int rn1, int rn2, double *recv_data, int num_of_data);
+void dccm_f77_set_error_handler(void (*handler)(const char *message));
+void interpolate_data_(const char *recv_model, const char *send_model, const int32_t *mapping_tag,
+                       const int32_t *sn1, const int32_t *sn2, const double *send_data,
+                       const int32_t *rn1, const int32_t *rn2, double *recv_data,
+                       const int32_t *num_of_data, const int32_t *tn, const int32_t *exchange_tag,
+                       size_t recv_model_len, size_t send_model_len);
 
 /* ------------------------------------------------------------------ bulk flux (K2)
  * Replaces DSFCM_Util_SfcBulkFlux_Get, ref sfc/DSFCM_Util_SfcBulkFlux_mod.f90:108-439

@@ -30,6 +30,37 @@ def test_library_exports_every_declared_symbol(dccm):
     assert b"sm_100a" in dccm.lib().dccm_build_info()
 
 
+def test_library_exports_the_fortran_external_interpolate_data(dccm):
+    """ref common/interpolate_data.f90:1-17, Mkinclude:167: Jcup links the bare symbol `interpolate_data_`; the library
+    exports it itself.  Host-side behaviour only here: name table, blank-padded CHARACTER arguments, error paths."""
+    lib = dccm.lib()
+    assert hasattr(ctypes.CDLL(dccm._lib.LIB_PATH), "interpolate_data_")
+    dccm._lib.f77_interpolate_data()                          # binds with the 12 + 2 hidden-length signature
+    x, y = np.zeros((1, 4)), np.zeros((1, 4))
+    f = dccm._lib.dp
+    # unknown component name -> status + message (the Fortran entry would hand the message to the error handler)
+    rc = lib.dccm_interpolate_data_named(b"SFC     ", 8, b"ATM", 3, 1, 4, 1, f(x), 4, 1, f(y), 1)
+    assert rc == 1 and b"unknown component name 'SFC'" in lib.dccm_last_error()
+    dccm._lib.check(lib.dccm_interp_set_model_name(3, b"SFC"))
+    dccm._lib.check(lib.dccm_interp_set_model_name(1, b"ATM"))
+    rc = lib.dccm_interpolate_data_named(b"SFC     ", 8, b"ATM", 3, 7, 4, 1, f(x), 4, 1, f(y), 1)
+    assert rc == 1 and b"no operation index registered for (recv=3, send=1, tag=7)" in lib.dccm_last_error()
+    assert lib.dccm_interp_set_model_name(0, b"X") == 1 and lib.dccm_interp_set_model_name(2, b"") == 1
+    # the error handler receives the message when the Fortran-named entry fails
+    seen = []
+    H = ctypes.CFUNCTYPE(None, ctypes.c_char_p)
+    h = H(lambda m: seen.append(m))
+    lib.dccm_f77_set_error_handler(ctypes.cast(h, ctypes.c_void_p))
+    try:
+        i = lambda v: ctypes.byref(ctypes.c_int32(v))
+        p32 = lambda v: ctypes.cast(i(v), dccm._lib.i32p)
+        dccm._lib.f77_interpolate_data()(b"OCN  ", b"ATM  ", p32(1), p32(4), p32(1), f(x), p32(4), p32(1), f(y), p32(1),
+                                        p32(1), p32(1), 5, 5)
+        assert seen and b"unknown component name 'OCN'" in seen[0]
+    finally:
+        lib.dccm_f77_set_error_handler(None)
+
+
 def test_library_is_sm100a_only(dccm):
     import subprocess
     out = subprocess.run(["cuobjdump", "-lelf", dccm._lib.LIB_PATH], capture_output=True, text=True).stdout

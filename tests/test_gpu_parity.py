@@ -134,6 +134,26 @@ def test_remap_ragged_empty_and_duplicate_rows(gpu, orc, dccm):
         op.apply_host(x, rn1=n_recv - 1)
 
 
+def test_fortran_external_interpolate_data_symbol(gpu, orc, dccm, S):
+    """`interpolate_data_` as Jcup calls it (ref common/interpolate_data.f90:1-17): every argument by reference,
+    blank-padded component names with their hidden lengths; same bits as the oracle's loop."""
+    import ctypes as C
+    L = dccm._lib
+    lib = dccm.lib()
+    A, O, Sx = pair(orc, dccm, "T42_T42")
+    send_i, recv_i, coef = dccm.tables.gen_table_jones99(A, Sx, 2).index(A.im, Sx.im)
+    op = dccm.RemapOperator(send_i, recv_i, coef, A.n, Sx.n, A.im, Sx.im)
+    L.check(lib.dccm_interp_set_model_name(1, b"ATM"))
+    L.check(lib.dccm_interp_set_model_name(3, b"SFC"))
+    L.check(lib.dccm_interp_register(3, 1, 2, op._h))
+    x = S.generic_fields(np, A, 6)
+    recv = np.full((7, Sx.n), np.nan)
+    ints = [C.c_int32(v) for v in (2, A.n, 6, Sx.n, 7, 4, 1, 1)]          # mapping_tag sn1 sn2 rn1 rn2 num_of_data tn exchange_tag
+    p = [C.cast(C.byref(v), L.i32p) for v in ints]
+    L.f77_interpolate_data()(b"SFC       ", b"ATM   ", p[0], p[1], p[2], L.dp(x), p[3], p[4], L.dp(recv), p[5], p[6], p[7], 10, 6)
+    assert np.array_equal(recv, orc.remap_apply(send_i, recv_i, coef, x, Sx.n, 7, 4))
+
+
 @pytest.mark.parametrize("sizes", [(360, 181, 128, 65), (128, 65, 360, 181)])
 def test_remap_with_the_standalone_regular_grid_table(gpu, orc, dccm, sizes):
     """Tables of common/cal_mappingtable.f90:10-49 (make_mapping_table) through the remap apply, bit-exact."""
