@@ -126,8 +126,8 @@ class CpuSample:
         rows = max(2, min(A.jm, int(round(target_cols / (A.im * M)))))
         self.frac = rows / A.jm
         ja0 = (A.jm - rows) // 2
-        lat0, lat1 = (A.y_Lat[ja0] + (A.y_Lat[ja0 - 1] if ja0 else -np.pi / 2)) / 2, \
-                     (A.y_Lat[ja0 + rows - 1] + (A.y_Lat[ja0 + rows] if ja0 + rows < A.jm else np.pi / 2)) / 2
+        lat0 = (A.y_Lat[ja0] + A.y_Lat[ja0 - 1]) / 2 if ja0 else -np.inf                     # whole grid: every row
+        lat1 = (A.y_Lat[ja0 + rows - 1] + A.y_Lat[ja0 + rows]) / 2 if ja0 + rows < A.jm else np.inf
         band = lambda g: (int(np.searchsorted(g.y_Lat, lat0)), int(np.searchsorted(g.y_Lat, lat1)))
         self.bA, self.bS, self.bO = (ja0, ja0 + rows), band(S), band(O)
         self.grids = (A, O, S)
