@@ -1,0 +1,87 @@
+"""Second-order conservative A->S table through the whole exchange (run with -m gpu on a B200).
+
+gmapgen's default for the atmosphere -> exchange-grid table is interp_order_AS = 2 (ref tool/gmapgen/gmapgen_main.f90:219),
+and the reference's shipped conservative configuration (exp/APEI07Couple/common/genmapgen_ATM_T42-OCN_Pl42_conserve.conf)
+does not override it: every destination row then carries its first-order entry plus the -w2/dphi, +w2/dphi pair on the
+two neighbouring source latitudes (ref common/grid_mapping_util_jones99.f90:252-267) -- three source rows per stencil
+in the fused surface kernel's tiles instead of one.
+"""
+import importlib
+
+import numpy as np
+import pytest
+
+from util import pair
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def S(dccm):
+    return importlib.import_module("dennou-ccm_b200.synthetic")
+
+
+@pytest.mark.parametrize("name,members", [("T21_Pl42", 1), ("T21_1deg", 2), ("T106_1deg", 1)])
+def test_fused_surface_kernel_with_second_order_atmosphere_table(gpu, orc, dccm, S, name, members):
+    """staged and direct forms of the fused kernel == unfused remap -> bulk flux -> pack, bit for bit"""
+    import torch
+    X = importlib.import_module("dennou-ccm_b200.exchange")
+    L = dccm._lib
+    A, O, Sx = pair(orc, dccm, name)
+    tabs = X.build_tables(A, O, Sx, order_as=2)
+    assert len(tabs["as_cons"][2]) > 2 * Sx.n                     # the pairs are there
+    M, K = members, 8
+    tt = lambda d: {k: torch.as_tensor(v, device=gpu).contiguous() for k, v in d.items()}
+    cols = [tt(S.column_inputs(np, A, K, 1, member=m)) for m in range(M)]
+    atms = [tt(S.atm_surface_fields(np, A, member=m)) for m in range(M)]
+    ocns = [tt(S.ocn_surface_fields(np, O, member=m)) for m in range(M)]
+    ex = X.SurfaceExchange(A, O, Sx, K, 1, 1, tabs=tabs, members=M, device=gpu)
+    ex.set_inputs({k: torch.cat([c[k] for c in cols], dim=-1).contiguous() for k in cols[0]},
+                  {k: torch.stack([a[k] for a in atms]) for k in atms[0]},
+                  {k: torch.stack([o[k] for o in ocns]) for k in ocns[0]})
+    ex.forward()
+    ex.remap_to_sfc(); ex.bulk(); ex.pack_sfc()
+    torch.cuda.synchronize()
+    want = {"s2a": ex.s2a.clone(), "s2o": ex.s2o.clone()}
+    forms = []
+    try:
+        for staged in (1, 0):
+            L.check(L.lib().dccm_sfc_exchange_config(staged, 5))
+            ex.s2a.fill_(float("nan")); ex.s2o.fill_(float("nan"))
+            ex.sfc_fused()
+            torch.cuda.synchronize()
+            forms.append(L.lib().dccm_sfc_exchange_last_form())
+            assert torch.equal(ex.s2a, want["s2a"]), f"staged={staged} s2a"
+            assert torch.equal(ex.s2o, want["s2o"]), f"staged={staged} s2o"
+    finally:
+        L.check(L.lib().dccm_sfc_exchange_config(1, 5))
+    print(name, "forms launched (1 = staged):", forms)
+    assert forms[1] == 0
+
+
+def test_exchange_step_vs_oracle_second_order(gpu, orc, dccm, S):
+    """whole exchange with the second-order A->S table against the oracle: remaps and the reference-order column
+    solve bit-exact, bulk-flux-derived stages within the conditioning bar"""
+    import torch
+    from exchange_ref import compare_exchange, oracle_exchange
+    X = importlib.import_module("dennou-ccm_b200.exchange")
+    A, O, Sx = pair(orc, dccm, "T21_Pl42")
+    K = 16
+    tabs = X.build_tables(A, O, Sx, order_as=2)
+    ex = X.SurfaceExchange(A, O, Sx, K, 1, 1, tabs=tabs, fast=False, device=gpu)
+    col, atm, ocn = S.column_inputs(np, A, K, 1), S.atm_surface_fields(np, A), S.ocn_surface_fields(np, O)
+    tt = lambda d: {k: torch.as_tensor(v, device=gpu).contiguous() for k, v in d.items()}
+    ex.set_inputs(tt(col), {k: v[None] for k, v in tt(atm).items()}, {k: v[None] for k, v in tt(ocn).items()})
+    ex.step(fused=False)
+    torch.cuda.synchronize()
+    ref = oracle_exchange(orc, S, A, O, Sx, K, 1, 1, tabs, col, atm, ocn)
+    detail = {}
+    worst = compare_exchange(ex, ref, detail=detail)
+    exact = ("Coef1", "Coef2", "s_bil", "s_cons", "s_obil", "s_ocons")
+    assert all(detail[k] == 0.0 for k in exact), {k: detail[k] for k in exact}
+    assert worst <= 1e-11, detail
+    keep = {k: getattr(ex, k).clone() for k in ("s2a", "s2o", "a_recv", "o_recv")}
+    ex.step(fused=True)
+    torch.cuda.synchronize()
+    for k, v in keep.items():
+        assert torch.equal(getattr(ex, k), v), f"fused step differs in {k}"
