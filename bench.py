@@ -203,7 +203,15 @@ def cpu_baseline(dccm, wl, budget_s=12.0, min_reps=3, max_reps=200):
         spent += ts[-1][0]
     t = float(np.median([x[0] for x in ts]))
     parts = {k: float(np.median([x[1][k] for x in ts])) for k in ts[0][1]}
-    return {"value": cs.frac / t, "unit": "exchanges/s", "cores": cs.orc.num_threads(), "kind": "port",
+    cores = cs.orc.num_threads()
+    one = None
+    if cores > 1:                      # the reference's SFC / OCN components are single-rank: one-thread figure too
+        cs.orc.set_num_threads(1)
+        try:
+            one = cs.frac / cs.run_once()[0]
+        finally:
+            cs.orc.set_num_threads(cores)
+    return {"value": cs.frac / t, "unit": "exchanges/s", "cores": cores, "value_one_core": one, "kind": "port",
             "sample": cs.describe(), "sample_seconds": t, "repetitions": len(ts), "timed_seconds": spent, "parts_s": parts,
             "note": "C restatement of the reference loops (oracle/); remap and the tridiagonal sweeps are "
                     "serial as in the reference, OpenMP only where the reference has !$omp"}

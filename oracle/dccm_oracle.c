@@ -44,6 +44,16 @@ int orc_num_threads(void)
 #endif
 }
 
+/* threads used by the `!$omp` regions from now on (the reference's SFC / OCN components run on one rank) */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------ table container */
 
 orc_table *orc_table_new(void) { return (orc_table *)calloc(1, sizeof(orc_table)); }

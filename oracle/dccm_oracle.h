@@ -121,6 +121,7 @@ void orc_atm_store_surf_flx(int64_t n, const double *const *in, double *const *o
                             double LatentHeat, double CpDry, double delta_t);
 
 int orc_num_threads(void);
+void orc_set_num_threads(int n);
 
 #ifdef __cplusplus
 }
