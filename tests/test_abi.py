@@ -169,6 +169,22 @@ def test_dsfcm_admin_grid_layout(dccm):
     assert v.xy_SIceCon.shape == (66, 130)
 
 
+def test_staged_surface_kernel_is_compiled_with_tma_bulk_copies(dccm):
+    """B200_PROFILING.md: the SASS mnemonics that prove the TMA path -- UBLKCP (cp.async.bulk global -> shared) and
+    SYNCS (mbarrier arrive / try_wait) -- must appear in the staged fused surface kernel and nowhere tensor-core
+    instructions are expected (the path is HBM-bound fp64: no HMMA / UTCMMA in the library)."""
+    import subprocess
+    sass = subprocess.run(["cuobjdump", "-sass", dccm._lib.LIB_PATH], capture_output=True, text=True).stdout
+    funcs = re.split(r"\n\s*Function : ", sass)[1:]
+    staged = [f for f in funcs if "sfc_exchange_staged_kernel" in f.split("\n", 1)[0]]
+    assert len(staged) >= 6                                   # MINB 4/5/6 x peer-segment on/off (+ the API-complete form)
+    for f in staged:
+        assert "UBLKCP" in f and "SYNCS" in f, f.split("\n", 1)[0]
+    assert not re.search(r"\b(HMMA|UTCHMMA|UTCMMA|IMMA|DMMA)\b", sass)
+    others = [f for f in funcs if "UBLKCP" in f and "sfc_exchange_staged_kernel" not in f.split("\n", 1)[0]]
+    assert not others
+
+
 def test_no_cpu_fallback_without_gpu(dccm):
     import torch
     if torch.cuda.is_available():
