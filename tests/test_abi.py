@@ -169,6 +169,36 @@ def test_dsfcm_admin_grid_layout(dccm):
     assert v.xy_SIceCon.shape == (66, 130)
 
 
+def test_header_is_plain_c_and_links_from_c(dccm, tmp_path):
+    """The boundary is a C ABI: include/dccm_b200.h compiles as strict C99 and a C client links against the library
+    (host-only entry points here; dccm_init must fail loudly without a GPU instead of falling back)."""
+    import subprocess
+    src = tmp_path / "client.c"
+    src.write_text(r"""
+#include "dccm_b200.h"
+#include <stdio.h>
+int main(void) {
+    double lon[8], lat[4], lw[8], aw[4];
+    dccm_table *t = 0;
+    if (dccm_grid_gauss(8, 4, lon, lat, lw, aw)) return 1;
+    if (dccm_table_gen_make_mapping_table(8, 5, 4, 3, &t)) return 2;
+    printf("entries=%lld\n", (long long)dccm_table_size(t));
+    dccm_table_free(t);
+    if (dccm_table_gen_make_mapping_table(8, 1, 4, 3, &t) != DCCM_ERR_ARG) return 3;
+    printf("error=%s\n", dccm_last_error());
+    return 0;
+}
+""")
+    exe = tmp_path / "client"
+    libdir = os.path.dirname(dccm._lib.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-o", str(exe), str(src), "-L", libdir, "-ldccm_b200", f"-Wl,-rpath,{libdir}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "entries=84" in r.stdout and "ny >= 2" in r.stdout, r.stdout + r.stderr
+
+
 def test_staged_surface_kernel_is_compiled_with_tma_bulk_copies(dccm):
     """B200_PROFILING.md: the SASS mnemonics that prove the TMA path -- UBLKCP (cp.async.bulk global -> shared) and
     SYNCS (mbarrier arrive / try_wait) -- must appear in the staged fused surface kernel and nowhere tensor-core
