@@ -8,7 +8,7 @@ importlib.import_module("dennou-ccm_b200") (the directory name is not a Python i
 from . import _lib
 from ._lib import DccmError, build, build_driver, build_gmapgen, lib
 from . import tables, grid_mapping_util, grid_mapping_util_jones99, cal_mappingtable
-from . import interpolation_data_latlon_mod, dsfcm, dcpam_sfc_implicit_coupling_mod, dccm_ocn_mod, dcpam_main_mod
+from . import interpolation_data_latlon_mod, dsfcm, dcpam_sfc_implicit_coupling_mod, dccm_ocn_mod, dccm_atm_mod, dcpam_main_mod
 from .interpolation_data_latlon_mod import RemapOperator, interpolate_data
 from .dcpam_sfc_implicit_coupling_mod import SfcImplicitCoupling
 from .dsfcm import DSFCM_Util_SfcBulkFlux_Get

@@ -40,7 +40,37 @@ atm_store_surf_flx_kernel(int64_t n, const dccm_atm_sfcflx f, double LatentHeat,
     f.DSurfLatentFlxDTs[c] = dlat;
     f.DSurfHFlxDTs[c] = CpDry * tempTC + dlat - f.DelRadLDwFlux00[c];                                // :1108-1112
 }
+
+// Atmosphere get side after the S->A remaps (ref atm/dccm_atm_mod.f90:823-836): the surface temperature the AGCM is
+// handed is the radiative one, (LUwRFlx / StB)**0.25 of the composite upward long-wave flux; the other gets are
+// the remapped layers themselves (albedo, fluxes) or go to level 1 of the tendencies (the backward solve's level1).
+__global__ void __launch_bounds__(kThreads)
+atm_get_kernel(int64_t n, const double *__restrict__ a_recv, int64_t ld, double StB, double *__restrict__ SfcTemp,
+               double *__restrict__ SfcAlbedo, double *__restrict__ SurfHeatFlux, double *__restrict__ SurfH2OVapFlux)
+{
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= n) return;
+    // S->A layers (exchange.py S2A_CONS / S2A_BIL): 0 LUwRFlx, 1 SUwRFlx, 2 SenHFlx, 3 QVapMFlx, 4 SfcAlbedo, 5..8 DelVarImplCPL
+    SfcTemp[c] = pow(a_recv[c] / StB, 0.25);                                                         // :831
+    if (SfcAlbedo) SfcAlbedo[c] = a_recv[c + 4 * ld];                                                // :827
+    if (SurfHeatFlux) SurfHeatFlux[c] = a_recv[c + 2 * ld];                                          // :825
+    if (SurfH2OVapFlux) SurfH2OVapFlux[c] = a_recv[c + 3 * ld];                                      // :826, :836
+}
 }  // namespace
+
+extern "C" int dccm_atm_get_assemble_device(int64_t n, const double *a_recv, int64_t ld, double StB, double *SfcTemp,
+                                            double *SfcAlbedo, double *SurfHeatFlux, double *SurfH2OVapFlux, void *stream)
+{
+    if (!a_recv || !SfcTemp) return fail(DCCM_ERR_ARG, "dccm_atm_get_assemble: null buffer");
+    if (n < 1 || ld < n) return fail(DCCM_ERR_ARG, "dccm_atm_get_assemble: need 1 <= n <= ld");
+    if (!(StB > 0.0)) return fail(DCCM_ERR_ARG, "dccm_atm_get_assemble: StB must be positive");
+    int rc = ensure_device();
+    if (rc) return rc;
+    atm_get_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        n, a_recv, ld, StB, SfcTemp, SfcAlbedo, SurfHeatFlux, SurfH2OVapFlux);
+    DCCM_CUDA_TRY(cudaGetLastError());
+    return DCCM_OK;
+}
 
 extern "C" int dccm_atm_store_surf_flx_device(int64_t n, const dccm_atm_sfcflx *f, double LatentHeat, double CpDry,
                                               double DelTime, void *stream)

@@ -366,6 +366,14 @@ typedef struct dccm_atm_sfcflx {
 int dccm_atm_store_surf_flx_device(int64_t n, const dccm_atm_sfcflx *f, double LatentHeat, double CpDry,
                                    double DelTime, void *stream);
 
+/* Atmosphere get side, ref atm/dccm_atm_mod.f90:823-836: from the 9 remapped S->A layers (row length ld, order as in
+ * dccm_sfc_exchange_device's s2a) the surface temperature handed to the AGCM, xy_SfcTemp = (xy_LUwRFlx/StB)**0.25
+ * (:831), and -- where the pointers are not NULL -- copies of SfcAlbedo (:827), SenHFlx -> xy_SurfHeatFlux (:825) and
+ * QVapMFlx -> xyf_SurfQMixFlux(:,:,IndexH2OVap) (:826, :836).  Level 1 of the tendencies (:832-835) is the `level1`
+ * argument of dccm_vdiff_backward_device.  StB is the glue's own constant (ref :789). */
+int dccm_atm_get_assemble_device(int64_t n, const double *a_recv, int64_t ld, double StB, double *SfcTemp,
+                                 double *SfcAlbedo, double *SurfHeatFlux, double *SurfH2OVapFlux, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

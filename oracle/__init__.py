@@ -66,6 +66,7 @@ def lib():
         L.orc_avg_finish.argtypes = [_f64p, C.c_int64, C.c_int]
         L.orc_atm_store_surf_flx.argtypes = [C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                              C.c_double, C.c_double, C.c_double]
+        L.orc_atm_sfc_temp.argtypes = [C.c_int64, _f64p, C.c_double, _f64p]
         L.orc_num_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -291,6 +292,14 @@ def atm_store_surf_flx(fields, LatentHeat, CpDry, DelTime):
     pin = (C.c_void_p * len(a))(*[x.ctypes.data for x in a])
     pout = (C.c_void_p * len(out))(*[out[k].ctypes.data for k in ATM_SFCFLX_OUT])
     lib().orc_atm_store_surf_flx(n, pin, pout, LatentHeat, CpDry, DelTime)
+    return out
+
+
+def atm_sfc_temp(LUwRFlx, StB=5.670373e-8):
+    """ref atm/dccm_atm_mod.f90:831"""
+    x = np.ascontiguousarray(LUwRFlx, dtype=np.float64)
+    out = np.empty_like(x)
+    lib().orc_atm_sfc_temp(x.size, x, StB, out)
     return out
 
 

@@ -1091,3 +1091,11 @@ void orc_atm_store_surf_flx(int64_t n, const double *const *in, double *const *o
         out[10][c] = CpDry * TempTC[c] + out[9][c] - DelLDw00[c];
     }
 }
+
+/* ref atm/dccm_atm_mod.f90:831: xy_SfcTemp(:,:) = (xy_LUwRFlx/StB)**0.25d0 -- the radiative surface temperature the
+ * atmosphere derives from the remapped composite upward long-wave flux */
+void orc_atm_sfc_temp(int64_t n, const double *LUwRFlx, double StB, double *SfcTemp)
+{
+    for (int64_t c = 0; c < n; c++) SfcTemp[c] = pow(LUwRFlx[c] / StB, 0.25);
+}
+

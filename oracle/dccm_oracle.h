@@ -120,6 +120,9 @@ void orc_avg_finish(double *acc, int64_t n, int count);
 void orc_atm_store_surf_flx(int64_t n, const double *const *in, double *const *out,
                             double LatentHeat, double CpDry, double delta_t);
 
+/* ref atm/dccm_atm_mod.f90:831 */
+void orc_atm_sfc_temp(int64_t n, const double *LUwRFlx, double StB, double *SfcTemp);
+
 int orc_num_threads(void);
 void orc_set_num_threads(int n);
 

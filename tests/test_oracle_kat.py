@@ -402,6 +402,18 @@ def test_atm_surface_flux_bookkeeping_known_answers(orc):
     assert o["DSurfHFlxDTs"][0] == 1004.6 * 0.03 + o["DSurfLatentFlxDTs"][0] - 0.5
 
 
+def test_atm_radiative_surface_temperature_known_answers(orc):
+    """ref atm/dccm_atm_mod.f90:831: xy_SfcTemp = (xy_LUwRFlx/StB)**0.25 inverts the bulk routine's LUwRFlx = StB*T**4
+    (ref sfc/DSFCM_Util_SfcBulkFlux_mod.f90:318); for the composite slot T is the area-weighted 4th-power mean."""
+    StB = 5.670373e-8
+    t = np.array([220.0, 271.35, 273.15, 288.0, 310.0])
+    np.testing.assert_allclose(orc.atm_sfc_temp(StB * t ** 4), t, rtol=4e-16, atol=0)
+    f = 0.3                                                     # 30 % ice at 260 K over 274 K water
+    lu3 = (1 - f) * StB * 274.0 ** 4 + f * StB * 260.0 ** 4     # composite LUwRFlx (ref :334)
+    want = ((1 - f) * 274.0 ** 4 + f * 260.0 ** 4) ** 0.25
+    assert abs(orc.atm_sfc_temp(np.array([lu3]))[0] - want) <= 1e-12
+
+
 def test_time_average_is_the_mean_of_the_puts(orc):
     rng = np.random.default_rng(3)
     puts = [rng.normal(size=(12, 50)) for _ in range(4)]

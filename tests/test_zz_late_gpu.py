@@ -85,3 +85,24 @@ def test_exchange_step_vs_oracle_second_order(gpu, orc, dccm, S):
     torch.cuda.synchronize()
     for k, v in keep.items():
         assert torch.equal(getattr(ex, k), v), f"fused step differs in {k}"
+
+
+def test_atm_get_side_assembly(gpu, orc, dccm, S):
+    """ref atm/dccm_atm_mod.f90:823-836 on the device: radiative surface temperature from the remapped composite LUwRFlx
+    (device pow vs libm pow: within 1e-15), the other gets are exact copies of their layers; cells beyond n untouched."""
+    import torch
+    A = dccm.tables.get_LonLatGrid(128, 64)
+    n, ld = A.n, A.n + 32
+    rng = np.random.default_rng(5)
+    r = rng.normal(0.0, 50.0, (9, ld))
+    r[0] = 5.670373e-8 * (240.0 + 70.0 * rng.random(ld)) ** 4
+    a_recv = torch.as_tensor(r, device=gpu).contiguous()
+    got = dccm.dccm_atm_mod.atm_get_assemble(a_recv, n)
+    want = orc.atm_sfc_temp(r[0, :n])
+    np.testing.assert_allclose(got["SfcTemp"].cpu().numpy(), want, rtol=1e-15, atol=0)     # CUDA pow: 2 ulp, glibc: < 1 ulp
+    assert np.array_equal(got["SfcAlbedo"].cpu().numpy(), r[4, :n])
+    assert np.array_equal(got["SurfHeatFlux"].cpu().numpy(), r[2, :n])
+    assert np.array_equal(got["SurfH2OVapFlux"].cpu().numpy(), r[3, :n])
+    with pytest.raises(dccm.DccmError, match="n <= ld"):
+        dccm.dccm_atm_mod.atm_get_assemble(a_recv, ld + 1)
+
