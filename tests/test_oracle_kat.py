@@ -51,6 +51,48 @@ def test_kat1_first_order_rows_sum_to_one(orc, dccm, name):
         assert send.min() >= 1 and send.max() <= s.n and recv.min() >= 1 and recv.max() <= d.n
 
 
+def _independent_overlap_matrix(s, d):
+    """First-order conservative weights from first principles (Jones 1999, eq. for lat-lon cells): the share of the
+    destination cell's area covered by each source cell.  Written independently of the generator: latitude edges
+    from the cumulative quadrature weights (sin phi_edge = -1 + sum w, no asin/sin recurrence), longitude edges half a
+    spacing either side of the centres, interval overlap on the circle by direct unwrapping."""
+    def lat_edges(g):
+        e = np.concatenate([[-1.0], -1.0 + np.cumsum(g.y_LatWt)])
+        e[-1] = 1.0
+        return e
+    def lon_overlap(gs, gd):
+        ws, wd = 2.0 * math.pi / gs.im, 2.0 * math.pi / gd.im
+        lo_s, lo_d = gs.x_Lon - ws / 2.0, gd.x_Lon - wd / 2.0
+        out = np.zeros((gd.im, gs.im))
+        for shift in (-2.0 * math.pi, 0.0, 2.0 * math.pi):
+            a = np.maximum(lo_d[:, None], lo_s[None, :] + shift)
+            b = np.minimum(lo_d[:, None] + wd, lo_s[None, :] + ws + shift)
+            out += np.clip(b - a, 0.0, None)
+        return np.minimum(out, min(ws, wd)) / wd            # a full-circle cell meets itself in every shift
+    es, ed = lat_edges(s), lat_edges(d)
+    a = np.maximum(ed[:-1, None], es[None, :-1])
+    b = np.minimum(ed[1:, None], es[None, 1:])
+    wy = np.clip(b - a, 0.0, None) / (ed[1:] - ed[:-1])[:, None]          # (jm_d, jm_s)
+    wx = lon_overlap(s, d)                                                # (im_d, im_s)
+    return np.einsum("js,ir->jisr", wy, wx).reshape(d.n, s.n)
+
+
+@pytest.mark.parametrize("name", ["T21_Pl42", "T21_1deg"])
+def test_kat1b_every_first_order_weight_equals_the_cell_overlap_fraction(orc, dccm, name):
+    """ref common/grid_mapping_util_jones99.f90:341-350: w1 = dlon_overlap * (sin phi2 - sin phi1) / A_dst.  Every
+    entry of every table against the independently computed overlap fraction (dense, small grids)."""
+    A, O, Sx = [as_orc_grid(orc, g) for g in pair(orc, dccm, name)]
+    for s, d in [(A, Sx), (Sx, A), (Sx, O), (O, Sx), (A, O), (O, A)]:
+        t = orc.gen_jones99(s, d, 1, lon_mode=1)
+        send, recv, coef = t.to_index(s.im, d.im)
+        W = np.zeros((d.n, s.n))
+        np.add.at(W, (recv - 1, send - 1), coef)
+        want = _independent_overlap_matrix(s, d)
+        assert np.abs(W - want).max() <= 2e-12, (name, s.im, s.jm, d.im, d.jm)
+        # the same cells overlap (slivers of ~1e-13 come and go with the rounding of the edge recurrence, ref :147-151)
+        assert np.array_equal(W > 1e-9, want > 1e-9)
+
+
 @pytest.mark.parametrize("name", PAIRS)
 def test_kat2_global_integral_is_conserved(orc, dccm, name, S):
     A, O, Sx = [as_orc_grid(orc, g) for g in pair(orc, dccm, name)]
@@ -72,6 +114,47 @@ def test_kat3_constant_field_is_preserved(orc, dccm, name):
             send, recv, coef = t.to_index(s.im, d.im)
             y = orc.remap_apply(send, recv, coef, np.full((1, s.n), 7.25), d.n)
             assert np.abs(y / 7.25 - 1.0).max() <= 1e-12
+
+
+def test_kat3b_second_order_term_reproduces_latitude_linear_fields(orc, dccm):
+    """ref common/grid_mapping_util_jones99.f90:252-267, :354-365 (w2 of eq. (7) in Jones 1999).  For a field that is
+    linear in the source CENTRE latitudes, f_n = a + b*phi_n, the centred (one-sided at the poles) gradient is b in
+    every source cell, so the second-order remap must return, per destination cell k,
+        a + b * ( mean_k(phi) + sum_n w1_nk * (phi_n - centroid_n) )
+    with mean_k / centroid_n the area-weighted mean latitudes of the destination cell / source cell.  The right-hand
+    side is computed here by Gauss-Legendre quadrature of phi*cos(phi) on edges rebuilt from the cumulative weights --
+    nothing of the generator's closed forms or recurrences is reused."""
+    A, O, Sx = [as_orc_grid(orc, g) for g in pair(orc, dccm, "T21_Pl42")]
+    xg, wg = np.polynomial.legendre.leggauss(12)
+
+    def edges(g):
+        e = np.concatenate([[-1.0], -1.0 + np.cumsum(g.y_LatWt)])
+        e[-1] = 1.0
+        return np.arcsin(np.clip(e, -1.0, 1.0))
+
+    def mean_lat(p1, p2):                       # area-weighted mean latitude of the band [p1, p2]
+        h, c = 0.5 * (p2 - p1), 0.5 * (p2 + p1)
+        phi = c[..., None] + h[..., None] * xg
+        return (phi * np.cos(phi) * wg).sum(-1) * h / (np.sin(p2) - np.sin(p1))
+
+    a, b = 3.0, 0.75
+    for s, d in [(A, Sx), (A, O), (O, A), (Sx, A)]:
+        es, ed = edges(s), edges(d)
+        lo = np.maximum(ed[:-1, None], es[None, :-1]); hi = np.minimum(ed[1:, None], es[None, 1:])
+        w1 = np.clip(np.sin(hi) - np.sin(lo), 0.0, None) / (np.sin(ed[1:]) - np.sin(ed[:-1]))[:, None]   # (jm_d, jm_s)
+        centroid = mean_lat(es[:-1], es[1:])
+        want_row = a + b * (mean_lat(ed[:-1], ed[1:]) + (w1 * (s.y_Lat - centroid)[None, :]).sum(1))
+        t = orc.gen_jones99(s, d, 2)
+        send, recv, coef = t.to_index(s.im, d.im)
+        f = np.repeat(a + b * s.y_Lat, s.im)[None, :]
+        got = orc.remap_apply(send, recv, coef, f, d.n).reshape(d.jm, d.im)
+        assert np.abs(got - want_row[:, None]).max() <= 1e-11, (s.im, s.jm, d.im, d.jm)
+        # and it is a genuine correction: first order alone misses the target by far more -- except S -> A, where every
+        # destination cell is a union of whole source cells and the correction cancels (mean of centroids = centroid)
+        if s is not Sx:
+            t1 = orc.gen_jones99(s, d, 1)
+            got1 = orc.remap_apply(*t1.to_index(s.im, d.im), f, d.n).reshape(d.jm, d.im)
+            assert np.abs(got1 - want_row[:, None]).max() > 1e-4
 
 
 def test_kat3_bilinear_coefficients_by_hand(orc):
