@@ -409,6 +409,120 @@ def test_kat5_neutral_limit_and_no_ice(orc, dccm, S):
     assert np.all(out["SfcTemp"][2][0, :] == -999.0)
 
 
+def _bulk_one_column(u, v, T1, q1, sw, lw, ps, ice, c1, c2, ts, alb, sig1):
+    """One surface column of DSFCM_Util_SfcBulkFlux_Get in scalar Python, written from the equations
+    (ref sfc/DSFCM_Util_SfcBulkFlux_mod.f90:194-415, BulkCoefL82 :478-568; constants :35-58, limits :576-589) --
+    an independent second reading of the routine: physics first, no arrays, no shared code with the C oracle."""
+    karman, Rstar, sigma, g = 0.4, 8.3144621, 5.670373e-8, 9.8
+    R = Rstar / 1.8e-2                      # dry and wet gas constants coincide (both molar weights 0.018)
+    cp, Lv, Lf, p0, es0, z0 = 1616.0, 2425300.0, 334000.0, 1e5, 611.0, 1e-4
+    kappa = R / cp
+    L = (Lv, Lv + Lf)
+    frac = (1.0 - ice, ice)
+    exner_air, exner_sfc = (ps * sig1 / p0) ** kappa, (ps / p0) ** kappa
+    speed = math.sqrt(u * u + v * v)
+    z = R / g * T1 * (1.0 - sig1)           # EpsV = 1: virtual temperature == temperature; surface height 0
+    neutral = (karman / math.log((z + z0) / z0)) ** 2           # heat roughness == momentum roughness
+    out = {k: [0.0, 0.0, 0.0] for k in ("taux", "tauy", "sh", "evap", "lh", "lwup", "swup", "cv", "ct", "cq")}
+    qsat, Ts4, alb3 = [0.0, 0.0], 0.0, 0.0
+    active = (True, ice > 1e-12)
+    for n in (0, 1):
+        qsat[n] = es0 / ps * math.exp(L[n] / R * (1.0 / 273.0 - 1.0 / ts[n]))
+        ri = g / (ts[n] / exner_sfc) * (T1 / exner_air - ts[n] / exner_sfc) / max(speed, 0.01) ** 2 * z
+        if not active[n]:
+            cm = ch = 0.0
+        elif ri > 0.0:                      # stable (Louis et al. 1982)
+            cm = neutral / (1.0 + 10.0 * ri / math.sqrt(1.0 + 5.0 * ri))
+            ch = neutral / (1.0 + 15.0 * ri * math.sqrt(1.0 + 5.0 * ri))
+        else:                               # unstable
+            root = math.sqrt(-(z + z0) / z0 * ri)
+            cm = neutral * (1.0 - 10.0 * ri / (1.0 + 75.0 * neutral * root))
+            ch = neutral * (1.0 - 15.0 * ri / (1.0 + 75.0 * neutral * root))
+        cm, ch = min(max(cm, 0.0), 1.0), min(max(ch, 0.0), 1.0)
+        rho_v = ps / (R * ts[n]) * min(max(speed, 0.01), 1000.0)
+        out["cv"][n], out["ct"][n], out["cq"][n] = cm * rho_v, ch * rho_v, ch * rho_v
+        if active[n]:
+            out["taux"][n], out["tauy"][n] = -out["cv"][n] * u, -out["cv"][n] * v
+            out["sh"][n] = -cp * exner_sfc * out["ct"][n] * (T1 / exner_air - ts[n] / exner_sfc)
+            out["evap"][n] = -out["cq"][n] * (q1 - qsat[n])
+            out["lh"][n] = L[n] * out["evap"][n]
+            out["lwup"][n] = sigma * ts[n] ** 4
+            out["swup"][n] = alb[n] * sw
+            Ts4 += frac[n] * ts[n] ** 4
+            alb3 += frac[n] * alb[n]
+            for k in out:
+                out[k][2] += frac[n] * out[k][n]
+    # implicit surface-layer update (:357-368) and the flux correction (:370-380)
+    dsh = -cp * exner_sfc * out["ct"][2] / exner_air
+    delta = [(out["taux"][2] + c2[0]) / (c1[0] + out["cv"][2]), (out["tauy"][2] + c2[1]) / (c1[1] + out["cv"][2]),
+             (out["sh"][2] + c2[2]) / (c1[2] - dsh), (out["evap"][2] + c2[3]) / (c1[3] + out["cq"][2])]
+    for n in (0, 1, 2):
+        out["taux"][n] -= out["cv"][n] * delta[0]
+        out["tauy"][n] -= out["cv"][n] * delta[1]
+        out["sh"][n] -= cp * exner_sfc / exner_air * out["ct"][n] * delta[2]
+        out["evap"][n] -= out["cq"][n] * delta[3]
+    for n in (0, 1):
+        out["lh"][n] = L[n] * out["evap"][n]
+    net = {"ns": [0.0, 0.0], "sr": [0.0, 0.0], "dfdt": [0.0, 0.0]}
+    for n in (0, 1):
+        if active[n]:
+            net["ns"][n] = out["lwup"][n] - lw + out["lh"][n] + out["sh"][n]
+            net["sr"][n] = out["swup"][n] - sw
+            net["dfdt"][n] = (4.0 * sigma * ts[n] ** 3 + cp * out["ct"][n]
+                              + L[n] * out["cq"][n] * (L[n] * qsat[n] / (R * ts[n] ** 2)))
+    return out, delta, net, Ts4, alb3
+
+
+@pytest.mark.parametrize("case", ["unstable_open_ocean", "stable_with_ice", "calm_full_ice"])
+def test_bulk_flux_against_an_independent_scalar_restatement(orc, case):
+    """Three hand-picked columns: warm sea under cold air (unstable branch, no ice), cold surfaces under warm air
+    with 40 % ice (stable branch, both surface types, composite), and calm air over full ice cover (wind floors)."""
+    col = {"unstable_open_ocean": dict(u=6.0, v=-3.0, T1=285.0, q1=6e-3, sw=220.0, lw=330.0, ps=1.012e5, ice=0.0,
+                                       ts=(291.0, 271.0), alb=(0.07, 0.6)),
+           "stable_with_ice": dict(u=-2.5, v=1.0, T1=276.0, q1=3e-3, sw=90.0, lw=280.0, ps=0.995e5, ice=0.4,
+                                   ts=(271.6, 262.0), alb=(0.1, 0.65)),
+           "calm_full_ice": dict(u=0.0, v=0.0, T1=255.0, q1=5e-4, sw=10.0, lw=190.0, ps=1.02e5, ice=1.0,
+                                 ts=(271.35, 250.0), alb=(0.1, 0.8))}[case]
+    c1, c2, sig1 = (0.021, 0.019, 0.02 * 1616.0, 0.018), (0.04, -0.03, 12.0, -2e-5), 0.995
+    want, delta, net, Ts4, alb3 = _bulk_one_column(c1=c1, c2=c2, sig1=sig1, **col)
+    full = lambda x: np.full((3, 3), float(x))
+    inp = {"WindU": full(col["u"]), "WindV": full(col["v"]), "SfcAirTemp": full(col["T1"]), "QVap1": full(col["q1"]),
+           "SDwRFlx": full(col["sw"]), "LDwRFlx": full(col["lw"]), "SfcPress": full(col["ps"]), "SIceCon": full(col["ice"]),
+           "ImplCplCoef1": np.stack([full(x) for x in c1]), "ImplCplCoef2": np.stack([full(x) for x in c2]),
+           "SfcTemp": np.stack([full(col["ts"][0]), full(col["ts"][1]), full(0.0)]),
+           "SfcAlbedo": np.stack([full(col["alb"][0]), full(col["alb"][1]), full(0.0)]),
+           "SfcHeight": np.zeros((3, 3)), "Sig1Info": np.array([sig1, 0.01])}
+    got = orc.bulkflux(3, 3, inp)
+    names = {"taux": "WindStressX", "tauy": "WindStressY", "sh": "SenHFlx", "evap": "QVapMFlx", "lh": "LatHFlx",
+             "lwup": "LUwRFlx", "swup": "SUwRFlx", "cv": "SfcVelTransCoef", "ct": "SfcTempTransCoef", "cq": "SfcQVapTransCoef"}
+    close = lambda a, b: abs(a - b) <= 1e-13 * max(abs(a), abs(b), 1e-300)
+    for k, name in names.items():
+        for n in range(3):
+            if k == "lh" and n == 2:
+                continue                                     # reference defect B-1: slot 3 undefined there
+            assert close(got[name][n][1, 1], want[k][n]), (case, name, n, got[name][n][1, 1], want[k][n])
+    for k in range(4):
+        assert close(got["DelVarImplCPL"][k][1, 1], delta[k]), (case, "Del", k)
+    for n in range(2):
+        assert close(got["SfcHFlx_ns"][n][1, 1], net["ns"][n]) and close(got["SfcHFlx_sr"][n][1, 1], net["sr"][n])
+        assert close(got["DSfcHFlxDTs"][n][1, 1], net["dfdt"][n])
+    assert close(got["SfcTemp"][2][1, 1], Ts4) and close(got["SfcAlbedo"][2][1, 1], alb3)
+    # the cases do take the branches they are named after: C_H above / below its neutral value
+    R = 8.3144621 / 0.018
+    neutral = (0.4 / math.log((R / 9.8 * col["T1"] * (1 - sig1) + 1e-4) / 1e-4)) ** 2
+    ch = lambda n: want["ct"][n] / (col["ps"] / (R * col["ts"][n]) * min(max(math.hypot(col["u"], col["v"]), 0.01), 1e3))
+    if case == "unstable_open_ocean":
+        assert ch(0) > neutral
+    elif case == "stable_with_ice":
+        assert 0.0 < ch(0) < neutral and 0.0 < ch(1) < neutral
+    else:
+        assert 0.0 <= ch(1) < neutral and ch(0) > neutral     # ice under warmer air: stable; open water under it: unstable
+    if case == "unstable_open_ocean":
+        assert got["SfcHFlx_ns"][1][1, 1] == 0.0 and want["cv"][1] == 0.0
+    if case == "calm_full_ice":
+        assert want["cv"][1] > 0.0                                     # zero wind: the 0.01 m/s floor keeps the exchange alive
+
+
 def test_bulk_implicit_update_is_consistent(orc, dccm, S):
     """DelVarImplCPL satisfies the reduced surface-layer equation and the corrected composite
     flux equals Coef1*Del - Coef2 (ref :357-380)."""
