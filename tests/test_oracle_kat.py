@@ -157,6 +157,37 @@ def test_kat3b_second_order_term_reproduces_latitude_linear_fields(orc, dccm):
             assert np.abs(got1 - want_row[:, None]).max() > 1e-4
 
 
+def test_kat3c_bilinear_tables_reproduce_bilinear_fields(orc, dccm):
+    """ref common/grid_mapping_util.f90:114-127, :154-165: the four-point weights interpolate f = a + b*lon + c*lat +
+    d*lon*lat exactly (linear extrapolation beyond the last latitude rows included).  At the 2*pi wrap the reference
+    does not unwrap the east neighbour (defect A5-2): its weights there are the straight line through (x_N, x_1) --
+    exact for this non-periodic f, but not convex; lon_mode 1 unwraps, giving convex weights that treat the field as
+    periodic.  Both are pinned: values west of the wrap in both modes, weight ranges at the wrap per mode."""
+    A, O, Sx = [as_orc_grid(orc, g) for g in pair(orc, dccm, "T21_1deg")]
+    f = lambda lon, lat: 1.5 + 0.3 * lon - 0.7 * lat + 0.11 * lon * lat
+    for s, d in [(A, O), (O, A), (Sx, O), (O, Sx)]:
+        src = f(np.tile(s.x_Lon, s.jm), np.repeat(s.y_Lat, s.im))[None, :]
+        want = f(np.tile(d.x_Lon, d.jm), np.repeat(d.y_Lat, d.im)).reshape(d.jm, d.im)
+        west = d.x_Lon <= s.x_Lon[-1]                                # destination columns west of the last source column
+        rows_inside = (d.y_Lat >= s.y_Lat[0]) & (d.y_Lat <= s.y_Lat[-1])
+        for lon_mode in (0, 1):
+            t = orc.gen_bilinear(s, d, lon_mode=lon_mode)
+            send, recv, coef = t.to_index(s.im, d.im)
+            got = orc.remap_apply(send, recv, coef, src, d.n).reshape(d.jm, d.im)
+            assert np.abs(got - want)[:, west].max() <= 1e-12, (s.im, d.im, lon_mode)
+            rows = np.zeros(d.n); np.add.at(rows, recv - 1, coef)
+            assert np.abs(rows - 1.0).max() <= 1e-13
+            cmin = np.full(d.n, np.inf); np.minimum.at(cmin, recv - 1, coef)
+            cmin = cmin.reshape(d.jm, d.im)[rows_inside]
+            assert cmin[:, west].min() >= -1e-15                     # inside the source box: convex weights
+            if (~west).any():
+                if lon_mode == 1:
+                    assert cmin[:, ~west].min() >= -1e-15
+                else:
+                    assert cmin[:, ~west].min() < -1e-3              # A5-2, reproduced verbatim
+                    assert np.abs(got - want)[:, ~west].max() <= 1e-12
+
+
 def test_kat3_bilinear_coefficients_by_hand(orc):
     """coef = (a2*b2, a1*b2, a1*b1, a2*b1) on (is,js), (is+1,js), (is+1,js+1), (is,js+1)
     (ref common/grid_mapping_util.f90:120-123,154-165; same in common/cal_mappingtable.f90:66-74)."""
