@@ -367,6 +367,56 @@ def test_kat4_split_solve_equals_monolithic(orc, dccm, S):
     assert worst <= 1e-12
 
 
+def test_kat4b_temperature_and_vapour_systems_equal_monolithic(orc, dccm, S):
+    """KAT-4 for the other two systems: temperature (Cp * Exner-ratio weighted, ref
+    atm/dcpam_sfc_implicit_coupling_mod.f90:237-261) and the water-vapour tracer picked by IndexH2OVap (:265-293,
+    :316, :371-374; here tracer 2 of 2), each against ONE dense solve with the surface coefficient on row 1."""
+    g = dccm.tables.get_LonLatGrid(8, 4)
+    K, nc, iq = 12, 2, 2
+    inp = S.column_inputs(np, g, K, nc)
+    vd = orc.VDiff(g.im, g.jm, K, nc, iq, S.GRAV, S.CPDRY, S.GASRDRY, S.DELTIME)
+    out = vd.forward(inp)
+    ncol = g.n
+    idx = np.arange(ncol, dtype=np.float64)
+    Csfc = {"T": S.CPDRY * (0.01 + 0.02 * S.unit(np, idx, 9.0)), "q": 0.01 + 0.02 * S.unit(np, idx, 19.0)}
+    Fsfc = {"T": 15.0 * S.normal(np, idx, 11.0), "q": 2e-5 * S.normal(np, idx, 21.0)}
+    DT, DQ = out["DTempDt"].copy(), out["DQMixDt"].copy()
+    DT[0] = (Fsfc["T"] + out["ImplCplCoef2"][2]) / (out["ImplCplCoef1"][2] + Csfc["T"])
+    DQ[iq - 1, 0] = (Fsfc["q"] + out["ImplCplCoef2"][3]) / (out["ImplCplCoef1"][3] + Csfc["q"])
+    back = vd.backward(out["DUDt"], out["DVDt"], DT, DQ)
+    xT, xq = back[2] * (2.0 * S.DELTIME), back[3][iq - 1] * (2.0 * S.DELTIME)
+    P, Tv, H = inp["Press"], inp["VirTemp"], inp["Height"]
+    rEx, zEx = inp["rExner"], inp["zExner"]                    # half levels 0..K, full levels 1..K (array row k-1)
+    worst = {"T": 0.0, "q": 0.0}
+    for c in range(ncol):
+        geom = np.zeros(K + 1)
+        for k in range(1, K):
+            geom[k] = P[k, c] / (S.GASRDRY * Tv[k, c]) / (H[k, c] - H[k - 1, c])
+        Tt, Tq = inp["TempDiffCoef"][:, c] * geom, inp["QMixDiffCoef"][:, c] * geom
+        MT, Mq = np.zeros((K, K)), np.zeros((K, K))
+        rT, rq = np.zeros(K), np.zeros(K)
+        for k in range(1, K + 1):
+            mass = -(P[k, c] - P[k - 1, c]) / S.GRAV / (2.0 * S.DELTIME)
+            MT[k - 1, k - 1] = S.CPDRY * mass + S.CPDRY * rEx[k, c] / zEx[k - 1, c] * Tt[k]
+            Mq[k - 1, k - 1] = mass + Tq[k - 1] + Tq[k]
+            if k > 1:
+                MT[k - 1, k - 1] += S.CPDRY * rEx[k - 1, c] / zEx[k - 1, c] * Tt[k - 1]
+                MT[k - 1, k - 2] = -S.CPDRY * rEx[k - 1, c] / zEx[k - 2, c] * Tt[k - 1]
+                Mq[k - 1, k - 2] = -Tq[k - 1]
+            if k < K:
+                MT[k - 1, k] = -S.CPDRY * rEx[k, c] / zEx[k, c] * Tt[k]
+                Mq[k - 1, k] = -Tq[k]
+            rT[k - 1] = -(inp["HeatFlux"][k, c] - inp["HeatFlux"][k - 1, c])
+            rq[k - 1] = -(inp["QMixFlux"][iq - 1, k, c] - inp["QMixFlux"][iq - 1, k - 1, c])
+        MT[0, 0] += Csfc["T"][c]; rT[0] += Fsfc["T"][c]
+        Mq[0, 0] += Csfc["q"][c]; rq[0] += Fsfc["q"][c]
+        x = np.linalg.solve(MT, rT)
+        worst["T"] = max(worst["T"], np.abs(x - xT[:, c]).max() / np.abs(x).max())
+        x = np.linalg.solve(Mq, rq)
+        worst["q"] = max(worst["q"], np.abs(x - xq[:, c]).max() / np.abs(x).max())
+    assert worst["T"] <= 1e-12 and worst["q"] <= 1e-12, worst
+
+
 def test_vdiff_forward_leaves_level1_unswept(orc, dccm, S):
     """Defect C-1 (division by Mtx(k=1,-1) = 0, ref atm/dcpam_sfc_implicit_coupling_mod.f90:393-400):
     the oracle stops the sweep at k = 2; RHS(1) is the flux divergence and equals Coef2 before
