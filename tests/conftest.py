@@ -35,6 +35,5 @@ def gpu(dccm):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     torch.cuda.set_device(0)
-    from ctypes import c_int
     dccm._lib.check(dccm.lib().dccm_init(0))
     return torch.device("cuda:0")
