@@ -27,3 +27,17 @@ except Exception as e:
 PY
   n=$((n*2))
 done
+# BASELINE config 4: T341 <-> 0.25 deg sharded over 2 / 4 GPUs
+for n in 2 4; do
+  [ $n -le $N ] || continue
+  ( timeout -k 5 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29640+n)) \
+      bench.py --gpus $n --steps 20 --warmup 3 --workload T341_0p25deg --no-e2e ) > $OUT/bench_T341_n$n.json 2> $OUT/bench_T341_n$n.err
+  python -c "
+import json
+try:
+    d=[json.loads(l) for l in open('$OUT/bench_T341_n$n.json') if l.startswith('{')][-1]
+    print('T341 N=$n', round(d['value'],1), 'ex/s', round(d['ms_per_step'],3), 'ms')
+except Exception as e:
+    print('T341 N=$n failed', e)
+"
+done
