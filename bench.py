@@ -260,9 +260,17 @@ def run_ours(args, rank, world):
     A, O, S, K, nc, M = make_grids(dccm, wl)
 
     t_setup = time.time()
-    if world > 1:
-        if M > 1:
-            raise SystemExit("ensemble workloads shard by member (replicas): run them with --gpus 1 per member block")
+    member0 = 0
+    by_member = world > 1 and M > 1
+    if by_member:
+        # ensembles shard by member: rank r owns members [r*M/N, (r+1)*M/N), shared tables, no data-path collective
+        if M % world:
+            raise SystemExit(f"--gpus {world} does not divide the {M} ensemble members")
+        M, member0 = M // world, rank * (M // world)
+        ex = exch_mod.SurfaceExchange(A, O, S, K, nc, 1, members=M, fast=not args.reference_order, device=dev)
+        (ja0, ja1), (jo0, jo1) = (0, A.jm), (0, O.jm)
+        halo_mode = "none"
+    elif world > 1:
         sh = importlib.import_module("dennou-ccm_b200.sharding")
         ex, halo_mode = None, args.halo
         if args.halo == "peer":
@@ -280,11 +288,11 @@ def run_ours(args, rank, world):
         ex = exch_mod.SurfaceExchange(A, O, S, K, nc, 1, members=M, fast=not args.reference_order, device=dev)
         (ja0, ja1), (jo0, jo1) = (0, A.jm), (0, O.jm)
     # synthetic inputs, generated on the device (pure functions of the global cell index)
-    col = [syn.column_inputs(torch, A, K, nc, ja0, ja1, dev=dev, member=m) for m in range(M)]
+    col = [syn.column_inputs(torch, A, K, nc, ja0, ja1, dev=dev, member=member0 + m) for m in range(M)]
     col_in = {k: torch.cat([c[k] for c in col], dim=-1).contiguous() for k in col[0]}
     del col
-    atm = [syn.atm_surface_fields(torch, A, ja0, ja1, dev=dev, member=m) for m in range(M)]
-    ocn = [syn.ocn_surface_fields(torch, O, jo0, jo1, dev=dev, member=m) for m in range(M)]
+    atm = [syn.atm_surface_fields(torch, A, ja0, ja1, dev=dev, member=member0 + m) for m in range(M)]
+    ocn = [syn.ocn_surface_fields(torch, O, jo0, jo1, dev=dev, member=member0 + m) for m in range(M)]
     atm_sfc = {k: torch.stack([a[k] for a in atm]) for k in atm[0]}
     ocn_sfc = {k: torch.stack([o[k] for o in ocn]) for k in ocn[0]}
     ex.set_inputs(col_in, atm_sfc, ocn_sfc)
@@ -398,14 +406,15 @@ def run_ours(args, rank, world):
         "metric": "coupling exchanges/sec", "value": value, "unit": "exchanges/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl, "description": DESCR[wl], "columns_atm": A.n * M, "cells_sfc": S.n * M,
-                   "cells_ocn": O.n * M, "kmax": K, "ncmax": nc, "remapped_layers": 43,
+        "config": {"workload": wl, "description": DESCR[wl], "columns_atm": A.n * M * (world if by_member else 1),
+                   "cells_sfc": S.n * M * (world if by_member else 1), "cells_ocn": O.n * M * (world if by_member else 1),
+                   "kmax": K, "ncmax": nc, "remapped_layers": 43,
                    "l2": l2_note,
                    "mode": "reference-order" if args.reference_order else "fast (shared reciprocals)",
                    "surface_step": "unfused (4 remaps + bulk + pack)" if args.unfused else "fused (one kernel)",
                    "launch": "one CUDA graph per exchange" if graph is not None else "eager launches",
                    "setup_s": round(t_setup, 1)},
-        "remapped_cell_fields_per_s": ex.remapped_cell_fields() * value,
+        "remapped_cell_fields_per_s": ex.remapped_cell_fields() * value * (world if by_member else 1),
         "exchange_algorithmic_gbytes": bytes_alg[total_key] / 1e9,
         "exchange_hbm_gbs": bytes_alg[total_key] / (ms * 1e-3) / 1e9,
         "exchange_frac_of_peak": bytes_alg[total_key] / (ms * 1e-3) / 1e9 / (peak * world),   # per GPU
@@ -418,7 +427,13 @@ def run_ours(args, rank, world):
                      "algorithmic_bytes_per_launch": bytes_alg["fwd"]},
         "clocks": clocks, "gpu_launches": launches,
     }
-    if world > 1:
+    if by_member:
+        line["config"]["sharding"] = f"{world} member blocks of {M} (replicas of the tables, no data-path collective)"
+        line["roofline"]["note"] = "per-rank kernel on rank 0's member block"
+        line["roofline"]["achieved"] = ex.algorithmic_bytes()["fwd"] / (part_ms["fwd"] * 1e-3) / 1e9
+        line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
+        line["roofline"]["algorithmic_bytes_per_launch"] = ex.algorithmic_bytes()["fwd"]
+    elif world > 1:
         how = ("read in place from the neighbours' buffers over NVLink peer memory inside the surface / remap kernels, "
                "2 device barriers per exchange" if halo_mode == "peer" else "packed NCCL send/recv, one message per neighbour")
         line["config"]["sharding"] = (f"{world} latitude bands (row blocks); halo rows {how}; "

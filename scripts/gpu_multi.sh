@@ -41,3 +41,7 @@ except Exception as e:
     print('T341 N=$n failed', e)
 "
 done
+# BASELINE config 2 across GPUs: the 64-member ensemble sharded by member (replicas of the tables, no collective)
+( timeout -k 5 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29660 \
+    bench.py --gpus $N --steps 20 --warmup 3 --workload T42x64 --no-e2e ) > $OUT/bench_T42x64_n$N.json 2> $OUT/bench_T42x64_n$N.err
+cut -c1-400 $OUT/bench_T42x64_n$N.json
