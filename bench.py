@@ -282,6 +282,7 @@ def run_ours(args, rank, world):
                 halo_mode = "nccl"
         if ex is None:
             ex = sh.ShardedExchange(A, O, S, K, nc, 1, rank=rank, world=world, dist=dist,
+                                    halo="allgather" if halo_mode == "allgather" else "sendrecv",
                                     fast=not args.reference_order, device=dev)
         (ja0, ja1), (jo0, jo1) = ex.plan.bands["A"][rank], ex.plan.bands["O"][rank]
     else:
@@ -435,7 +436,9 @@ def run_ours(args, rank, world):
         line["roofline"]["algorithmic_bytes_per_launch"] = ex.algorithmic_bytes()["fwd"]
     elif world > 1:
         how = ("read in place from the neighbours' buffers over NVLink peer memory inside the surface / remap kernels, "
-               "2 device barriers per exchange" if halo_mode == "peer" else "packed NCCL send/recv, one message per neighbour")
+               "2 device barriers per exchange" if halo_mode == "peer" else
+               "one NCCL all-gather of every rank's boundary rows per phase" if halo_mode == "allgather" else
+               "packed NCCL send/recv, one message per neighbour")
         line["config"]["sharding"] = (f"{world} latitude bands (row blocks); halo rows {how}; "
                                       f"{ex.plan.halo_bytes(rank, {'A': 17, 'O': 5, 'S': 21})} B of halo on rank {rank} per exchange")
         line["roofline"]["note"] = "per-rank kernel on rank 0's band; achieved = rank-0 bytes / rank-0 time"
@@ -664,7 +667,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e with one monolithic H2D / D2H instead of slab pipelining")
     ap.add_argument("--no-dropin", action="store_true", help="skip the reference-interface-only e2e leg")
-    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"], help="multi-GPU halo: peer-memory reads or NCCL send/recv")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl", "allgather"],
+                    help="multi-GPU halo: peer-memory reads, NCCL send/recv, or one NCCL all-gather of the boundary rows")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of as a CUDA graph")
     ap.add_argument("--unfused", action="store_true", help="surface step as 4 remaps + bulk flux + pack")
     ap.add_argument("--reference-order", action="store_true", help="bit-exact column solves (IEEE divisions)")

@@ -204,24 +204,82 @@ class HaloExchanger:
                     buf[:, c0:c1] = stage[o:o + buf.shape[0] * (c1 - c0)].view(buf.shape[0], c1 - c0)
 
 
-def exchange_halo(bufs_msgs, rank, dist):
-    """one-shot form of HaloExchanger (tests)"""
-    HaloExchanger(bufs_msgs, dist)()
+class AllGatherHalo(HaloExchanger):
+    """The same halo rows moved by ONE all-gather per phase (the collective north_star names: "NCCL-over-NVLink
+    allgather of the source field halo each coupling interval").  Every rank contributes one fixed-size block
+    [rows for its lower neighbour | rows for its upper neighbour] -- the boundary rows of all layers of all buffers,
+    a few MB at most, never the fields -- and picks its two neighbours' segments out of the gathered blocks.
+    Slot sizes are the maxima over the ranks (one MAX all-reduce at construction; unused tails travel as padding)."""
+
+    def __init__(self, bufs_msgs, dist, rank, world):
+        super().__init__(bufs_msgs, None)
+        self.dist, self.rank, self.world = dist, rank, world
+        torch = __import__("torch")
+        size = {"lo": 0, "hi": 0}
+        for peer, kind, stage, parts in self.items:
+            if kind == "send":
+                size["lo" if peer < rank else "hi"] = stage.numel()
+        like = bufs_msgs[0][0]               # every rank takes part in the collective, with or without rows of its own
+        t = torch.tensor([size["lo"], size["hi"]], dtype=torch.int64, device=like.device)
+        if dist is not None and world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        self.n_lo, self.n_hi = int(t[0]), int(t[1])
+        n = self.n_lo + self.n_hi
+        if n > 0:
+            self.block = like.new_zeros(n)
+            self.gathered = like.new_empty(world * n)
+        else:                                # no rank has halo rows for these buffers: nothing to do anywhere
+            self.block = self.gathered = None
+
+    def __call__(self):
+        if self.block is None:
+            return
+        n = self.n_lo + self.n_hi
+        for peer, kind, stage, parts in self.items:
+            if kind == "send":
+                base = 0 if peer < self.rank else self.n_lo
+                for buf, c0, c1, o in parts:
+                    m = buf.shape[0] * (c1 - c0)
+                    self.block[base + o:base + o + m].view(buf.shape[0], c1 - c0).copy_(buf[:, c0:c1])
+        self.dist.all_gather_into_tensor(self.gathered, self.block)
+        for peer, kind, stage, parts in self.items:
+            if kind == "recv":
+                # what the lower neighbour sent upwards sits in the "hi" slot of its block, and vice versa
+                base = peer * n + (self.n_lo if peer < self.rank else 0)
+                for buf, c0, c1, o in parts:
+                    m = buf.shape[0] * (c1 - c0)
+                    buf[:, c0:c1] = self.gathered[base + o:base + o + m].view(buf.shape[0], c1 - c0)
+
+
+def exchange_halo(bufs_msgs, rank, dist, mode="sendrecv", world=None):
+    """one-shot form of HaloExchanger / AllGatherHalo (tests)"""
+    if mode == "allgather":
+        AllGatherHalo(bufs_msgs, dist, rank, world)()
+    else:
+        HaloExchanger(bufs_msgs, dist)()
 
 
 class ShardedExchange(SurfaceExchange):
     """SurfaceExchange on rank `rank` of `world`: local bands + halo exchange around the surface step."""
 
-    def __init__(self, A, O, S, kmax, ncmax=1, index_h2ovap=1, rank=0, world=1, plan=None, dist=None, **kw):
+    def __init__(self, A, O, S, kmax, ncmax=1, index_h2ovap=1, rank=0, world=1, plan=None, dist=None,
+                 halo="sendrecv", **kw):
+        """halo: "sendrecv" = grouped NCCL send/recv with the two neighbours, "allgather" = one all-gather of every
+        rank's boundary rows per phase (AllGatherHalo)"""
         self.plan = plan or BandPlan(A, O, S, world)
         self.rank, self.world, self.dist = rank, world, dist
         lA, lO, lS = self.plan.local_grids(rank)
         super().__init__(lA, lO, lS, kmax, ncmax, index_h2ovap, tabs=self.plan.local_tables(rank),
                          layout=self.plan.layout(rank), **kw)
         mA, mO, mS = (self.plan.halo_messages(g, rank) for g in ("A", "O", "S"))
-        self.halo_in = HaloExchanger([(self.a2s_bil, mA), (self.a2s_cons, mA),
-                                      (self.o2s_bil, mO), (self.o2s_cons, mO)], dist)
-        self.halo_out = HaloExchanger([(self.s2a, mS), (self.s2o, mS)], dist)
+        bufs_in = [(self.a2s_bil, mA), (self.a2s_cons, mA), (self.o2s_bil, mO), (self.o2s_cons, mO)]
+        bufs_out = [(self.s2a, mS), (self.s2o, mS)]
+        if halo == "allgather" and dist is not None:
+            self.halo_in = AllGatherHalo(bufs_in, dist, rank, world)
+            self.halo_out = AllGatherHalo(bufs_out, dist, rank, world)
+        else:
+            self.halo_in = HaloExchanger(bufs_in, dist)
+            self.halo_out = HaloExchanger(bufs_out, dist)
 
     def halo_to_sfc(self):
         if self.world > 1:

@@ -45,3 +45,16 @@ done
 ( timeout -k 5 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29660 \
     bench.py --gpus $N --steps 20 --warmup 3 --workload T42x64 --no-e2e ) > $OUT/bench_T42x64_n$N.json 2> $OUT/bench_T42x64_n$N.err
 cut -c1-400 $OUT/bench_T42x64_n$N.json
+# the other two halo transports at N (default above is the peer-memory halo)
+for h in nccl allgather; do
+  ( timeout -k 5 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29670 \
+      bench.py --gpus $N --steps 10 --warmup 3 --halo $h --no-e2e ) > $OUT/bench_halo_${h}_n$N.json 2> $OUT/bench_halo_${h}_n$N.err
+  python -c "
+import json
+try:
+    d=[json.loads(l) for l in open('$OUT/bench_halo_${h}_n$N.json') if l.startswith('{')][-1]
+    print('halo $h N=$N', round(d['value'],1), 'ex/s')
+except Exception as e:
+    print('halo $h N=$N failed', e)
+"
+done

@@ -17,7 +17,7 @@ from util import as_orc_grid, pair
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _worker(rank, world, port, name, q):
+def _worker(rank, world, port, name, q, mode="sendrecv"):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -46,7 +46,7 @@ def _worker(rank, world, port, name, q):
             j0 = plan.bands[s][rank][0]
             buf = torch.full((D, n_ext), float("nan"), dtype=torch.float64)
             buf[:, off:off + n_own] = torch.from_numpy(x[:, j0 * gs.im:j0 * gs.im + n_own])
-            sh.exchange_halo([(buf, plan.halo_messages(s, rank))], rank, dist)
+            sh.exchange_halo([(buf, plan.halo_messages(s, rank))], rank, dist, mode=mode, world=world)
             assert not torch.isnan(buf).any(), f"{key}: halo cells left unfilled"
             d0 = plan.bands[d][rank][0] * gd.im
             got = orc.remap_apply(*ltabs[key], buf.numpy(), lay[d][0])
@@ -58,12 +58,17 @@ def _worker(rank, world, port, name, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,world", [("T21_1deg", 2), ("T42_T42", 2), ("T106_1deg", 3), ("T21_Pl42", 2)])
-def test_sharded_remap_equals_global_gloo(name, world):
+@pytest.mark.parametrize("name,world,mode", [("T21_1deg", 2, "sendrecv"), ("T42_T42", 2, "sendrecv"),
+                                             ("T106_1deg", 3, "sendrecv"), ("T21_Pl42", 2, "sendrecv"),
+                                             ("T21_1deg", 2, "allgather"), ("T106_1deg", 3, "allgather"),
+                                             ("T106_1deg", 4, "allgather")])
+def test_sharded_remap_equals_global_gloo(name, world, mode):
+    """mode "sendrecv": grouped send / receive with the two neighbours; "allgather": every rank's boundary rows in
+    one all-gather (the collective north_star names), middle ranks picking both neighbours' segments."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() + hash(name)) % 2000
-    procs = [ctx.Process(target=_worker, args=(r, world, port, name, q)) for r in range(world)]
+    port = 29500 + (os.getpid() + hash(name + mode) + world) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
