@@ -8,7 +8,11 @@ nvidia-smi topo -m > $OUT/topo.txt 2>&1
     tests/sharded_gpu_check.py T106_1deg ) > $OUT/check_T106.log 2>&1; echo "check T106 exit $?" | tee -a $OUT/check_T106.log
 ( timeout -k 5 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29612 \
     tests/sharded_gpu_check.py T341_0p25deg ) > $OUT/check_T341.log 2>&1; echo "check T341 exit $?" | tee -a $OUT/check_T341.log
-grep "rank" $OUT/check_T106.log $OUT/check_T341.log | head -20
+for h in nccl allgather; do
+( DCCM_HALO=$h timeout -k 5 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29613 \
+    tests/sharded_gpu_check.py T106_1deg ) > $OUT/check_T106_$h.log 2>&1; echo "check T106 halo=$h exit $?" | tee -a $OUT/check_T106_$h.log
+done
+grep "rank" $OUT/check_T106*.log $OUT/check_T341.log | head -40
 n=${3:-1}
 while [ $n -le $N ]; do
   if [ $n -eq 1 ]; then

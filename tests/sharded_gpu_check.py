@@ -31,8 +31,10 @@ def main():
                     {k: v[None] for k, v in syn.atm_surface_fields(torch, A, dev=dev).items()},
                     {k: v[None] for k, v in syn.ocn_surface_fields(torch, O, dev=dev).items()})
     full.step()
-    cls = sh.PeerShardedExchange if os.environ.get("DCCM_HALO", "peer") == "peer" else sh.ShardedExchange
-    ex = cls(A, O, S, K, nc, 1, rank=rank, world=world, dist=dist, device=dev)
+    halo = os.environ.get("DCCM_HALO", "peer")           # peer | nccl | allgather
+    cls = sh.PeerShardedExchange if halo == "peer" else sh.ShardedExchange
+    kw = {"halo": "allgather"} if halo == "allgather" else {}
+    ex = cls(A, O, S, K, nc, 1, rank=rank, world=world, dist=dist, device=dev, **kw)
     (a0, a1), (o0, o1) = ex.plan.bands["A"][rank], ex.plan.bands["O"][rank]
     ex.set_inputs(syn.column_inputs(torch, A, K, nc, a0, a1, dev=dev),
                   {k: v[None] for k, v in syn.atm_surface_fields(torch, A, a0, a1, dev=dev).items()},
@@ -50,7 +52,7 @@ def main():
     t = torch.tensor([len(bad)], device=dev)
     dist.all_reduce(t)
     form = {1: "staged", 0: "direct"}.get(dccm.lib().dccm_sfc_exchange_last_form(), "?")
-    print(f"rank {rank}/{world} [{cls.__name__}, fused surface kernel: {form}]: bands A{(a0, a1)} O{(o0, o1)} mismatches {bad}", flush=True)
+    print(f"rank {rank}/{world} [{cls.__name__} halo={halo}, fused surface kernel: {form}]: bands A{(a0, a1)} O{(o0, o1)} mismatches {bad}", flush=True)
     dist.destroy_process_group()
     sys.exit(1 if int(t.item()) else 0)
 
