@@ -103,6 +103,55 @@ module dccm_b200_c
        type(c_ptr), intent(out) :: handle
        integer(c_int) :: rc
      end function
+     !> table generators, files and the index arithmetic of set_mappingTable_interpCoef
+     !! (ref common/grid_mapping_util_jones99.f90:35-54, :446-506; common/grid_mapping_util.f90:32-48, :181-241)
+     function dccm_table_gen_jones99(nxs, x_LonS, nys, y_LatS, nxd, x_LonD, nyd, y_LatD, &
+          & y_LatIntWtS, y_LatIntWtD, accuracy_order, lon_mode, table) &
+          & bind(C, name="dccm_table_gen_jones99") result(rc)
+       import
+       integer(c_int), value :: nxs, nys, nxd, nyd, accuracy_order, lon_mode
+       real(c_double), intent(in) :: x_LonS(nxs), y_LatS(nys), x_LonD(nxd), y_LatD(nyd), y_LatIntWtS(nys), y_LatIntWtD(nyd)
+       type(c_ptr), intent(out) :: table
+       integer(c_int) :: rc
+     end function
+     function dccm_table_gen_bilinear(nxs, x_LonS, nys, y_LatS, nxr, x_LonR, nyr, y_LatR, lon_mode, table) &
+          & bind(C, name="dccm_table_gen_bilinear") result(rc)
+       import
+       integer(c_int), value :: nxs, nys, nxr, nyr, lon_mode
+       real(c_double), intent(in) :: x_LonS(nxs), y_LatS(nys), x_LonR(nxr), y_LatR(nyr)
+       type(c_ptr), intent(out) :: table
+       integer(c_int) :: rc
+     end function
+     function dccm_table_write_text(table, filename) bind(C, name="dccm_table_write_text") result(rc)
+       import
+       type(c_ptr), value :: table
+       character(kind=c_char), intent(in) :: filename(*)
+       integer(c_int) :: rc
+     end function
+     function dccm_table_read_text(filename, table) bind(C, name="dccm_table_read_text") result(rc)
+       import
+       character(kind=c_char), intent(in) :: filename(*)
+       type(c_ptr), intent(out) :: table
+       integer(c_int) :: rc
+     end function
+     function dccm_table_size(table) bind(C, name="dccm_table_size") result(n)
+       import
+       type(c_ptr), value :: table
+       integer(c_int64_t) :: n
+     end function
+     function dccm_table_index(table, gnxs, gnxr, send_index, recv_index, coef_s) &
+          & bind(C, name="dccm_table_index") result(rc)
+       import
+       type(c_ptr), value :: table
+       integer(c_int), value :: gnxs, gnxr
+       integer(c_int32_t) :: send_index(*), recv_index(*)
+       real(c_double) :: coef_s(*)
+       integer(c_int) :: rc
+     end function
+     subroutine dccm_table_free(table) bind(C, name="dccm_table_free")
+       import
+       type(c_ptr), value :: table
+     end subroutine
   end interface
 
 contains

@@ -10,12 +10,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def c_prototypes():
     text = open(os.path.join(ROOT, "include", "dccm_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
-    protos = {}
+    protos, returns = {}, {}
     for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(dccm_\w+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S):
         name, args = m.group(2), " ".join(m.group(3).split())
         params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
         protos[name] = params
-    return protos
+        returns[name] = " ".join(m.group(1).split())
+    return protos, returns
 
 
 def fortran_interfaces():
@@ -35,14 +36,17 @@ def fortran_interfaces():
         cur = ""
     out, k = {}, 0
     while k < len(joined):
-        m = re.match(r'function\s+(\w+)\s*\(([^)]*)\)\s*bind\(C,\s*name="(\w+)"\)\s*result\((\w+)\)', joined[k], flags=re.I)
+        m = re.match(r'(function|subroutine)\s+(\w+)\s*\(([^)]*)\)\s*bind\(C,\s*name="(\w+)"\)(?:\s*result\((\w+)\))?',
+                     joined[k], flags=re.I)
         if not m:
             k += 1
             continue
-        fname, dummies, cname, res = m.group(1), [d.strip().lower() for d in m.group(2).split(",") if d.strip()], m.group(3), m.group(4).lower()
+        fname, dummies, cname = m.group(2), [d.strip().lower() for d in m.group(3).split(",") if d.strip()], m.group(4)
+        res = m.group(5).lower() if m.group(5) else None         # None: a subroutine, i.e. a void C function
+        assert (m.group(1).lower() == "function") == (res is not None), joined[k]
         decl = {}
         k += 1
-        while not re.match(r"end\s+function", joined[k], flags=re.I):
+        while not re.match(r"end\s+(function|subroutine)", joined[k], flags=re.I):
             for stmt in joined[k].split(";"):
                 if "::" not in stmt:
                     continue
@@ -54,17 +58,23 @@ def fortran_interfaces():
     return out
 
 
-KIND = {"int": "c_int", "int32_t": "c_int32_t", "int64_t": "c_int64_t", "double": "c_double"}
+KIND = {"int": "c_int", "int32_t": "c_int32_t", "int64_t": "c_int64_t", "double": "c_double", "char": "c_char"}
 
 
 def test_every_fortran_interface_matches_its_c_prototype():
-    protos, ifaces = c_prototypes(), fortran_interfaces()
-    assert len(ifaces) >= 12
+    (protos, returns), ifaces = c_prototypes(), fortran_interfaces()
+    assert len(ifaces) >= 19
     for cname, (fname, dummies, decl, res) in ifaces.items():
         assert fname == cname and cname in protos, f"{cname}: not declared in include/dccm_b200.h"
         params = protos[cname]
         assert len(params) == len(dummies), f"{cname}: {len(dummies)} Fortran dummies vs {len(params)} C parameters"
-        assert res in decl, f"{cname}: result variable undeclared"
+        ret = returns[cname].replace("const", "").strip()
+        if res is None:
+            assert ret == "void", f"{cname}: a subroutine binds a C function returning '{ret}'"
+        else:
+            assert res in decl, f"{cname}: result variable undeclared"
+            want = "type(c_ptr)" if "*" in ret else KIND[ret]
+            assert want in decl[res][0], f"{cname}: result declared '{decl[res][0]}' for C return type '{ret}'"
         for p, d in zip(params, dummies):
             assert d in decl, f"{cname}: dummy {d} has no declaration"
             spec, is_array = decl[d]
@@ -86,6 +96,7 @@ def test_every_fortran_interface_matches_its_c_prototype():
 def test_shims_only_call_declared_interfaces():
     """every dccm_* name the shim sources call is declared in the interface module (and hence in the header)"""
     ifaces = set(fortran_interfaces()) | {"dccm_check", "dccm_b200_c"}
+    assert {"grid_mapping_util.f90", "grid_mapping_util_jones99.f90"} <= set(os.listdir(os.path.join(ROOT, "fortran")))
     for f in os.listdir(os.path.join(ROOT, "fortran")):
         text = open(os.path.join(ROOT, "fortran", f)).read()
         text = "\n".join(l.split("!")[0] for l in text.splitlines())
