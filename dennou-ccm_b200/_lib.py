@@ -160,6 +160,8 @@ _SIGS = {
     "dccm_avg_accumulate_device": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp]),
     "dccm_avg_finish_device": (C.c_int, [vp, C.c_int64, C.c_int, vp]),
     "dccm_atm_get_assemble_device": (C.c_int, [C.c_int64, vp, C.c_int64, C.c_double, vp, vp, vp, vp, vp]),
+    "dccm_atm_legacy_get_assemble_device": (C.c_int, [C.c_int64, vp, C.c_int64, C.c_double, C.c_double, C.c_double,
+                                                      vp, vp, vp, vp, vp, vp, vp]),
     "dccm_atm_store_surf_flx_device": (C.c_int, [C.c_int64, C.POINTER(AtmSfcFlx), C.c_double, C.c_double, C.c_double, vp]),
     "dccm_vdiff_create": (C.c_int, [C.c_int] * 5 + [C.c_double] * 4 + [C.POINTER(vp)]),
     "dccm_vdiff_destroy": (None, [vp]),

@@ -56,7 +56,42 @@ atm_get_kernel(int64_t n, const double *__restrict__ a_recv, int64_t ld, double 
     if (SurfHeatFlux) SurfHeatFlux[c] = a_recv[c + 2 * ld];                                          // :825
     if (SurfH2OVapFlux) SurfH2OVapFlux[c] = a_recv[c + 3 * ld];                                      // :826, :836
 }
+
+// Legacy 2-component mode, atmosphere get side (ref atm/mod_atm.f90:740-775, atm/dcpam_main_mod.f90:1003-1031): the four
+// remapped O->A layers (SfcTemp**4, SfcAlbedo, SfcEngyFlxMod | SfcSnow) become the AGCM's surface temperature (fourth
+// root), albedo, snow (x 1e3) and a correction of the lowest-level temperature by the ocean's energy-flux residual
+// accumulated over the coupling cycle.
+__global__ void __launch_bounds__(kThreads)
+atm_legacy_get_kernel(int64_t n, const double *__restrict__ r, int64_t ld, double cycle_sec, double Grav, double CpDry,
+                      const double *__restrict__ Press0, const double *__restrict__ Press1,
+                      double *__restrict__ SurfTemp, double *__restrict__ SurfAlbedo, double *__restrict__ SurfSnow,
+                      double *__restrict__ TempB1)
+{
+    const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= n) return;
+    SurfTemp[c] = pow(r[c], 0.25);                                                                   // mod_atm.f90:743
+    SurfAlbedo[c] = r[c + ld];                                                                       // :745-746, dcpam_main_mod.f90:1017
+    SurfSnow[c] = 1e3 * r[c + 3 * ld];                                                               // mod_atm.f90:772
+    const double mod = r[c + 2 * ld] * cycle_sec;                                                    // :773
+    TempB1[c] = TempB1[c] + (mod - 0.0) / (Press0[c] - Press1[c]) * Grav / CpDry;                    // dcpam_main_mod.f90:1026-1028
+}
 }  // namespace
+
+extern "C" int dccm_atm_legacy_get_assemble_device(int64_t n, const double *o2a_recv, int64_t ld, double cycle_sec,
+                                                   double Grav, double CpDry, const double *Press0, const double *Press1,
+                                                   double *SurfTemp, double *SurfAlbedo, double *SurfSnow, double *TempB1,
+                                                   void *stream)
+{
+    if (!o2a_recv || !Press0 || !Press1 || !SurfTemp || !SurfAlbedo || !SurfSnow || !TempB1)
+        return fail(DCCM_ERR_ARG, "dccm_atm_legacy_get_assemble: null buffer");
+    if (n < 1 || ld < n) return fail(DCCM_ERR_ARG, "dccm_atm_legacy_get_assemble: need 1 <= n <= ld");
+    int rc = ensure_device();
+    if (rc) return rc;
+    atm_legacy_get_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        n, o2a_recv, ld, cycle_sec, Grav, CpDry, Press0, Press1, SurfTemp, SurfAlbedo, SurfSnow, TempB1);
+    DCCM_CUDA_TRY(cudaGetLastError());
+    return DCCM_OK;
+}
 
 extern "C" int dccm_atm_get_assemble_device(int64_t n, const double *a_recv, int64_t ld, double StB, double *SfcTemp,
                                             double *SfcAlbedo, double *SurfHeatFlux, double *SurfH2OVapFlux, void *stream)

@@ -374,6 +374,16 @@ int dccm_atm_store_surf_flx_device(int64_t n, const dccm_atm_sfcflx *f, double L
 int dccm_atm_get_assemble_device(int64_t n, const double *a_recv, int64_t ld, double StB, double *SfcTemp,
                                  double *SfcAlbedo, double *SurfHeatFlux, double *SurfH2OVapFlux, void *stream);
 
+/* Legacy 2-component mode, atmosphere get side (ref atm/mod_atm.f90:740-775 + dcpam_UpdateSurfaceProperties,
+ * atm/dcpam_main_mod.f90:1003-1031): o2a_recv = the 4 remapped O->A layers (SfcTemp**4, SfcAlbedo, SfcEngyFlxMod |
+ * SfcSnow; row length ld).  SurfTemp = recv**0.25, SurfAlbedo = recv, SurfSnow = 1e3*recv, and level 1 of the
+ * temperature (TempB1, in place) += SfcEngyFlxMod*cycle_sec / (Press0 - Press1) * Grav / CpDry, Press0 / Press1 being
+ * xyr_Press at half levels 0 and 1 (DCPAM's AuxVars, external). */
+int dccm_atm_legacy_get_assemble_device(int64_t n, const double *o2a_recv, int64_t ld, double cycle_sec,
+                                        double Grav, double CpDry, const double *Press0, const double *Press1,
+                                        double *SurfTemp, double *SurfAlbedo, double *SurfSnow, double *TempB1,
+                                        void *stream);
+
 #ifdef __cplusplus
 }
 #endif

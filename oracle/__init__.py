@@ -67,6 +67,8 @@ def lib():
         L.orc_atm_store_surf_flx.argtypes = [C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                              C.c_double, C.c_double, C.c_double]
         L.orc_atm_sfc_temp.argtypes = [C.c_int64, _f64p, C.c_double, _f64p]
+        L.orc_atm_legacy_get.argtypes = [C.c_int64, _f64p, _f64p, _f64p, C.c_double, C.c_double, C.c_double,
+                                         _f64p, _f64p, _f64p, _f64p, _f64p]
         L.orc_num_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -301,6 +303,15 @@ def atm_sfc_temp(LUwRFlx, StB=5.670373e-8):
     out = np.empty_like(x)
     lib().orc_atm_sfc_temp(x.size, x, StB, out)
     return out
+
+
+def atm_legacy_get(SfcTemp4, SfcSnow, SfcEngyFlxMod, cycle_sec, Grav, CpDry, Press0, Press1, TempB1):
+    """ref atm/mod_atm.f90:743, :772-773; atm/dcpam_main_mod.f90:1026-1028.  Returns (SurfTemp, SurfSnow, TempB1 corrected)."""
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    n = f(SfcTemp4).size
+    st, sn, tb = np.empty(n), np.empty(n), f(TempB1).copy()
+    lib().orc_atm_legacy_get(n, f(SfcTemp4), f(SfcSnow), f(SfcEngyFlxMod), cycle_sec, Grav, CpDry, f(Press0), f(Press1), st, sn, tb)
+    return st, sn, tb
 
 
 def time_average(puts):

@@ -1099,3 +1099,17 @@ void orc_atm_sfc_temp(int64_t n, const double *LUwRFlx, double StB, double *SfcT
     for (int64_t c = 0; c < n; c++) SfcTemp[c] = pow(LUwRFlx[c] / StB, 0.25);
 }
 
+/* legacy 2-component get side: ref atm/mod_atm.f90:743 (fourth root), :772-773 (snow x 1e3, flux residual x coupling
+ * cycle) and dcpam_UpdateSurfaceProperties, ref atm/dcpam_main_mod.f90:1026-1028 (lowest-level temperature correction) */
+void orc_atm_legacy_get(int64_t n, const double *SfcTemp4, const double *SfcSnow, const double *SfcEngyFlxMod,
+                        double cycle_sec, double Grav, double CpDry, const double *Press0, const double *Press1,
+                        double *SurfTemp, double *SurfSnow, double *TempB1)
+{
+    for (int64_t c = 0; c < n; c++) {
+        SurfTemp[c] = pow(SfcTemp4[c], 0.25);
+        SurfSnow[c] = 1e3 * SfcSnow[c];
+        double recv = SfcEngyFlxMod[c] * cycle_sec;
+        TempB1[c] = TempB1[c] + (recv - 0.0) / (Press0[c] - Press1[c]) * Grav / CpDry;
+    }
+}
+

@@ -123,6 +123,11 @@ void orc_atm_store_surf_flx(int64_t n, const double *const *in, double *const *o
 /* ref atm/dccm_atm_mod.f90:831 */
 void orc_atm_sfc_temp(int64_t n, const double *LUwRFlx, double StB, double *SfcTemp);
 
+/* ref atm/mod_atm.f90:743, :772-773; atm/dcpam_main_mod.f90:1026-1028 */
+void orc_atm_legacy_get(int64_t n, const double *SfcTemp4, const double *SfcSnow, const double *SfcEngyFlxMod,
+                        double cycle_sec, double Grav, double CpDry, const double *Press0, const double *Press1,
+                        double *SurfTemp, double *SurfSnow, double *TempB1);
+
 int orc_num_threads(void);
 void orc_set_num_threads(int n);
 

@@ -692,6 +692,17 @@ def test_atm_radiative_surface_temperature_known_answers(orc):
     assert abs(orc.atm_sfc_temp(np.array([lu3]))[0] - want) <= 1e-12
 
 
+def test_atm_legacy_get_side_known_answers(orc):
+    """ref atm/mod_atm.f90:743, :772-773 and atm/dcpam_main_mod.f90:1026-1028: a residual of 2 W/m2 held over a 14400 s
+    coupling cycle warms a 10 hPa thick lowest layer (mass 1000/9.8 kg/m2, cp 1004) by 2*14400/(1000/9.8*1004) K."""
+    st, sn, tb = orc.atm_legacy_get(np.array([280.0 ** 4, 0.0]), np.array([0.25, 0.0]), np.array([2.0, -1.0]), 14400.0,
+                                    9.8, 1004.0, np.array([1.0e5, 1.0e5]), np.array([0.99e5, 0.98e5]), np.array([285.0, 270.0]))
+    assert abs(st[0] - 280.0) <= 1e-12 and st[1] == 0.0
+    assert sn[0] == 250.0 and sn[1] == 0.0
+    np.testing.assert_allclose(tb, [285.0 + 2.0 * 14400.0 / (1000.0 / 9.8 * 1004.0), 270.0 - 14400.0 / (2000.0 / 9.8 * 1004.0)],
+                               rtol=1e-15)
+
+
 def test_time_average_is_the_mean_of_the_puts(orc):
     rng = np.random.default_rng(3)
     puts = [rng.normal(size=(12, 50)) for _ in range(4)]

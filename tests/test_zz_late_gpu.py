@@ -106,3 +106,24 @@ def test_atm_get_side_assembly(gpu, orc, dccm, S):
     with pytest.raises(dccm.DccmError, match="n <= ld"):
         dccm.dccm_atm_mod.atm_get_assemble(a_recv, ld + 1)
 
+
+def test_atm_legacy_get_side_assembly(gpu, orc, dccm):
+    """legacy 2-component mode (ref atm/mod_atm.f90:740-775, atm/dcpam_main_mod.f90:1003-1031) on the device: fourth
+    root within 1e-15 (device pow vs libm), everything else the oracle's bits; cells beyond n untouched."""
+    import torch
+    n, ld = 64 * 32 + 5, 64 * 32 + 16
+    rng = np.random.default_rng(9)
+    r = np.empty((4, ld))
+    r[0] = (250.0 + 50.0 * rng.random(ld)) ** 4; r[1] = 0.05 + 0.6 * rng.random(ld)
+    r[2] = rng.normal(0.0, 3.0, ld); r[3] = rng.random(ld) * 0.4
+    p0 = 1.0e5 + rng.normal(0.0, 500.0, n); p1 = p0 - (900.0 + 100.0 * rng.random(n))
+    tb = 280.0 + rng.normal(0.0, 5.0, n)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), device=gpu)
+    tb_dev = t(tb)
+    got = dccm.dccm_atm_mod.atm_legacy_get_assemble(t(r), 14400.0, 9.8, 1004.6, t(p0), t(p1), tb_dev, n)
+    st, sn, tb_want = orc.atm_legacy_get(r[0, :n], r[3, :n], r[2, :n], 14400.0, 9.8, 1004.6, p0, p1, tb)
+    np.testing.assert_allclose(got["SurfTemp"].cpu().numpy(), st, rtol=1e-15, atol=0)
+    assert np.array_equal(got["SurfSnow"].cpu().numpy(), sn)
+    assert np.array_equal(got["SurfAlbedo"].cpu().numpy(), r[1, :n])
+    assert np.array_equal(tb_dev.cpu().numpy(), tb_want)
+
