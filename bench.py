@@ -145,6 +145,10 @@ class CpuSample:
         self.vd_r = [oracle.VDiff(b - a, 1, K, nc, 1, syn.GRAV, syn.CPDRY, syn.GASRDRY, syn.DELTIME)
                      for a, b in zip(cut[:-1], cut[1:])]
         del self.vin
+        # the tendency / coefficient arrays exist before the call, as the reference's module arrays do
+        self.vout_r = [{"DUDt": np.zeros((K, b - a)), "DVDt": np.zeros((K, b - a)), "DTempDt": np.zeros((K, b - a)),
+                        "DQMixDt": np.zeros((nc, K, b - a)), "ImplCplCoef1": np.zeros((4, b - a)),
+                        "ImplCplCoef2": np.zeros((4, b - a))} for a, b in zip(cut[:-1], cut[1:])]
         self.parallel_atm = True
         # remap: tables restricted to the destination rows of the band; sources full size
         T = dccm.tables
@@ -165,7 +169,7 @@ class CpuSample:
                 send_i = (send_i - smin).astype(np.int32)
                 nsrc = int(send_i.max())
                 x = rng.standard_normal((D * M, nsrc))
-                self.remaps.append((send_i, recv_i, coef, x, hi - lo))
+                self.remaps.append((send_i, recv_i, coef, x, hi - lo, np.zeros((D * M, hi - lo))))
         # bulk flux on the S band (halo'd arrays as the reference passes them)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from test_oracle_kat import _bulk_inputs
@@ -194,18 +198,18 @@ class CpuSample:
     def run_once(self):
         o = self.orc
         t0 = time.perf_counter()
-        f = self._atm(lambda r: self.vd_r[r].forward(self.vin_r[r]))
+        f = self._atm(lambda r: self.vd_r[r].forward(self.vin_r[r], out=self.vout_r[r]))
         t1 = time.perf_counter()
-        for send_i, recv_i, coef, x, nd in self.remaps[:4]:
-            o.remap_apply(send_i, recv_i, coef, x, nd)
+        for send_i, recv_i, coef, x, nd, y in self.remaps[:4]:
+            o.remap_apply(send_i, recv_i, coef, x, nd, recv=y)
         t2 = time.perf_counter()
         IA, JA, inp = self.bulk
-        o.bulkflux(IA, JA, inp)
+        self.bulk_out = o.bulkflux(IA, JA, inp, out=getattr(self, "bulk_out", None))
         t3 = time.perf_counter()
-        for send_i, recv_i, coef, x, nd in self.remaps[4:]:
-            o.remap_apply(send_i, recv_i, coef, x, nd)
+        for send_i, recv_i, coef, x, nd, y in self.remaps[4:]:
+            o.remap_apply(send_i, recv_i, coef, x, nd, recv=y)
         t4 = time.perf_counter()
-        self._atm(lambda r: self.vd_r[r].backward(f[r]["DUDt"], f[r]["DVDt"], f[r]["DTempDt"], f[r]["DQMixDt"]))
+        self._atm(lambda r: self.vd_r[r].backward(f[r]["DUDt"], f[r]["DVDt"], f[r]["DTempDt"], f[r]["DQMixDt"], inplace=True))
         t5 = time.perf_counter()
         return t5 - t0, {"fwd": t1 - t0, "remap_to_sfc": t2 - t1, "bulk": t3 - t2, "remap_from_sfc": t4 - t3, "bwd": t5 - t4}
 

@@ -176,13 +176,16 @@ def read_table(filename):
     return _take(t)
 
 
-def remap_apply(send_index, recv_index, coef, send, rn1, rn2=None, num_of_data=None):
-    """send: (sn2, sn1) C-order == Fortran send_data(sn1, sn2). Returns recv (rn2, rn1)."""
+def remap_apply(send_index, recv_index, coef, send, rn1, rn2=None, num_of_data=None, recv=None):
+    """send: (sn2, sn1) C-order == Fortran send_data(sn1, sn2). Returns recv (rn2, rn1); `recv` = a caller-owned
+    array to reuse (timing runs), default a fresh NaN-filled one."""
     send = np.ascontiguousarray(send, dtype=np.float64)
     sn2, sn1 = send.shape
     rn2 = sn2 if rn2 is None else rn2
     nd = sn2 if num_of_data is None else num_of_data
-    recv = np.full((rn2, rn1), np.nan)
+    if recv is None:
+        recv = np.full((rn2, rn1), np.nan)
+    assert recv.shape == (rn2, rn1) and recv.dtype == np.float64 and recv.flags["C_CONTIGUOUS"]
     lib().orc_remap_apply(len(coef), np.ascontiguousarray(send_index, np.int32),
                           np.ascontiguousarray(recv_index, np.int32),
                           np.ascontiguousarray(coef, np.float64), send, sn1, sn2, recv, rn1, rn2, nd)
@@ -195,16 +198,21 @@ BULK_OUT3B = ["SUwRFlx", "LUwRFlx", "SfcHFlx_ns", "SfcHFlx_sr", "DSfcHFlxDTs"]
 BULK_IN2 = ["WindU", "WindV", "SfcAirTemp", "QVap1", "SDwRFlx", "LDwRFlx"]
 
 
-def bulkflux(IA, JA, inp, fill=np.nan):
+def bulkflux(IA, JA, inp, fill=np.nan, out=None):
     """inp: dict with (JA,IA) arrays WindU.. and (4,JA,IA) ImplCplCoef1/2, (3,JA,IA) SfcTemp/SfcAlbedo
     (slots 1,2 set), SIceCon, SfcHeight, SfcPress (JA,IA), Sig1Info (2,).
-    Returns dict of outputs (arrays (3|4,JA,IA)); SfcTemp/SfcAlbedo are updated copies."""
-    out = {}
-    for k in BULK_OUT3 + BULK_OUT3B:
-        out[k] = np.full((3, JA, IA), fill)
-    out["DelVarImplCPL"] = np.full((4, JA, IA), fill)
-    out["SfcTemp"] = np.ascontiguousarray(inp["SfcTemp"], dtype=np.float64).copy()
-    out["SfcAlbedo"] = np.ascontiguousarray(inp["SfcAlbedo"], dtype=np.float64).copy()
+    Returns dict of outputs (arrays (3|4,JA,IA)); SfcTemp/SfcAlbedo are updated copies.
+    out: the dict of a previous call to write into again (timing runs: the reference's module arrays exist before the call)."""
+    if out is None:
+        out = {}
+        for k in BULK_OUT3 + BULK_OUT3B:
+            out[k] = np.full((3, JA, IA), fill)
+        out["DelVarImplCPL"] = np.full((4, JA, IA), fill)
+        out["SfcTemp"] = np.ascontiguousarray(inp["SfcTemp"], dtype=np.float64).copy()
+        out["SfcAlbedo"] = np.ascontiguousarray(inp["SfcAlbedo"], dtype=np.float64).copy()
+    else:
+        out["SfcTemp"][:2] = inp["SfcTemp"][:2]
+        out["SfcAlbedo"][:2] = inp["SfcAlbedo"][:2]
     g = lambda k: np.ascontiguousarray(inp[k], dtype=np.float64)
     lib().orc_bulkflux(IA, JA,
                        out["WindStressX"], out["WindStressY"], out["SenHFlx"], out["QVapMFlx"], out["LatHFlx"],
@@ -234,20 +242,26 @@ class VDiff:
             lib().orc_vdiff_free(self.h)
             self.h = None
 
-    def forward(self, inp):
+    def forward(self, inp, out=None):
+        """out: dict of preallocated result arrays to reuse (timing runs: the reference's arrays exist before the
+        call); default = fresh NaN-filled arrays, so that anything left unwritten shows in the tests"""
         imax, jmax, K, nc = self.shape
         ncol = imax * jmax
         g = lambda k: np.ascontiguousarray(inp[k], dtype=np.float64)
-        out = {"DUDt": np.full((K, ncol), np.nan), "DVDt": np.full((K, ncol), np.nan),
-               "DTempDt": np.full((K, ncol), np.nan), "DQMixDt": np.full((nc, K, ncol), np.nan),
-               "ImplCplCoef1": np.full((4, ncol), np.nan), "ImplCplCoef2": np.full((4, ncol), np.nan)}
+        if out is None:
+            out = {"DUDt": np.full((K, ncol), np.nan), "DVDt": np.full((K, ncol), np.nan),
+                   "DTempDt": np.full((K, ncol), np.nan), "DQMixDt": np.full((nc, K, ncol), np.nan),
+                   "ImplCplCoef1": np.full((4, ncol), np.nan), "ImplCplCoef2": np.full((4, ncol), np.nan)}
         lib().orc_vdiff_forward(self.h, *[g(k) for k in VDIFF_IN],
                                 out["DUDt"], out["DVDt"], out["DTempDt"], out["DQMixDt"],
                                 out["ImplCplCoef1"], out["ImplCplCoef2"])
         return out
 
-    def backward(self, DUDt, DVDt, DTempDt, DQMixDt):
-        a = [np.ascontiguousarray(x, dtype=np.float64).copy() for x in (DUDt, DVDt, DTempDt, DQMixDt)]
+    def backward(self, DUDt, DVDt, DTempDt, DQMixDt, inplace=False):
+        """inplace: overwrite the (contiguous float64) arguments as the reference does (timing runs)"""
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in (DUDt, DVDt, DTempDt, DQMixDt)]
+        if not inplace:
+            a = [x.copy() for x in a]
         lib().orc_vdiff_backward(self.h, *a)
         return a
 
