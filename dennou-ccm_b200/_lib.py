@@ -152,6 +152,7 @@ _SIGS = {
                                            C.POINTER(SfcFields), vp]),
     "dccm_sfc_exchange_seg_device": (C.c_int, [vp] * 4 + [C.POINTER(SrcSeg)] * 4 + [C.c_int64, C.c_int64, C.c_int, C.c_double,
                                                vp, vp, C.c_int64, C.POINTER(SfcFields), vp]),
+    "dccm_selftest_pmath_device": (C.c_int, [C.c_int, vp, C.c_int64, C.c_double, vp]),
     "dccm_selftest_fast_arith_device": (C.c_int, [vp, vp, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "dccm_sfc_exchange_config": (C.c_int, [C.c_int, C.c_int]),
     "dccm_sfc_exchange_last_form": (C.c_int, []),

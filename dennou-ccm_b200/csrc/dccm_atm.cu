@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include "dccm_common.h"
+#include "dccm_pmath.cuh"
 
 using namespace dccm;
 
@@ -51,7 +52,7 @@ atm_get_kernel(int64_t n, const double *__restrict__ a_recv, int64_t ld, double 
     const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (c >= n) return;
     // S->A layers (exchange.py S2A_CONS / S2A_BIL): 0 LUwRFlx, 1 SUwRFlx, 2 SenHFlx, 3 QVapMFlx, 4 SfcAlbedo, 5..8 DelVarImplCPL
-    SfcTemp[c] = pow(a_recv[c] / StB, 0.25);                                                         // :831
+    SfcTemp[c] = pfourth_root(a_recv[c] / StB);                                                         // :831
     if (SfcAlbedo) SfcAlbedo[c] = a_recv[c + 4 * ld];                                                // :827
     if (SurfHeatFlux) SurfHeatFlux[c] = a_recv[c + 2 * ld];                                          // :825
     if (SurfH2OVapFlux) SurfH2OVapFlux[c] = a_recv[c + 3 * ld];                                      // :826, :836
@@ -69,7 +70,7 @@ atm_legacy_get_kernel(int64_t n, const double *__restrict__ r, int64_t ld, doubl
 {
     const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (c >= n) return;
-    SurfTemp[c] = pow(r[c], 0.25);                                                                   // mod_atm.f90:743
+    SurfTemp[c] = pfourth_root(r[c]);                                                                   // mod_atm.f90:743
     SurfAlbedo[c] = r[c + ld];                                                                       // :745-746, dcpam_main_mod.f90:1017
     SurfSnow[c] = 1e3 * r[c + 3 * ld];                                                               // mod_atm.f90:772
     const double mod = r[c + 2 * ld] * cycle_sec;                                                    // :773

@@ -84,7 +84,36 @@ __global__ void fast_arith_selftest_kernel(const double *a, const double *b, int
     if (rej) atomicAdd(&counts[1], rej);
 }
 
+// dccm_pmath.cuh element by element, through the product's own arithmetic (FastArith, IEEE redo when rejected)
+__global__ void pmath_selftest_kernel(int which, const double *x, int64_t n, double y, double *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    double r;
+    if (which == 0) r = pexp(v);
+    else if (which == 3) r = pfourth_root(v);
+    else {
+        FastArith f;
+        r = (which == 1) ? plog(v, f) : ppow(v, y, f);
+        if (!f.good()) { IeeeArith g; r = (which == 1) ? plog(v, g) : ppow(v, y, g); }
+    }
+    out[i] = r;
+}
+
 }  // namespace
+
+extern "C" int dccm_selftest_pmath_device(int which, const double *d_x, int64_t n, double y, double *d_out)
+{
+    if (which < 0 || which > 3 || n < 0) return fail(DCCM_ERR_ARG, "dccm_selftest_pmath: bad arguments");
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (n == 0) return DCCM_OK;
+    pmath_selftest_kernel<<<(unsigned)((n + 255) / 256), 256>>>(which, d_x, n, y, d_out);
+    DCCM_CUDA_TRY(cudaGetLastError());
+    DCCM_CUDA_TRY(cudaDeviceSynchronize());
+    return DCCM_OK;
+}
 
 extern "C" int dccm_bulkflux_device(int nx, int ny, int ld, int64_t off, int64_t slot_stride,
                                     const dccm_sfc_fields *f, double sig1, void *stream)

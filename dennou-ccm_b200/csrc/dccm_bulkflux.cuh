@@ -4,11 +4,13 @@
 //
 // Restates DSFCM_Util_SfcBulkFlux_Get + BulkCoefL82 for ONE column
 // (ref sfc/DSFCM_Util_SfcBulkFlux_mod.f90:194-415, :478-568), keeping the reference's
-// operation order (the library is compiled with -fmad=false), so the only differences from
-// the reference arithmetic are the last-ulp differences of exp/log/pow.
+// operation order (the library is compiled with -fmad=false); exp / log / ** are the fixed IEEE
+// sequences of dccm_pmath.cuh (within 1 ulp of any libm, same bits on every machine), so the whole
+// column is reproducible bit for bit by a CPU that follows the same definitions.
 // The reference's ~25 full-grid temporaries (:157-186) and six OpenMP passes collapse into
 // registers: each input is read once and each output written once.
 #pragma once
+#include "dccm_pmath.cuh"
 
 namespace dccm {
 
@@ -159,15 +161,15 @@ __device__ __forceinline__ void bulk_fluxes(const BulkIn &in, double sig1, BulkO
     for (int n = 0; n < 2; n++) {                                                    // :208-213
         if (n == 1 && !ice) continue;
         QVapSat[n] = ar.div(EpsV * Es0, in.SfcPress)
-                   * exp(LatentHeatLocal[n] / GasRWet * (1.0 / 273.0 - ar.rcp(in.SfcTemp[n])));
+                   * pexp(LatentHeatLocal[n] / GasRWet * (1.0 / 273.0 - ar.rcp(in.SfcTemp[n])));
         SfcVirTemp[n] = in.SfcTemp[n] * (1.0 + (((1.0 / EpsV) - 1.0) * QVapSat[n]));
     }
     const double VirTemp = in.SfcAirTemp * (1.0 + (((1.0 / EpsV) - 1.0) * in.QVap1));   // :215
     const double Press1 = in.SfcPress * sig1;                                        // :217
-    // x**kappa as exp(kappa*log(x)): |log x| << 1 here, so the result is within 1 ulp of the
-    // correctly rounded power (as good as pow()) at a fraction of its instruction count.
-    const double Exner = exp((GasRDry / CpDry) * log(ar.div(Press1, RefPress)));            // :218
-    const double SfcExner = exp((GasRDry / CpDry) * log(ar.div(in.SfcPress, RefPress)));    // :219
+    // x**kappa = pexp(kappa*plog(x)): |kappa log x| << 1 here, so the result is within 1 ulp of the
+    // correctly rounded power.
+    const double Exner = ppow(ar.div(Press1, RefPress), GasRDry / CpDry, ar);               // :218
+    const double SfcExner = ppow(ar.div(in.SfcPress, RefPress), GasRDry / CpDry, ar);       // :219
     mid.Exner = Exner; mid.SfcExner = SfcExner;
     const double VelAbs = ar.root(in.WindU * in.WindU + in.WindV * in.WindV);           // :221
     const double Height = in.SfcHeight + GasRDry / Grav * VirTemp * (1.0 - sig1);    // :223-224
@@ -182,8 +184,8 @@ __device__ __forceinline__ void bulk_fluxes(const BulkIn &in, double sig1, BulkO
     // unstable branch: -(x)/z0 == -(x/z0) exactly.
     const double hzm = ar.div(Height - in.SfcHeight + z0m, z0m);
     const double hzh = (z0h == z0m) ? hzm : ar.div(Height - in.SfcHeight + z0h, z0h);
-    const double lgm = log(hzm);
-    const double lgh = (z0h == z0m) ? lgm : log(hzh);
+    const double lgm = plog(hzm, ar);
+    const double lgh = (z0h == z0m) ? lgm : plog(hzh, ar);
     const double tmp = ar.div(FKarm, lgm);                                                 // :250-253
     const double CMn = tmp * tmp;
     const double CHn = tmp * ar.div(FKarm, lgh);                                         // :255-259

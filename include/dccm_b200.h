@@ -242,6 +242,12 @@ int dccm_bulkflux_device(int nx, int ny, int ld, int64_t off, int64_t slot_strid
 int dccm_selftest_fast_arith_device(const double *d_a, const double *d_b, int64_t n,
                                     int64_t *mismatches, int64_t *rejected);
 
+/* The elementary functions of the bulk flux (csrc/dccm_pmath.cuh: exp, log, x**y as fixed sequences of IEEE
+ * binary64 operations -- DESIGN.md section 5), evaluated element-wise on device arrays so a host can check
+ * its own text of the sequences against the device's bit for bit.
+ * which: 0 = exp(x), 1 = log(x), 2 = x**y, 3 = x**0.25 (two square roots). */
+int dccm_selftest_pmath_device(int which, const double *d_x, int64_t n, double y, double *d_out);
+
 /* ------------------------------------------------------------------ fused surface step (K1+K2)
  * The surface component's whole coupling step, get -> bulk flux -> put, in one kernel:
  * replaces jcup_get_data x16 -> interpolate_data -> unpack (ref sfc/dccm_sfc_mod.f90:865-881,

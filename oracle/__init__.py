@@ -18,7 +18,7 @@ _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 
 def build(force=False):
-    src = [os.path.join(_HERE, f) for f in ("dccm_oracle.c", "dccm_oracle.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("dccm_oracle.c", "dccm_oracle.h", "orc_pmath.h", "Makefile")]
     if (not force and os.path.exists(_LIB)
             and os.path.getmtime(_LIB) >= max(os.path.getmtime(s) for s in src)):
         return _LIB
@@ -54,6 +54,10 @@ def lib():
         L.orc_remap_apply.argtypes = [C.c_int64, _i32p, _i32p, _f64p, _f64p, C.c_int, C.c_int,
                                       _f64p, C.c_int, C.c_int, C.c_int]
         L.orc_bulkflux.argtypes = [C.c_int, C.c_int] + [_f64p] * 28
+        L.orc_set_math.argtypes = [C.c_int]
+        L.orc_pm_exp_v.argtypes = [C.c_int64, _f64p, _f64p]
+        L.orc_pm_log_v.argtypes = [C.c_int64, _f64p, _f64p]
+        L.orc_pm_pow_v.argtypes = [C.c_int64, _f64p, C.c_double, _f64p]
         L.orc_vdiff_new.restype = C.c_void_p
         L.orc_vdiff_new.argtypes = [C.c_int] * 5 + [C.c_double] * 4
         L.orc_vdiff_free.argtypes = [C.c_void_p]
@@ -343,3 +347,27 @@ def num_threads():
 
 def set_num_threads(n):
     lib().orc_set_num_threads(int(n))
+
+
+def set_math(portable=True):
+    """exp / log / x**y of the bulk flux: portable fixed IEEE sequences (orc_pmath.h, default) or libm."""
+    lib().orc_set_math(1 if portable else 0)
+
+
+def get_math():
+    return bool(lib().orc_get_math())
+
+
+def pm_exp(x):
+    x = np.ascontiguousarray(x, dtype=np.float64); y = np.empty_like(x)
+    lib().orc_pm_exp_v(x.size, x.reshape(-1), y.reshape(-1)); return y
+
+
+def pm_log(x):
+    x = np.ascontiguousarray(x, dtype=np.float64); y = np.empty_like(x)
+    lib().orc_pm_log_v(x.size, x.reshape(-1), y.reshape(-1)); return y
+
+
+def pm_pow(x, e):
+    x = np.ascontiguousarray(x, dtype=np.float64); y = np.empty_like(x)
+    lib().orc_pm_pow_v(x.size, x.reshape(-1), float(e), y.reshape(-1)); return y

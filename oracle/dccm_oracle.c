@@ -27,6 +27,7 @@
  */
 #define _GNU_SOURCE
 #include "dccm_oracle.h"
+#include "orc_pmath.h"
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -34,6 +35,21 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+
+/* exp / log / x**y of the bulk flux and of the atmosphere's fourth root: 1 (default) = the portable
+ * definitions of orc_pmath.h (fixed IEEE sequences; the CUDA path evaluates the same sequences, so the two
+ * can be compared bit for bit), 0 = the C library's (the reading a Fortran compiler's run-time gives; used
+ * to MEASURE how far the portable definitions are from libm over a whole exchange). */
+static int g_math = 1;
+void orc_set_math(int portable) { g_math = portable ? 1 : 0; }
+int orc_get_math(void) { return g_math; }
+static inline double m_exp(double x) { return g_math ? orc_pm_exp(x) : exp(x); }
+static inline double m_log(double x) { return g_math ? orc_pm_log(x) : log(x); }
+static inline double m_pow(double x, double y) { return g_math ? orc_pm_pow(x, y) : pow(x, y); }
+
+void orc_pm_exp_v(int64_t n, const double *x, double *y) { for (int64_t i = 0; i < n; i++) y[i] = orc_pm_exp(x[i]); }
+void orc_pm_log_v(int64_t n, const double *x, double *y) { for (int64_t i = 0; i < n; i++) y[i] = orc_pm_log(x[i]); }
+void orc_pm_pow_v(int64_t n, const double *x, double e, double *y) { for (int64_t i = 0; i < n; i++) y[i] = orc_pm_pow(x[i], e); }
 
 int orc_num_threads(void)
 {
@@ -654,13 +670,13 @@ void orc_bulkflux(int IA, int JA,
         A3(Frac, c, 1) = SIceCon[c];
         for (int n = 0; n < SPMAX - 1; n++) {
             A3(SfcQVapSat, c, n) = EpsV * Es0 / SfcPress[c]
-                * exp(LatentHeatLocal[n] / GasRWet * (1.0 / 273.0 - 1.0 / A3(SfcTemp, c, n)));
+                * m_exp(LatentHeatLocal[n] / GasRWet * (1.0 / 273.0 - 1.0 / A3(SfcTemp, c, n)));
             A3(SfcVirTemp, c, n) = A3(SfcTemp, c, n) * (1.0 + (((1.0 / EpsV) - 1.0) * A3(SfcQVapSat, c, n)));
         }
         VirTemp[c] = SfcAirTemp[c] * (1.0 + (((1.0 / EpsV) - 1.0) * QVap1[c]));
         Press1[c] = SfcPress[c] * Sig1Info[0];
-        Exner[c] = pow(Press1[c] / RefPress, GasRDry / CpDry_sfc);
-        SfcExner[c] = pow(SfcPress[c] / RefPress, GasRDry / CpDry_sfc);
+        Exner[c] = m_pow(Press1[c] / RefPress, GasRDry / CpDry_sfc);
+        SfcExner[c] = m_pow(SfcPress[c] / RefPress, GasRDry / CpDry_sfc);
         VelAbs[c] = sqrt(WindU[c] * WindU[c] + WindV[c] * WindV[c]);
         Height[c] = SfcHeight[c] + GasRDry / Grav_sfc * VirTemp[c] * (1.0 - Sig1Info[0]);
         A3(WSX, c, 2) = 0.0; A3(WSY, c, 2) = 0.0; A3(SenH, c, 2) = 0.0; A3(LatH, c, 2) = 0.0;
@@ -674,9 +690,9 @@ void orc_bulkflux(int IA, int JA,
         for (int j = JS; j <= JE; j++)                                            /* :247-276 */
         for (int i = IS; i <= IE; i++) {
             size_t c = i + (size_t)IA * j;
-            double tmp = FKarm / log((Height[c] - SfcHeight[c] + A3(z0m, c, n)) / A3(z0m, c, n));
+            double tmp = FKarm / m_log((Height[c] - SfcHeight[c] + A3(z0m, c, n)) / A3(z0m, c, n));
             CMn[c] = tmp * tmp;
-            CHn[c] = tmp * (FKarm / log((Height[c] - SfcHeight[c] + A3(z0h, c, n)) / A3(z0h, c, n)));
+            CHn[c] = tmp * (FKarm / m_log((Height[c] - SfcHeight[c] + A3(z0h, c, n)) / A3(z0h, c, n)));
             double vr = dmax(VelAbs[c], VelMinForRi);
             A3(RiNum, c, n) = Grav_sfc / (A3(SfcVirTemp, c, n) / SfcExner[c])
                 * (VirTemp[c] / Exner[c] - A3(SfcVirTemp, c, n) / SfcExner[c])
@@ -1096,7 +1112,7 @@ void orc_atm_store_surf_flx(int64_t n, const double *const *in, double *const *o
  * atmosphere derives from the remapped composite upward long-wave flux */
 void orc_atm_sfc_temp(int64_t n, const double *LUwRFlx, double StB, double *SfcTemp)
 {
-    for (int64_t c = 0; c < n; c++) SfcTemp[c] = pow(LUwRFlx[c] / StB, 0.25);
+    for (int64_t c = 0; c < n; c++) SfcTemp[c] = m_pow(LUwRFlx[c] / StB, 0.25);
 }
 
 /* legacy 2-component get side: ref atm/mod_atm.f90:743 (fourth root), :772-773 (snow x 1e3, flux residual x coupling
@@ -1106,7 +1122,7 @@ void orc_atm_legacy_get(int64_t n, const double *SfcTemp4, const double *SfcSnow
                         double *SurfTemp, double *SurfSnow, double *TempB1)
 {
     for (int64_t c = 0; c < n; c++) {
-        SurfTemp[c] = pow(SfcTemp4[c], 0.25);
+        SurfTemp[c] = m_pow(SfcTemp4[c], 0.25);
         SurfSnow[c] = 1e3 * SfcSnow[c];
         double recv = SfcEngyFlxMod[c] * cycle_sec;
         TempB1[c] = TempB1[c] + (recv - 0.0) / (Press0[c] - Press1[c]) * Grav / CpDry;

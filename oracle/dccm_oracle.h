@@ -67,6 +67,13 @@ void orc_remap_apply(int64_t nops, const int32_t *send_index, const int32_t *rec
                      const double *coef, const double *send, int sn1, int sn2,
                      double *recv, int rn1, int rn2, int num_of_data);
 
+/* ---- elementary functions of the bulk flux (orc_pmath.h): 1 = portable fixed IEEE sequences (default), 0 = libm ---- */
+void orc_set_math(int portable);
+int  orc_get_math(void);
+void orc_pm_exp_v(int64_t n, const double *x, double *y);
+void orc_pm_log_v(int64_t n, const double *x, double *y);
+void orc_pm_pow_v(int64_t n, const double *x, double e, double *y);
+
 /* ---- bulk flux ---- */
 void orc_bulkflux(int IA, int JA,
     double *xya_WindStressX, double *xya_WindStressY,

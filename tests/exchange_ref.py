@@ -70,8 +70,15 @@ def floor_rel(a, b, frac=1e-3):
     return worst
 
 
-def compare_exchange(ex, ref, members=1, detail=None):
-    """max floored relative error over every stage output of a 1-member SurfaceExchange."""
+def bits_equal(a, b):
+    """same shape and the same 64-bit patterns in every cell (so +0 / -0 and NaN payloads count too)."""
+    a, b = np.ascontiguousarray(a, dtype=np.float64), np.ascontiguousarray(b, dtype=np.float64)
+    return a.size == b.size and np.array_equal(a.reshape(-1).view(np.int64), b.reshape(-1).view(np.int64))
+
+
+def compare_exchange(ex, ref, members=1, detail=None, bitwise=None):
+    """max floored relative error over every stage output of a 1-member SurfaceExchange; `bitwise` (a dict)
+    receives, per stage, whether the device array and the oracle's have identical bits."""
     g = lambda t: t.detach().cpu().numpy()
     M = ex.M
     checks = [("Coef1", g(ex.a2s_bil[5 * M:9 * M]), ref["fwd"]["ImplCplCoef1"]),
@@ -85,6 +92,8 @@ def compare_exchange(ex, ref, members=1, detail=None):
     worst = 0.0
     for name, a, b in checks:
         e = floor_rel(a, b)
+        if bitwise is not None:
+            bitwise[name] = bits_equal(a, b)
         if detail is not None:
             detail[name] = e
         worst = max(worst, e)
