@@ -106,174 +106,455 @@ def make_grids(dccm, wl):
     return A, O, S, K, nc, M
 
 
+def load_synthetic():
+    """dennou-ccm_b200/synthetic.py (pure numpy / torch input generator) WITHOUT importing the package, so the
+    reference arm never loads libdccm_b200.so"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("dccm_synthetic", os.path.join(ROOT, "dennou-ccm_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def loaded_repo_libraries():
+    """shared objects of this repository mapped into the process (the reference arm must show the oracle only)"""
+    try:
+        libs = {l.split()[-1] for l in open("/proc/self/maps") if ".so" in l and ROOT in l}
+        return sorted(os.path.relpath(x, ROOT) for x in libs)
+    except Exception:
+        return None
+
+
+def host_cores():
+    """the cores this process may use -- NOT OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1 to every rank)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def consts_of(syn):
+    return {"Grav": syn.GRAV, "CpDry": syn.CPDRY, "GasRDry": syn.GASRDRY, "DelTime": syn.DELTIME, "Sig1": syn.SIG1}
+
+
 # ------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle on the host cores, bounded latitude-band sample
+# reference arm / cpu_baseline: the oracle on the host cores, bounded latitude-band sample.
+# Grids, tables and the exchange itself come from oracle/ only (oracle/band.py); the product
+# package is not imported on this path.
 # ------------------------------------------------------------------------------------------
 
 class CpuSample:
-    """A latitude band holding `frac` of every grid; one call = the whole exchange on it.
-    750 k atmosphere columns (10 % of config 5) cost 2-4 s of host time per exchange, so warm-up + timed
-    repetitions stay inside the 10-30 s the bounded sample is allowed."""
+    """A latitude band of the workload; one call = the reference's whole exchange on it with the real data flow
+    (oracle/band.BandExchange).  ~750 k atmosphere columns (10 % of config 5) cost about half a second of host time
+    per exchange on 16 cores.  Ensembles: every member is an independent run of the reference, one host thread each."""
 
-    def __init__(self, dccm, wl, target_cols=750_000):
+    def __init__(self, wl, target_cols=750_000, a_rows=None, cores=None, member0=0, col_master=None):
         import oracle
+        from oracle.band import BandExchange, make_grids as orc_grids
         oracle.build()
-        self.orc = oracle
-        syn = importlib.import_module("dennou-ccm_b200.synthetic")
-        self.syn = syn
-        A, O, S, K, nc, M = make_grids(dccm, wl)
-        self.K, self.nc, self.M = K, nc, M
-        rows = max(2, min(A.jm, int(round(target_cols / (A.im * M)))))
-        self.frac = rows / A.jm
-        ja0 = (A.jm - rows) // 2
-        lat0 = (A.y_Lat[ja0] + A.y_Lat[ja0 - 1]) / 2 if ja0 else -np.inf                     # whole grid: every row
-        lat1 = (A.y_Lat[ja0 + rows - 1] + A.y_Lat[ja0 + rows]) / 2 if ja0 + rows < A.jm else np.inf
-        band = lambda g: (int(np.searchsorted(g.y_Lat, lat0)), int(np.searchsorted(g.y_Lat, lat1)))
-        self.bA, self.bS, self.bO = (ja0, ja0 + rows), band(S), band(O)
-        self.grids = (A, O, S)
-        # column-solve inputs of the band (members = extra columns)
-        self.vin = syn.column_inputs(np, A, K, nc, *self.bA)
-        if M > 1:
-            self.vin = {k: np.concatenate([v] * M, axis=-1) for k, v in self.vin.items()}
-        ncolA = (self.bA[1] - self.bA[0]) * A.im * M
-        # The reference's atmosphere is decomposed into latitude bands over MPI ranks (ref atm/dccm_atm_mod.f90:172-176,
-        # :953-1001), one module instance per rank: the column solves run as `ranks` independent column blocks, one per
-        # host core, each a serial instance of the reference loops.  SFC / OCN stay single-rank (ref sfc/dccm_sfc_mod.f90:168-178).
-        self.ranks = max(1, min(oracle.num_threads(), ncolA // 1024 or 1))
-        cut = [ncolA * r // self.ranks for r in range(self.ranks + 1)]
-        self.vin_r = [{k: np.ascontiguousarray(v[..., a:b]) for k, v in self.vin.items()} for a, b in zip(cut[:-1], cut[1:])]
-        self.vd_r = [oracle.VDiff(b - a, 1, K, nc, 1, syn.GRAV, syn.CPDRY, syn.GASRDRY, syn.DELTIME)
-                     for a, b in zip(cut[:-1], cut[1:])]
-        del self.vin
-        # the tendency / coefficient arrays exist before the call, as the reference's module arrays do
-        self.vout_r = [{"DUDt": np.zeros((K, b - a)), "DVDt": np.zeros((K, b - a)), "DTempDt": np.zeros((K, b - a)),
-                        "DQMixDt": np.zeros((nc, K, b - a)), "ImplCplCoef1": np.zeros((4, b - a)),
-                        "ImplCplCoef2": np.zeros((4, b - a))} for a, b in zip(cut[:-1], cut[1:])]
-        self.parallel_atm = True
-        # remap: tables restricted to the destination rows of the band; sources full size
-        T = dccm.tables
-        self.remaps = []
-        spec = [("as", A, S, self.bS, 13, 4), ("os", O, S, self.bS, 2, 3), ("sa", S, A, self.bA, 5, 4), ("so", S, O, self.bO, 2, 10)]
-        rng = np.random.default_rng(1)
-        for key, s, d, (j0, j1), dbil, dcons in spec:
-            for kind, D in (("bil", dbil), ("cons", dcons)):
-                # only the band's destination rows are generated (indices stay global)
-                tab = (T.gen_table_bilinear(s, d, 1, rows=(j0, j1)) if kind == "bil"
-                       else T.gen_table_jones99(s, d, 1, 1, rows=(j0, j1)))
-                send_i, recv_i, coef = tab.index(s.im, d.im)
-                del tab
-                lo, hi = j0 * d.im, j1 * d.im
-                assert recv_i.min() > lo and recv_i.max() <= hi
-                recv_i = (recv_i - lo).astype(np.int32)
-                smin = int(send_i.min()) - 1
-                send_i = (send_i - smin).astype(np.int32)
-                nsrc = int(send_i.max())
-                x = rng.standard_normal((D * M, nsrc))
-                self.remaps.append((send_i, recv_i, coef, x, hi - lo, np.zeros((D * M, hi - lo))))
-        # bulk flux on the S band (halo'd arrays as the reference passes them)
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from test_oracle_kat import _bulk_inputs
-
-        class G:
-            pass
-        g = G()
-        g.im, g.jm = S.im * M, self.bS[1] - self.bS[0]
-        g.x_Lon = np.tile(S.x_Lon, M); g.y_Lat = S.y_Lat[self.bS[0]:self.bS[1]]
-        g.n = g.im * g.jm
-        self.bulk = _bulk_inputs(syn, g)
-
-    def _atm(self, fn):
-        """fn(rank) on every atmosphere rank: concurrently (one thread per rank; the library calls release the GIL and
-        run their own OpenMP regions single-threaded) or one after the other for the one-core figure"""
-        if not self.parallel_atm or self.ranks == 1:
-            return [fn(r) for r in range(self.ranks)]
-        from concurrent.futures import ThreadPoolExecutor
-
-        def work(r):
-            self.orc.set_num_threads(1)
-            return fn(r)
-        with ThreadPoolExecutor(max_workers=self.ranks) as ex:
-            return list(ex.map(work, range(self.ranks)))
+        self.orc, self.syn = oracle, load_synthetic()
+        ima, jma, imo, jmo, reg, K, nc, M = WORKLOADS[wl]
+        self.cores = cores or host_cores()
+        oracle.set_num_threads(self.cores)
+        A, O, S = orc_grids(oracle, ima, jma, imo, jmo, reg)
+        self.grids, self.K, self.nc, self.M = (A, O, S), K, nc, M
+        if a_rows is None:
+            rows = max(2, min(A.jm, int(round(target_cols / (A.im * M)))))
+            ja0 = (A.jm - rows) // 2
+            a_rows = (ja0, ja0 + rows)
+        self.a_rows = a_rows
+        ranks = self.cores if M == 1 else 1
+        self.members = []
+        for m in range(M):
+            bx = BandExchange(oracle, A, O, S, K, nc, a_rows, consts_of(self.syn), ranks=ranks)
+            (ae0, ae1), (oe0, oe1) = bx.input_rows()
+            if col_master is not None:          # full_grid_pass: column inputs of another band of the same width (see there)
+                col = {k: v[..., :bx.nA_ext] for k, v in col_master.items()}
+            else:
+                col = self.syn.column_inputs(np, A, K, nc, ae0, ae1, member=member0 + m)
+            if m == 0:
+                self.col0 = col
+            bx.set_inputs(col,
+                          self.syn.atm_surface_fields(np, A, ae0, ae1, member=member0 + m),
+                          self.syn.ocn_surface_fields(np, O, oe0, oe1, member=member0 + m))
+            self.members.append(bx)
+        self.frac = self.members[0].fraction()
+        self.parallel = True
 
     def run_once(self):
-        o = self.orc
         t0 = time.perf_counter()
-        f = self._atm(lambda r: self.vd_r[r].forward(self.vin_r[r], out=self.vout_r[r]))
-        t1 = time.perf_counter()
-        for send_i, recv_i, coef, x, nd, y in self.remaps[:4]:
-            o.remap_apply(send_i, recv_i, coef, x, nd, recv=y)
-        t2 = time.perf_counter()
-        IA, JA, inp = self.bulk
-        self.bulk_out = o.bulkflux(IA, JA, inp, out=getattr(self, "bulk_out", None))
-        t3 = time.perf_counter()
-        for send_i, recv_i, coef, x, nd, y in self.remaps[4:]:
-            o.remap_apply(send_i, recv_i, coef, x, nd, recv=y)
-        t4 = time.perf_counter()
-        self._atm(lambda r: self.vd_r[r].backward(f[r]["DUDt"], f[r]["DVDt"], f[r]["DTempDt"], f[r]["DQMixDt"], inplace=True))
-        t5 = time.perf_counter()
-        return t5 - t0, {"fwd": t1 - t0, "remap_to_sfc": t2 - t1, "bulk": t3 - t2, "remap_from_sfc": t4 - t3, "bwd": t5 - t4}
+        if len(self.members) == 1:
+            self.members[0].parallel_atm = self.parallel
+            dt, parts = self.members[0].run()
+            return dt, parts
+        if not self.parallel:
+            res = [bx.run() for bx in self.members]
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+
+            def work(bx):
+                self.orc.set_num_threads(1)
+                return bx.run()
+            with ThreadPoolExecutor(max_workers=self.cores) as ex:
+                res = list(ex.map(work, self.members))
+        dt = time.perf_counter() - t0
+        parts = {k: sum(r[1][k] for r in res) / (self.cores if self.parallel else 1) for k in res[0][1]}
+        return dt, parts
+
+    def one_core(self):
+        self.orc.set_num_threads(1)
+        self.parallel = False
+        try:
+            return self.frac / self.run_once()[0]
+        finally:
+            self.orc.set_num_threads(self.cores)
+            self.parallel = True
 
     def describe(self):
         A, O, S = self.grids
-        return (f"latitude band = {self.frac:.4f} of every grid (ATM rows {self.bA[0]}:{self.bA[1]} of {A.jm}, "
-                f"SFC rows {self.bS[0]}:{self.bS[1]} of {S.jm}); time scaled by 1/{self.frac:.4f}")
+        bx = self.members[0]
+        return (f"latitude band: ATM rows {self.a_rows[0]}:{self.a_rows[1]} of {A.jm} (+{bx.ae[1] - bx.ae[0] - (self.a_rows[1] - self.a_rows[0])} halo rows), "
+                f"SFC rows {bx.s_rows[0]}:{bx.s_rows[1]} of {S.jm}, OCN rows {bx.o_rows[0]}:{bx.o_rows[1]} of {O.jm}, "
+                f"{self.M} member(s) = {self.frac:.4f} of one exchange; real data flow forward -> remaps -> bulk flux -> remaps -> backward; "
+                f"value = {self.frac:.4f} / seconds per sample")
 
 
-def cpu_baseline(dccm, wl, budget_s=12.0, min_reps=3, max_reps=200):
+CPU_NOTE = ("C restatement of the reference loops (oracle/), grids and tables from the oracle's own generators: the atmosphere's "
+            "column solves run as one serial instance per host core (the reference decomposes the atmosphere into latitude "
+            "bands over MPI ranks); surface and ocean components are single-rank as in the reference -- remap serial, "
+            "OpenMP only where the reference has !$omp")
+
+
+def cpu_baseline(wl, budget_s=12.0, min_reps=3, max_reps=200):
     """median over repetitions of the band sample; repeats until ~budget_s of host work has been timed"""
-    cs = CpuSample(dccm, wl)
-    cs.run_once()
+    cs = CpuSample(wl)
+    for _ in range(3):
+        cs.run_once()
     ts, spent = [], 0.0
     while len(ts) < min_reps or (spent < budget_s and len(ts) < max_reps):
         ts.append(cs.run_once())
         spent += ts[-1][0]
     t = float(np.median([x[0] for x in ts]))
     parts = {k: float(np.median([x[1][k] for x in ts])) for k in ts[0][1]}
-    cores = cs.orc.num_threads()
-    one = None
-    if cores > 1:                      # the reference's SFC / OCN components are single-rank: one-thread figure too
-        cs.orc.set_num_threads(1)
-        cs.parallel_atm = False
-        try:
-            one = cs.frac / cs.run_once()[0]
-        finally:
-            cs.orc.set_num_threads(cores)
-            cs.parallel_atm = True
-    return {"value": cs.frac / t, "unit": "exchanges/s", "cores": cores, "value_one_core": one, "kind": "port",
+    one = cs.one_core() if cs.cores > 1 else None     # the reference's SFC / OCN components are single-rank: one-thread figure too
+    return {"value": cs.frac / t, "unit": "exchanges/s", "cores": cs.cores, "value_one_core": one, "kind": "port",
             "sample": cs.describe(), "sample_seconds": t, "repetitions": len(ts), "timed_seconds": spent, "parts_s": parts,
-            "atm_ranks": cs.ranks,
-            "note": "C restatement of the reference loops (oracle/): the atmosphere's column solves run as one serial "
-                    "instance per host core (the reference decomposes the atmosphere into latitude bands over MPI ranks); "
-                    "surface and ocean components are single-rank as in the reference -- remap serial, OpenMP only "
-                    "where the reference has !$omp"}
+            "atm_ranks": cs.members[0].ranks, "math": "portable exp/log/pow (oracle/orc_pmath.h)", "note": CPU_NOTE}
+
+
+def full_grid_pass(wl, rows_per_band, cores):
+    """ONE repetition of the whole grid, band after band (every atmosphere row exactly once, each band with its own
+    tables and its own surface fields -- ice cover and stability change the bulk flux's work with latitude; the column
+    solve's inputs, whose values do not change its work, are generated once and reused, which keeps the set-up of ten
+    bands inside the run's time budget; second run of each band timed, the first touches the pages): the check on the
+    linear extrapolation of the band sample."""
+    ima, jma, K, nc = WORKLOADS[wl][0], WORKLOADS[wl][1], WORKLOADS[wl][5], WORKLOADS[wl][6]
+    total, work, n = 0.0, 0.0, 0
+    import oracle
+    syn = load_synthetic()
+    wide = min(jma, rows_per_band + rows_per_band // 4 + 8)
+    master = syn.column_inputs(np, oracle.gauss_grid(ima, jma), K, nc, (jma - wide) // 2, (jma - wide) // 2 + wide)
+    j = 0
+    while j < jma:
+        j1 = min(jma, j + rows_per_band)
+        if jma - j1 < rows_per_band // 4:
+            j1 = jma
+        cs = CpuSample(wl, a_rows=(j, j1), cores=cores, col_master=master)
+        cs.run_once()
+        total += cs.run_once()[0]
+        work += cs.frac
+        n += 1
+        del cs
+        j = j1
+    return total, work, n
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    dccm = importlib.import_module("dennou-ccm_b200")
-    cs = CpuSample(dccm, args.workload)
-    for _ in range(args.warmup):
+    wl = args.workload
+    cs = CpuSample(wl)
+    for _ in range(max(3, args.warmup)):        # the first calls start the OpenMP teams and touch the result pages
         cs.run_once()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cs.run_once()
     dt = (time.perf_counter() - t0) / args.steps
     v = cs.frac / dt
+    cb = {"value": v, "unit": "exchanges/s", "cores": cs.cores, "kind": "port", "sample": cs.describe(), "note": CPU_NOTE}
     line = {"impl": "reference", "metric": "coupling exchanges/sec", "value": v, "unit": "exchanges/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / cs.frac,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": max(3, args.warmup),
+            # a step of this arm IS the bounded sample: ms_per_step is its real duration (steps x ms_per_step is what the
+            # run took), value scales it to whole exchanges
+            "ms_per_step": 1e3 * dt, "ms_per_exchange_extrapolated": 1e3 * dt / cs.frac, "sample_fraction": cs.frac,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "description": DESCR[args.workload]},
-            "cpu_baseline": {"value": v, "unit": "exchanges/s", "cores": cs.orc.num_threads(), "kind": "port",
-                             "sample": cs.describe()},
+            "config": {"workload": wl, "description": DESCR[wl]},
+            "cpu_baseline": cb,
             "e2e": {"value": v, "unit": "exchanges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    if not args.no_full_grid and cs.frac < 1.0:
+        try:
+            rows = cs.a_rows[1] - cs.a_rows[0]
+            del cs
+            secs, work, nb = full_grid_pass(wl, rows, cb["cores"])
+            line["full_grid_check"] = {"seconds": secs, "bands": nb, "work_in_exchanges": work,
+                                       "value": work / secs, "unit": "exchanges/s",
+                                       "extrapolated_over_measured": v / (work / secs),
+                                       "note": "one repetition of the WHOLE grid, band after band (every row once; halo rows of "
+                                               "neighbouring bands are computed twice and counted as work); "
+                                               "extrapolated_over_measured = band-sample value / this value"}
+        except Exception as e:
+            line["full_grid_check"] = {"error": repr(e)}
+    line["loaded_repo_libraries"] = loaded_repo_libraries()
+    print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+
+def output_hash(torch, ex, dist, world):
+    """Order-independent 64-bit checksum of what the exchange hands back (a_recv, o_recv, the four tendencies): the sum
+    of the cells' bit patterns as int64, modulo 2^64, over every rank's OWNED cells -- the same number however the grids
+    are cut into bands or member blocks, so the lines of a 1/2/4/8-GPU scaling run can be compared with each other."""
+    tot = torch.zeros((), dtype=torch.int64, device=ex.dev)
+    for t in (ex.a_recv, ex.o_recv, ex.tend["DUDt"], ex.tend["DVDt"], ex.tend["DTempDt"], ex.tend["DQMixDt"]):
+        tot += t.contiguous().view(torch.int64).sum()
+    if world > 1:
+        dist.all_reduce(tot)
+    return "%016x" % (int(tot.item()) & 0xFFFFFFFFFFFFFFFF)
+
+
+def parity_rows(A, M, own):
+    """atmosphere rows of the parity band inside the owned rows `own`: the whole grid when it is small, else 48 rows --
+    around 60 N on one GPU (ice edge: both surface types, both Louis branches), at the TOP of rank 0's band in a
+    sharded run (the rows whose stencils reach into the neighbour's memory)."""
+    j0, j1 = own
+    if (j1 - j0) * A.im <= 200_000 and (j0, j1) == (0, A.jm):
+        return (0, A.jm)
+    n = min(48, j1 - j0)
+    if (j0, j1) == (0, A.jm):
+        c = int(np.searchsorted(A.y_Lat, np.deg2rad(60.0)))
+        lo = max(0, min(A.jm - n, c - n // 2))
+        return (lo, lo + n)
+    return (j1 - n, j1)
+
+
+def parity_check(torch, dccm, syn, ex, wl, grids, K, nc, M, member0, own_a, own_o, dev, fast):
+    """The GPU's outputs on a latitude band against the oracle (oracle/band.BandExchange) fed with THE SAME INPUT BITS:
+    the band's inputs are produced on the device by the generator that produced the resident inputs (checked to be
+    identical where they overlap), copied to the host and handed to the oracle.  Compared: a_recv (9 layers), o_recv (12),
+    the four tendencies -- everything the exchange returns -- of the band rows, member 0 of this rank."""
+    import oracle
+    from oracle.band import BandExchange, make_grids as orc_grids
+    A, O, S = grids
+    t0 = time.time()
+    Ao, Oo, So = orc_grids(oracle, A.im, A.jm, O.im, O.jm, WORKLOADS[wl][4])
+    for g, h in ((A, Ao), (O, Oo), (S, So)):          # the oracle's own grids are the product's, bit for bit
+        for k in ("x_Lon", "y_Lat", "y_LatWt"):
+            if not np.array_equal(getattr(g, k), getattr(h, k)):
+                return {"error": f"grid axis {k} differs between product and oracle"}
+    rows = parity_rows(A, M, own_a)
+    bx = BandExchange(oracle, Ao, Oo, So, K, nc, rows, consts_of(syn), ranks=host_cores())
+    (ae0, ae1), (oe0, oe1) = bx.input_rows()
+    col = syn.column_inputs(torch, A, K, nc, ae0, ae1, dev=dev, member=member0)
+    atm = syn.atm_surface_fields(torch, A, ae0, ae1, dev=dev, member=member0)
+    ocn = syn.ocn_surface_fields(torch, O, oe0, oe1, dev=dev, member=member0)
+    # overlap with the resident inputs of member 0: must be the same bits
+    nAl = ex.A.n
+    lo, hi = max(ae0, own_a[0]), min(ae1, own_a[1])
+    same_in = True
+    for k in ("Press", "HeatFlux", "VirTemp"):
+        res = ex.col_in[k][..., (lo - own_a[0]) * A.im:(hi - own_a[0]) * A.im]
+        same_in = same_in and bool(torch.equal(res, col[k][..., (lo - ae0) * A.im:(hi - ae0) * A.im]))
+    H = lambda d: {k: v.cpu().numpy() for k, v in d.items()}
+    bx.set_inputs(H(col), H(atm), H(ocn))
+    del col, atm, ocn
+    secs, _ = bx.run()
+    a0, a1 = rows
+    o0, o1 = bx.o_rows
+    ca = slice((a0 - own_a[0]) * A.im, (a1 - own_a[0]) * A.im)
+    co = slice((o0 - own_o[0]) * O.im, (o1 - own_o[0]) * O.im)
+    got = {"a_recv": ex.a_recv[0::M][:, ca], "o_recv": ex.o_recv[0::M][:, co]}
+    want = {"a_recv": bx.a_recv, "o_recv": bx.o_recv}
+    for k, v in bx.tend.items():
+        got[k] = ex.tend[k][..., :nAl][..., ca]
+        want[k] = v
+    stages, bitwise, worst, worst_fl, cells = {}, True, 0.0, 0.0, 0
+    for k in got:
+        g, w = got[k].cpu().numpy().reshape(-1), np.ascontiguousarray(want[k]).reshape(-1)
+        eq = bool(np.array_equal(g.view(np.int64), w.view(np.int64)))
+        nz = w != 0.0
+        rel = float(np.max(np.abs(g[nz] - w[nz]) / np.abs(w[nz]))) if nz.any() else 0.0
+        if not np.array_equal(g[~nz], w[~nz]):
+            rel = float("inf")
+        w2, g2 = np.ascontiguousarray(want[k]).reshape(-1, want[k].shape[-1]), got[k].cpu().numpy().reshape(-1, want[k].shape[-1])
+        fl = max(float(np.max(np.abs(x - y) / np.maximum(np.abs(y), 1e-3 * max(np.abs(y).max(), 1e-300)))) for x, y in zip(g2, w2))
+        stages[k] = {"bitwise": eq, "max_rel": rel}
+        bitwise, worst, worst_fl, cells = bitwise and eq, max(worst, rel), max(worst_fl, fl), cells + g.size
+    return {"bitwise": bitwise, "max_rel": worst, "max_rel_floored": worst_fl, "values_compared": cells,
+            "atm_rows": list(rows), "ocn_rows": [o0, o1], "member": member0, "inputs_identical": same_in,
+            "oracle_seconds": round(secs, 3), "seconds": round(time.time() - t0, 1), "stages": stages,
+            "mode": "fast (shared reciprocals): <= 1e-12 class, not bit-exact" if fast else "reference-order: bit-exact expected",
+            "note": "GPU outputs of the band rows vs oracle/band.BandExchange on the same input bits; max_rel = max |gpu-oracle|/|oracle| "
+                    "over cells with oracle != 0 (exact zeros must match exactly); max_rel_floored divides by max(|oracle|, 1e-3 max|layer|)"}
+
+
+def bind_numa(torch, local):
+    """pin this process to the CPUs of the NUMA node its GPU hangs off (pinned host buffers are then first-touched
+    there); returns (node, previous affinity) or (None, None)"""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None, None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        prev = os.sched_getaffinity(0)
+        use = prev & cpus
+        if not use:
+            return None, None
+        os.sched_setaffinity(0, use)
+        return node, prev
+    except Exception:
+        return None, None
+
+
+class Workload:
+    """grids + exchange object + resident synthetic inputs of one workload on this rank"""
+
+    def __init__(self, args, wl, torch, dist, dccm, rank, world, dev):
+        syn = importlib.import_module("dennou-ccm_b200.synthetic")
+        exch_mod = importlib.import_module("dennou-ccm_b200.exchange")
+        self.wl, self.syn = wl, syn
+        A, O, S, K, nc, M = make_grids(dccm, wl)
+        self.grids, self.K, self.nc, self.M_total = (A, O, S), K, nc, M
+        fast = args.fast
+        t0 = time.time()
+        self.member0, self.by_member, self.halo_mode = 0, world > 1 and M > 1, "none"
+        if self.by_member:
+            # ensembles shard by member: rank r owns members [r*M/N, (r+1)*M/N), shared tables, no data-path collective
+            if M % world:
+                raise SystemExit(f"--gpus {world} does not divide the {M} ensemble members")
+            M, self.member0 = M // world, rank * (M // world)
+            ex = exch_mod.SurfaceExchange(A, O, S, K, nc, 1, members=M, fast=fast, device=dev)
+            self.own_a, self.own_o = (0, A.jm), (0, O.jm)
+        elif world > 1:
+            sh = importlib.import_module("dennou-ccm_b200.sharding")
+            ex, self.halo_mode = None, args.halo
+            if args.halo == "peer":
+                try:
+                    ex = sh.PeerShardedExchange(A, O, S, K, nc, 1, rank=rank, world=world, dist=dist, fast=fast, device=dev)
+                except Exception as e:          # no peer access / symmetric memory: NCCL send/recv halo instead
+                    sys.stderr.write(f"[bench] peer-memory halo unavailable ({e!r}); using NCCL send/recv\n")
+                    self.halo_mode = "nccl"
+            if ex is None:
+                ex = sh.ShardedExchange(A, O, S, K, nc, 1, rank=rank, world=world, dist=dist,
+                                        halo="allgather" if self.halo_mode == "allgather" else "sendrecv",
+                                        fast=fast, device=dev)
+            self.own_a, self.own_o = ex.plan.bands["A"][rank], ex.plan.bands["O"][rank]
+        else:
+            ex = exch_mod.SurfaceExchange(A, O, S, K, nc, 1, members=M, fast=fast, device=dev)
+            self.own_a, self.own_o = (0, A.jm), (0, O.jm)
+        self.ex, self.M = ex, M
+        (ja0, ja1), (jo0, jo1) = self.own_a, self.own_o
+        # synthetic inputs, generated on the device (pure functions of the global cell index)
+        col = [syn.column_inputs(torch, A, K, nc, ja0, ja1, dev=dev, member=self.member0 + m) for m in range(M)]
+        self.col_in = {k: torch.cat([c[k] for c in col], dim=-1).contiguous() for k in col[0]}
+        del col
+        atm = [syn.atm_surface_fields(torch, A, ja0, ja1, dev=dev, member=self.member0 + m) for m in range(M)]
+        ocn = [syn.ocn_surface_fields(torch, O, jo0, jo1, dev=dev, member=self.member0 + m) for m in range(M)]
+        self.atm_sfc = {k: torch.stack([a[k] for a in atm]) for k in atm[0]}
+        self.ocn_sfc = {k: torch.stack([o[k] for o in ocn]) for k in ocn[0]}
+        ex.set_inputs(self.col_in, self.atm_sfc, self.ocn_sfc)
+        torch.cuda.synchronize()
+        self.setup_s = time.time() - t0
+        self.graph = None
+
+    def capture(self, torch, fused, no_graph):
+        """the whole step as ONE CUDA graph (kernels + halo): no per-launch host cost"""
+        ex = self.ex
+        if not no_graph:
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    ex.step(fused=fused)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    ex.step(fused=fused)
+                self.graph.replay()
+                torch.cuda.synchronize()
+            except Exception as e:
+                self.graph = None
+                sys.stderr.write(f"[bench] CUDA graph capture failed, running eagerly: {e!r}\n")
+        return self.graph.replay if self.graph is not None else (lambda: ex.step(fused=fused))
+
+    def time_steps(self, torch, dist, world, run_step, steps, bytes_per_gpu):
+        """device time of `steps` exchanges (CUDA events; max over ranks): L2 flushed between iterations when the
+        working set could sit in the 126 MB L2"""
+        dev = self.ex.dev
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if bytes_per_gpu < 2 * 126e6:
+            scrub = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
+            pairs = []
+            for _ in range(steps):
+                scrub.zero_()
+                a, b = ev(), ev()
+                a.record(); run_step(); b.record()
+                pairs.append((a, b))
+            torch.cuda.synchronize()
+            ms = sum(a.elapsed_time(b) for a, b in pairs) / steps
+            note = "L2 flushed (512 MB overwrite) between timed iterations; per-GPU working set %.0f MB" % (bytes_per_gpu / 1e6)
+            del scrub
+        else:
+            e0 = ev(); e0.record()
+            for _ in range(steps):
+                run_step()
+            e1 = ev(); e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            note = "inputs larger than L2 (per-GPU working set %.1f GB)" % (bytes_per_gpu / 1e9)
+        if world > 1:
+            dist.barrier()
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, note
+
+
+def other_workloads(args, torch, dccm, dev, skip):
+    """BASELINE configs 1-4 next to the headline (1 GPU): exchanges/s of the resident step + the parity block each"""
+    out = {}
+    for wl in ("T42", "T42x64", "T106_1deg", "T341_0p25deg"):
+        if wl == skip:
+            continue
+        try:
+            w = Workload(args, wl, torch, None, dccm, 0, 1, dev)
+            run = w.capture(torch, True, args.no_graph)
+            for _ in range(3):
+                run()
+            b = w.ex.algorithmic_bytes()["total_fused"]
+            ms, note = w.time_steps(torch, None, 1, run, 20, b)
+            out[wl] = {"value": 1e3 / ms, "unit": "exchanges/s", "ms_per_step": ms, "steps": 20, "warmup": 3,
+                       "description": DESCR[wl], "l2": note, "setup_s": round(w.setup_s, 2),
+                       "exchange_hbm_gbs": b / (ms * 1e-3) / 1e9,
+                       "output_hash": output_hash(torch, w.ex, None, 1),
+                       "parity": parity_check(torch, dccm, w.syn, w.ex, wl, w.grids, w.K, w.nc, w.M, 0, w.own_a, w.own_o, dev, args.fast)}
+            del w, run
+            torch.cuda.empty_cache()
+        except Exception as e:
+            out[wl] = {"error": repr(e)}
+    return out
+
 
 def run_ours(args, rank, world):
     import torch
@@ -285,51 +566,13 @@ def run_ours(args, rank, world):
         dist.init_process_group("nccl", device_id=dev)
     dccm = importlib.import_module("dennou-ccm_b200")
     dccm._lib.check(dccm.lib().dccm_init(local))
-    syn = importlib.import_module("dennou-ccm_b200.synthetic")
-    exch_mod = importlib.import_module("dennou-ccm_b200.exchange")
     wl = args.workload
-    A, O, S, K, nc, M = make_grids(dccm, wl)
-
-    t_setup = time.time()
-    member0 = 0
-    by_member = world > 1 and M > 1
-    if by_member:
-        # ensembles shard by member: rank r owns members [r*M/N, (r+1)*M/N), shared tables, no data-path collective
-        if M % world:
-            raise SystemExit(f"--gpus {world} does not divide the {M} ensemble members")
-        M, member0 = M // world, rank * (M // world)
-        ex = exch_mod.SurfaceExchange(A, O, S, K, nc, 1, members=M, fast=not args.reference_order, device=dev)
-        (ja0, ja1), (jo0, jo1) = (0, A.jm), (0, O.jm)
-        halo_mode = "none"
-    elif world > 1:
-        sh = importlib.import_module("dennou-ccm_b200.sharding")
-        ex, halo_mode = None, args.halo
-        if args.halo == "peer":
-            try:
-                ex = sh.PeerShardedExchange(A, O, S, K, nc, 1, rank=rank, world=world, dist=dist,
-                                            fast=not args.reference_order, device=dev)
-            except Exception as e:          # no peer access / symmetric memory: NCCL send/recv halo instead
-                sys.stderr.write(f"[bench] peer-memory halo unavailable ({e!r}); using NCCL send/recv\n")
-                halo_mode = "nccl"
-        if ex is None:
-            ex = sh.ShardedExchange(A, O, S, K, nc, 1, rank=rank, world=world, dist=dist,
-                                    halo="allgather" if halo_mode == "allgather" else "sendrecv",
-                                    fast=not args.reference_order, device=dev)
-        (ja0, ja1), (jo0, jo1) = ex.plan.bands["A"][rank], ex.plan.bands["O"][rank]
-    else:
-        ex = exch_mod.SurfaceExchange(A, O, S, K, nc, 1, members=M, fast=not args.reference_order, device=dev)
-        (ja0, ja1), (jo0, jo1) = (0, A.jm), (0, O.jm)
-    # synthetic inputs, generated on the device (pure functions of the global cell index)
-    col = [syn.column_inputs(torch, A, K, nc, ja0, ja1, dev=dev, member=member0 + m) for m in range(M)]
-    col_in = {k: torch.cat([c[k] for c in col], dim=-1).contiguous() for k in col[0]}
-    del col
-    atm = [syn.atm_surface_fields(torch, A, ja0, ja1, dev=dev, member=member0 + m) for m in range(M)]
-    ocn = [syn.ocn_surface_fields(torch, O, jo0, jo1, dev=dev, member=member0 + m) for m in range(M)]
-    atm_sfc = {k: torch.stack([a[k] for a in atm]) for k in atm[0]}
-    ocn_sfc = {k: torch.stack([o[k] for o in ocn]) for k in ocn[0]}
-    ex.set_inputs(col_in, atm_sfc, ocn_sfc)
-    torch.cuda.synchronize()
-    t_setup = time.time() - t_setup
+    W = Workload(args, wl, torch, dist, dccm, rank, world, dev)
+    ex, syn, M, by_member, halo_mode = W.ex, W.syn, W.M, W.by_member, W.halo_mode
+    A, O, S = W.grids
+    K, nc = W.K, W.nc
+    col_in, atm_sfc, ocn_sfc = W.col_in, W.atm_sfc, W.ocn_sfc
+    t_setup = W.setup_s
 
     bytes_alg = ex.algorithmic_bytes()
     if world > 1:                                  # whole-job bytes: sum over ranks
@@ -374,65 +617,19 @@ def run_ours(args, rank, world):
     part_ms = {n: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in marks])) for i, n in enumerate(names)
                if not n.startswith("_")}
 
-    # the whole step as ONE CUDA graph (kernels + NCCL halo): no per-launch host cost
-    graph = None
-    if not args.no_graph:
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                ex.step(fused=fused)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                ex.step(fused=fused)
-            graph.replay()
-            torch.cuda.synchronize()
-        except Exception as e:
-            graph = None
-            sys.stderr.write(f"[bench] CUDA graph capture failed, running eagerly: {e!r}\n")
-    run_step = graph.replay if graph is not None else (lambda: ex.step(fused=fused))
+    run_step = W.capture(torch, fused, args.no_graph)
+    graph = W.graph
     for _ in range(2):
         run_step()
 
     sampler = ClockSampler(local)
     sampler.start()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    small = bytes_alg[total_key] / world < 2 * 126e6          # per-GPU working set could sit in the 126 MB L2
-    if small:
-        # flush L2 (overwrite a 512 MB buffer) between iterations; each step has its own event pair
-        scrub = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
-        pairs = []
-        for _ in range(args.steps):
-            scrub.zero_()
-            a, b = ev(), ev()
-            a.record(); run_step(); b.record()
-            pairs.append((a, b))
-        torch.cuda.synchronize()
-        ms = sum(a.elapsed_time(b) for a, b in pairs) / args.steps
-        l2_note = "L2 flushed (512 MB overwrite) between timed iterations; per-GPU working set %.0f MB" % (
-            bytes_alg[total_key] / world / 1e6)
-    else:
-        e0 = ev(); e0.record()
-        for _ in range(args.steps):
-            run_step()
-        e1 = ev(); e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
-        l2_note = "inputs larger than L2 (per-GPU working set %.1f GB)" % (bytes_alg[total_key] / world / 1e9)
-    if world > 1:
-        dist.barrier()
+    ms, l2_note = W.time_steps(torch, dist, world, run_step, args.steps, bytes_alg[total_key] / world)
     clocks = sampler.stop()
-    if world > 1:                                  # device time, max over ranks
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     launches = launches_per_step * args.steps
 
     value = 1e3 / ms
+    moved = dict(bytes_alg)            # bytes the kernels actually move: zonal / separable operators read no table
     fwd_gbs = bytes_alg["fwd"] / (part_ms["fwd"] * 1e-3) / 1e9
     line = {
         "metric": "coupling exchanges/sec", "value": value, "unit": "exchanges/s", "n_gpus": world,
@@ -442,7 +639,8 @@ def run_ours(args, rank, world):
                    "cells_sfc": S.n * M * (world if by_member else 1), "cells_ocn": O.n * M * (world if by_member else 1),
                    "kmax": K, "ncmax": nc, "remapped_layers": 43,
                    "l2": l2_note,
-                   "mode": "reference-order" if args.reference_order else "fast (shared reciprocals)",
+                   "mode": "fast (shared reciprocals in the forward solve; <= 1e-12, not bit-exact)" if args.fast
+                           else "reference-order (every stage bit-exact against the oracle)",
                    "surface_step": "unfused (4 remaps + bulk + pack)" if args.unfused else "fused (one kernel)",
                    "launch": "one CUDA graph per exchange" if graph is not None else "eager launches",
                    "setup_s": round(t_setup, 1)},
@@ -455,10 +653,29 @@ def run_ours(args, rank, world):
         "part_algorithmic_gbytes": {n: bytes_alg[n] / 1e9 for n in bytes_alg if n in part_ms},
         "roofline": {"bound": "hbm", "kernel": "vdiff_forward_kernel", "achieved": fwd_gbs, "peak": peak,
                      "unit": "GB/s", "frac": fwd_gbs / peak, "traffic": load_traffic(wl) if world == 1 else None,
+                     "traffic_source": "profiles/roofline_traffic.json (ncu --set full capture of this kernel; not re-measured in this run)",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bytes_alg["fwd"]},
         "clocks": clocks, "gpu_launches": launches,
     }
+    if hasattr(ex, "moved_bytes"):
+        mv = ex.moved_bytes()
+        if world > 1:
+            t = torch.tensor([float(mv)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t)
+            mv = float(t.item())
+        line["exchange_moved_gbytes"] = mv / 1e9
+        line["exchange_moved_frac_of_peak"] = mv / (ms * 1e-3) / 1e9 / (peak * world)
+    # parity signal in every line: checksum of the outputs (comparable across N) + the oracle on a band (rank 0)
+    line["output_hash"] = output_hash(torch, ex, dist, world)
+    if not args.no_parity:
+        if rank == 0:
+            try:
+                line["parity"] = parity_check(torch, dccm, syn, ex, wl, W.grids, K, nc, M, W.member0, W.own_a, W.own_o, dev, args.fast)
+            except Exception as e:
+                line["parity"] = {"error": repr(e)}
+        if world > 1:
+            dist.barrier()
     if by_member:
         line["config"]["sharding"] = f"{world} member blocks of {M} (replicas of the tables, no data-path collective)"
         line["roofline"]["note"] = "per-rank kernel on rank 0's member block"
@@ -472,6 +689,7 @@ def run_ours(args, rank, world):
                "packed NCCL send/recv, one message per neighbour")
         line["config"]["sharding"] = (f"{world} latitude bands (row blocks); halo rows {how}; "
                                       f"{ex.plan.halo_bytes(rank, {'A': 17, 'O': 5, 'S': 21})} B of halo on rank {rank} per exchange")
+        line["config"]["halo"] = halo_mode
         line["roofline"]["note"] = "per-rank kernel on rank 0's band; achieved = rank-0 bytes / rank-0 time"
         line["roofline"]["achieved"] = ex.algorithmic_bytes()["fwd"] / (part_ms["fwd"] * 1e-3) / 1e9
         line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
@@ -482,26 +700,30 @@ def run_ours(args, rank, world):
             try:
                 line["e2e"] = run_e2e_pipelined(torch, dccm, syn, ex, A, O, S, K, nc, dev, args)
             except Exception as e:
-                sys.stderr.write(f"[bench] pipelined host exchange failed ({e!r}); monolithic copies instead\n")
-                line["e2e"] = run_e2e(torch, ex, col_in, atm_sfc, ocn_sfc, args)
+                sys.stderr.write(f"[bench] pipelined host exchange failed ({e!r}); overlapped whole-band copies instead\n")
+                line["e2e"] = run_e2e(torch, ex, col_in, atm_sfc, ocn_sfc, args, local)
         else:
-            line["e2e"] = run_e2e(torch, ex, col_in, atm_sfc, ocn_sfc, args)
+            line["e2e"] = run_e2e(torch, ex, col_in, atm_sfc, ocn_sfc, args, local)
         if world == 1 and M == 1 and not args.no_dropin:
             try:
                 line["e2e_dropin"] = run_e2e_dropin(torch, dccm, ex, A, O, S, K, nc, col_in, atm_sfc, ocn_sfc)
             except Exception as e:
                 line["e2e_dropin"] = {"error": repr(e)}
+    if world == 1 and rank == 0 and not args.no_others and wl == "T1279_0p1deg":
+        del W, ex, col_in, atm_sfc, ocn_sfc, run_step, graph, marks
+        torch.cuda.empty_cache()
+        line["other_workloads"] = other_workloads(args, torch, dccm, dev, wl)
     if not args.no_cpu and rank == 0 and world == 1:
         try:
-            line["cpu_baseline"] = cpu_baseline(dccm, wl)
+            line["cpu_baseline"] = cpu_baseline(wl)
         except Exception as e:           # the baseline must never take the GPU number down
             line["cpu_baseline"] = {"error": repr(e)}
     if rank == 0:
+        line["loaded_repo_libraries"] = loaded_repo_libraries()
         print(json.dumps(line), flush=True)
     if world > 1:
         # Tear down without dist.destroy_process_group(): with NCCL work captured in a CUDA graph the
         # communicator teardown can block forever.  Drain, meet at a barrier, then leave.
-        del graph, run_step
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
@@ -509,43 +731,66 @@ def run_ours(args, rank, world):
         os._exit(0)
 
 
-def run_e2e(torch, ex, col_in, atm_sfc, ocn_sfc, args):
-    """Same exchange, HOST buffers: every step copies the step's inputs from pinned host memory,
-    runs the exchange and reads the results (tendencies + fields for ATM and OCN) back."""
-    steps = max(1, min(args.steps, 3))
-    host_in = {}
+def run_e2e(torch, ex, col_in, atm_sfc, ocn_sfc, args, local=0):
+    """Same exchange, HOST buffers (sharded runs, ensembles): every step copies that step's inputs from pinned host
+    memory, runs the exchange and reads the results (tendencies + fields for ATM and OCN) back.  Consecutive steps
+    overlap on three streams: the device inputs are double-buffered, so H2D of step i+1 runs while step i computes
+    and its results leave (D2H) -- PCIe is full duplex.  Pinned buffers are first-touched on the GPU's NUMA node."""
+    import torch.distributed as dist
+    steps = max(2, min(args.steps, 4))
+    node, prev = bind_numa(torch, local)
     pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
-    for k, t in list(col_in.items()) + [("a:" + k, v) for k, v in atm_sfc.items()] + [("o:" + k, v) for k, v in ocn_sfc.items()]:
-        host_in[k] = pin(t)
+    src = {**{("c", k): v for k, v in col_in.items()}, **{("a", k): v for k, v in atm_sfc.items()},
+           **{("o", k): v for k, v in ocn_sfc.items()}}
+    host_in = {k: pin(t) for k, t in src.items()}
     outs = [ex.tend["DUDt"], ex.tend["DVDt"], ex.tend["DTempDt"], ex.tend["DQMixDt"], ex.a_recv, ex.o_recv]
     host_out = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs]
+    if prev is not None:
+        os.sched_setaffinity(0, prev)
+    dev_in = [src, {k: torch.empty_like(t) for k, t in src.items()}]      # double-buffered device inputs
     h2d = sum(t.numel() * 8 for t in host_in.values())
     d2h = sum(t.numel() * 8 for t in host_out)
+    s_in, s_out = torch.cuda.Stream(ex.dev), torch.cuda.Stream(ex.dev)
+    cs = torch.cuda.current_stream(ex.dev)
+    done_compute = [None, None]          # event: the exchange that read input set b has finished
+    done_out = None                      # event: results of the previous step have left the device
 
-    def one():
-        for k, t in host_in.items():
-            if k.startswith("a:"):
-                atm_sfc[k[2:]].copy_(t, non_blocking=True)
-            elif k.startswith("o:"):
-                ocn_sfc[k[2:]].copy_(t, non_blocking=True)
-            else:
-                col_in[k].copy_(t, non_blocking=True)
-        ex.set_inputs(col_in, atm_sfc, ocn_sfc)
+    def one(i):
+        nonlocal done_out
+        b = i % 2
+        if done_compute[b] is not None:
+            s_in.wait_event(done_compute[b])
+        with torch.cuda.stream(s_in):
+            for k, t in host_in.items():
+                dev_in[b][k].copy_(t, non_blocking=True)
+            e_in = torch.cuda.Event(); e_in.record(s_in)
+        cs.wait_event(e_in)
+        if done_out is not None:
+            cs.wait_event(done_out)      # ex.tend / a_recv / o_recv are about to be overwritten
+        d = dev_in[b]
+        ex.set_inputs({k[1]: v for k, v in d.items() if k[0] == "c"}, {k[1]: v for k, v in d.items() if k[0] == "a"},
+                      {k[1]: v for k, v in d.items() if k[0] == "o"})
         ex.step(fused=not args.unfused)
-        for h, d in zip(host_out, outs):
-            h.copy_(d, non_blocking=True)
+        e_c = torch.cuda.Event(); e_c.record(cs)
+        done_compute[b] = e_c
+        s_out.wait_event(e_c)
+        with torch.cuda.stream(s_out):
+            for h, o in zip(host_out, outs):
+                h.copy_(o, non_blocking=True)
+            done_out = torch.cuda.Event(); done_out.record(s_out)
 
-    import torch.distributed as dist
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-    one()
+    one(0); one(1)
     torch.cuda.synchronize()
     if multi:
         dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        one()
+    for i in range(steps):
+        one(i)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / steps
+    ok = all(bool(torch.equal(h, o.cpu())) for h, o in zip(host_out, outs))
+    ex.set_inputs(col_in, atm_sfc, ocn_sfc)
     if multi:
         t = torch.tensor([dt, float(h2d), float(d2h)], dtype=torch.float64, device=ex.dev)
         tm = t.clone()
@@ -553,8 +798,10 @@ def run_e2e(torch, ex, col_in, atm_sfc, ocn_sfc, args):
         dist.all_reduce(t)
         dt, h2d, d2h = float(tm[0]), int(t[1]), int(t[2])
     return {"value": 1.0 / dt, "unit": "exchanges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "ms_per_step": 1e3 * dt, "steps": steps,
-            "note": "pinned host buffers, H2D of all column/surface inputs and D2H of tendencies + remapped fields inside the timed region"}
+            "ms_per_step": 1e3 * dt, "steps": steps, "host_copy_equals_device_result": ok, "numa_node": node,
+            "note": "pinned host buffers (first-touched on the GPU's NUMA node), H2D of all column / surface inputs and D2H of "
+                    "tendencies + remapped fields for every step inside the timed region; device inputs double-buffered so the "
+                    "H2D of step i+1 overlaps the kernels and the D2H of step i; wall clock, max over ranks"}
 
 
 def run_e2e_pipelined(torch, dccm, syn, ex, A, O, S, K, nc, dev, args, nslab=12):
@@ -562,7 +809,7 @@ def run_e2e_pipelined(torch, dccm, syn, ex, A, O, S, K, nc, dev, args, nslab=12)
     H2D, kernels and D2H of successive latitude slabs overlap on three streams."""
     XH = importlib.import_module("dennou-ccm_b200.exchange_host")
     steps = max(1, min(args.steps, 3))
-    hx = XH.HostPipelinedExchange(A, O, S, K, nc, 1, nslab=nslab, device=dev, fast=not args.reference_order)
+    hx = XH.HostPipelinedExchange(A, O, S, K, nc, 1, nslab=nslab, device=dev, fast=args.fast)
     for s in range(nslab):                    # the host models' fields, slab by slab
         (a0, a1), (o0, o1) = hx.bands(s)
         col = syn.column_inputs(torch, A, K, nc, a0, a1, dev=dev)
@@ -702,7 +949,12 @@ def main():
                     help="multi-GPU halo: peer-memory reads, NCCL send/recv, or one NCCL all-gather of the boundary rows")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of as a CUDA graph")
     ap.add_argument("--unfused", action="store_true", help="surface step as 4 remaps + bulk flux + pack")
-    ap.add_argument("--reference-order", action="store_true", help="bit-exact column solves (IEEE divisions)")
+    ap.add_argument("--fast", action="store_true", help="forward solve with shared reciprocals (<= 1e-12, not bit-exact); "
+                    "the default is the reference-order solve, bit-exact against the oracle")
+    ap.add_argument("--reference-order", action="store_true", help="(default since round 2; kept for old command lines)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle-band parity block")
+    ap.add_argument("--no-others", action="store_true", help="skip the other_workloads block (BASELINE configs 1-4)")
+    ap.add_argument("--no-full-grid", action="store_true", help="reference arm: skip the one whole-grid repetition")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

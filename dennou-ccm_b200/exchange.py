@@ -268,6 +268,16 @@ class SurfaceExchange:
         b["total_fused"] = b["fwd"] + b["bwd"] + b["sfc_fused"] + b["remap_from_sfc"]
         return b
 
+    def moved_bytes(self):
+        """bytes the kernels of one (fused) exchange actually move: like algorithmic_bytes()["total_fused"], but a table
+        stored as zonal stencils (kind 1) or in separable form (kind 2) contributes no 12*nnz / row-pointer bytes --
+        its few KB of stencil / factor lists stay in L1/L2."""
+        b = self.algorithmic_bytes()
+        nA, nS, nO = self.A.n, self.S.n, self.O.n
+        ndst = {"as": nS, "os": nS, "sa": nA, "so": nO}
+        tab = sum(12 * self.nnz[k] + 4 * (ndst[k[:2]] + 1) for k, op in self.ops.items() if op.kind != 0)
+        return b["total_fused"] - tab
+
     def remapped_cell_fields(self):
         nA, nS, nO, M = self.A.n, self.S.n, self.O.n, self.M
         return M * (22 * nS + 9 * nA + 12 * nO)

@@ -44,6 +44,10 @@ def lib():
         L.orc_regular_grid.argtypes = [C.c_int, C.c_int, _f64p, _f64p, _f64p, _f64p]
         L.orc_gen_jones99.argtypes = [C.c_int, _f64p, C.c_int, _f64p, C.c_int, _f64p, C.c_int, _f64p,
                                       _f64p, _f64p, C.c_int, C.c_int, C.c_void_p]
+        L.orc_gen_jones99_rows.argtypes = [C.c_int, _f64p, C.c_int, _f64p, C.c_int, _f64p, C.c_int, _f64p,
+                                           _f64p, _f64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orc_gen_bilinear_rows.argtypes = [C.c_int, _f64p, C.c_int, _f64p, C.c_int, _f64p, C.c_int, _f64p,
+                                            C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orc_gen_bilinear.argtypes = [C.c_int, _f64p, C.c_int, _f64p, C.c_int, _f64p, C.c_int, _f64p,
                                        C.c_int, C.c_void_p]
         L.orc_make_mapping_table.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -135,20 +139,23 @@ def _take(t):
     return Table(*a)
 
 
-def gen_jones99(src, dst, order=1, lon_mode=0):
+def gen_jones99(src, dst, order=1, lon_mode=0, rows=None):
+    """rows = (j0, j1), 0-based half-open destination rows: only those lines of the full table"""
     t = lib().orc_table_new()
-    rc = lib().orc_gen_jones99(src.im, src.x_Lon, src.jm, src.y_Lat, dst.im, dst.x_Lon, dst.jm, dst.y_Lat,
-                               src.y_LatWt, dst.y_LatWt, order, lon_mode, t)
+    j0, j1 = rows if rows is not None else (0, dst.jm)
+    rc = lib().orc_gen_jones99_rows(src.im, src.x_Lon, src.jm, src.y_Lat, dst.im, dst.x_Lon, dst.jm, dst.y_Lat,
+                                    src.y_LatWt, dst.y_LatWt, order, lon_mode, j0 + 1, j1, t)
     if rc != 0:
         lib().orc_table_free(t)
         raise RuntimeError(f"orc_gen_jones99 failed rc={rc}")
     return _take(t)
 
 
-def gen_bilinear(src, dst, lon_mode=0):
+def gen_bilinear(src, dst, lon_mode=0, rows=None):
     t = lib().orc_table_new()
-    rc = lib().orc_gen_bilinear(src.im, src.x_Lon, src.jm, src.y_Lat, dst.im, dst.x_Lon, dst.jm, dst.y_Lat,
-                                lon_mode, t)
+    j0, j1 = rows if rows is not None else (0, dst.jm)
+    rc = lib().orc_gen_bilinear_rows(src.im, src.x_Lon, src.jm, src.y_Lat, dst.im, dst.x_Lon, dst.jm, dst.y_Lat,
+                                     lon_mode, j0 + 1, j1, t)
     if rc != 0:
         lib().orc_table_free(t)
         raise RuntimeError(f"orc_gen_bilinear failed rc={rc}")

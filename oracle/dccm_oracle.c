@@ -198,13 +198,21 @@ static void calc_lat_edges(int n, const double *wt, double *v)
 
 /* ref common/grid_mapping_util_jones99.f90:156-442 (gen_gridmapfile_lonlat2lonlatCore),
  * with the driver part :35-114.  Entries are appended in table-file order (:230-275). */
-int orc_gen_jones99(int nxs, const double *x_LonS, int nys, const double *y_LatS,
-                    int nxd, const double *x_LonD, int nyd, const double *y_LatD,
-                    const double *y_LatIntWtS, const double *y_LatIntWtD,
-                    int accuracy_order, int lon_mode, orc_table *out)
+/* jD0..jD1 (1-based, inclusive): the destination rows to emit -- the reference always emits 1..nyd; a sub-range gives
+ * exactly the lines of the full table that belong to those rows (bench.py's latitude-band samples).  The two
+ * searches of search_OverwrapRange are evaluated as written but only once per destination column (longitude
+ * search: independent of jD) and once per destination row (latitude search: independent of iD). */
+int orc_gen_jones99_rows(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                         int nxd, const double *x_LonD, int nyd, const double *y_LatD,
+                         const double *y_LatIntWtS, const double *y_LatIntWtD,
+                         int accuracy_order, int lon_mode, int jD0, int jD1, orc_table *out)
 {
     const double PI = acos(-1.0);
     (void)y_LatD; (void)x_LonD;
+    if (jD0 < 1) jD0 = 1;
+    if (jD1 > nyd) jD1 = nyd;
+    int *memo_rx = (int *)malloc(sizeof(int) * 2 * (size_t)(nxd + 1));
+    for (int i = 0; i < 2 * (nxd + 1); i++) memo_rx[i] = -2;
     double *uS = (double *)malloc(sizeof(double) * (nxs + 1));
     double *uD = (double *)malloc(sizeof(double) * (nxd + 1));
     double *vS = (double *)malloc(sizeof(double) * (nys + 1));
@@ -257,7 +265,8 @@ int orc_gen_jones99(int nxs, const double *x_LonS, int nys, const double *y_LatS
         }
     }
 
-    for (int jD = 1; jD <= nyd; jD++) {
+    for (int jD = jD0; jD <= jD1; jD++) {
+        int memo_ry1 = -2, memo_ry2 = -2;
         for (int iD = 1; iD <= nxd; iD++) {
             /* ---- search_OverwrapRange (:384-440) ---- */
             int rx1 = -1, rx2 = -1, ry1 = -1, ry2 = -1;
@@ -268,18 +277,26 @@ int orc_gen_jones99(int nxs, const double *x_LonS, int nys, const double *y_LatS
                 rx1 = 1; rx2 = 1;                                   /* :405-406 */
             } else if (nxs != 1 && nxd == 1) {
                 rx1 = 1; rx2 = nxs;                                 /* :407-408 */
+            } else if (memo_rx[2 * iD] != -2) {
+                rx1 = memo_rx[2 * iD]; rx2 = memo_rx[2 * iD + 1];
             } else {
                 for (int i = 1; i <= nxs; i++) {                    /* :410-418 */
                     if (uS[i - 1] <= X1 && X1 <= uS[i]) rx1 = i;
                     if (uS[i - 1] <= X2 && X2 <= uS[i]) { rx2 = i; break; }
                 }
                 if (rx1 < 0 || rx2 < 0) { rc = -1; goto done; }     /* unsupported by the reference */
+                memo_rx[2 * iD] = rx1; memo_rx[2 * iD + 1] = rx2;
             }
-            for (int j = 1; j <= nys; j++) {                        /* :421-429 */
-                if (vS[j - 1] <= Y1 && Y1 <= vS[j]) ry1 = j;
-                if (vS[j - 1] <= Y2 && Y2 <= vS[j]) { ry2 = j; break; }
+            if (memo_ry1 != -2) {
+                ry1 = memo_ry1; ry2 = memo_ry2;
+            } else {
+                for (int j = 1; j <= nys; j++) {                    /* :421-429 */
+                    if (vS[j - 1] <= Y1 && Y1 <= vS[j]) ry1 = j;
+                    if (vS[j - 1] <= Y2 && Y2 <= vS[j]) { ry2 = j; break; }
+                }
+                if (ry1 < 0 || ry2 < 0) { rc = -2; goto done; }     /* :433-438 "Exception.." stop */
+                memo_ry1 = ry1; memo_ry2 = ry2;
             }
-            if (ry1 < 0 || ry2 < 0) { rc = -2; goto done; }         /* :433-438 "Exception.." stop */
 
             /* ---- calc_RemappingWeight (:280-382) ---- */
             int nxr = general_lon ? (glon_ptr[iD] - glon_ptr[iD - 1]) : (rx2 - rx1 + 1);
@@ -333,21 +350,32 @@ int orc_gen_jones99(int nxs, const double *x_LonS, int nys, const double *y_LatS
     }
 done:
     free(uS); free(uD); free(vS); free(vD); free(segLat); free(w1); free(w2);
-    free(glon_ptr); free(glon_idx); free(glon_w);
+    free(glon_ptr); free(glon_idx); free(glon_w); free(memo_rx);
     return rc;
+}
+
+int orc_gen_jones99(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                    int nxd, const double *x_LonD, int nyd, const double *y_LatD,
+                    const double *y_LatIntWtS, const double *y_LatIntWtD,
+                    int accuracy_order, int lon_mode, orc_table *out)
+{
+    return orc_gen_jones99_rows(nxs, x_LonS, nys, y_LatS, nxd, x_LonD, nyd, y_LatD, y_LatIntWtS, y_LatIntWtD,
+                                accuracy_order, lon_mode, 1, nyd, out);
 }
 
 /* ------------------------------------------------------------------ bilinear generator */
 
 /* ref common/grid_mapping_util.f90:32-177 */
-int orc_gen_bilinear(int nxs, const double *x_LonS, int nys, const double *y_LatS,
-                     int nxr, const double *x_LonR, int nyr, const double *y_LatR,
-                     int lon_mode, orc_table *out)
+int orc_gen_bilinear_rows(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                          int nxr, const double *x_LonR, int nyr, const double *y_LatR,
+                          int lon_mode, int jr0, int jr1, orc_table *out)
 {
     const double PI = acos(-1.0);
     double dlon_r = 360.0 / (double)nxr;     /* :78 */
     double dlon_s = 360.0 / (double)nxs;     /* :79 */
-    for (int jr = 1; jr <= nyr; jr++) {
+    if (jr0 < 1) jr0 = 1;
+    if (jr1 > nyr) jr1 = nyr;
+    for (int jr = jr0; jr <= jr1; jr++) {     /* the reference: 1..nyr; a sub-range = those lines of the full table */
         /* get_correspondID_latS (:130-152) */
         double latR = y_LatR[jr - 1];
         int js = -1, extp = 1;
@@ -401,6 +429,13 @@ int orc_gen_bilinear(int nxs, const double *x_LonS, int nys, const double *y_Lat
         }
     }
     return 0;
+}
+
+int orc_gen_bilinear(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                     int nxr, const double *x_LonR, int nyr, const double *y_LatR,
+                     int lon_mode, orc_table *out)
+{
+    return orc_gen_bilinear_rows(nxs, x_LonS, nys, y_LatS, nxr, x_LonR, nyr, y_LatR, lon_mode, 1, nyr, out);
 }
 
 /* ------------------------------------------------------------------ exchange grid */

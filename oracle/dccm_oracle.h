@@ -50,6 +50,14 @@ int orc_gen_jones99(int nxs, const double *x_LonS, int nys, const double *y_LatS
 int orc_gen_bilinear(int nxs, const double *x_LonS, int nys, const double *y_LatS,
                      int nxr, const double *x_LonR, int nyr, const double *y_LatR,
                      int lon_mode, orc_table *out);
+/* the same generators restricted to destination rows j0..j1 (1-based, inclusive): exactly those lines of the full table */
+int orc_gen_jones99_rows(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                         int nxd, const double *x_LonD, int nyd, const double *y_LatD,
+                         const double *y_LatIntWtS, const double *y_LatIntWtD,
+                         int accuracy_order, int lon_mode, int jD0, int jD1, orc_table *out);
+int orc_gen_bilinear_rows(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                          int nxr, const double *x_LonR, int nyr, const double *y_LatR,
+                          int lon_mode, int jr0, int jr1, orc_table *out);
 /* make_mapping_table of the stand-alone regular-grid generator, ref common/cal_mappingtable.f90:10-49 */
 int orc_make_mapping_table(int nx_r, int ny_r, int nx_s, int ny_s, orc_table *out);
 int orc_exchange_grid(int jma, const double *y_LatA, const double *y_IntWtLatA,

@@ -21,6 +21,23 @@ def test_reference_arm_prints_one_contract_line():
     assert d["config"]["workload"] == "T42" and "model" not in d["config"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] > 0
+    # the reference arm runs on the oracle alone: the product library is never mapped into the process
+    assert d["loaded_repo_libraries"] == ["oracle/libdccm_oracle.so"]
+    # a step of this arm is the bounded sample: steps x ms_per_step is what the run really took
+    assert abs(d["value"] - d["sample_fraction"] / (d["ms_per_step"] * 1e-3)) <= 1e-9 * d["value"]
+
+
+def test_reference_arm_uses_every_core_under_torchrun_and_checks_the_whole_grid():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the arm must still use all the cores it may run on.  On a
+    workload cut into bands the line carries one whole-grid repetition next to the band extrapolation."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                        "--workload", "T106_1deg", "--steps", "2", "--warmup", "1"], capture_output=True, text=True,
+                       timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert d["sample_fraction"] == 1.0 and "full_grid_check" not in d        # 51 k columns: the sample IS the whole grid
 
 
 def test_reference_arm_non_zero_ranks_exit_quietly():
