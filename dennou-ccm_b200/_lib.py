@@ -130,6 +130,14 @@ _SIGS = {
                                             f64p, f64p, C.c_int, C.c_int, C.POINTER(vp)]),
     "dccm_remap_create_bilinear": (C.c_int, [C.c_int, f64p, C.c_int, f64p, C.c_int, f64p, C.c_int, f64p,
                                              C.c_int, C.POINTER(vp)]),
+    "dccm_remap_create_jones99_band": (C.c_int, [C.c_int, f64p, C.c_int, f64p, C.c_int, f64p, C.c_int, f64p,
+                                                 f64p, f64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                 C.POINTER(vp)]),
+    "dccm_remap_create_bilinear_band": (C.c_int, [C.c_int, f64p, C.c_int, f64p, C.c_int, f64p, C.c_int, f64p,
+                                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "dccm_table_gen_band_expanded": (C.c_int, [C.c_int, C.c_int, f64p, C.c_int, f64p, C.c_int, f64p, C.c_int, f64p,
+                                               f64p, f64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               C.POINTER(vp)]),
     "dccm_remap_classify": (C.c_int, [C.c_int64, i32p, i32p, f64p, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "dccm_remap_destroy": (None, [vp]),

@@ -76,6 +76,8 @@ __global__ void fast_arith_selftest_kernel(const double *a, const double *b, int
     unsigned long long bad = 0, rej = 0;
     { FastArith f; const double q = f.div(x, y);
       if (!f.good()) rej++; else if (__double_as_longlong(q) != __double_as_longlong(x / y)) bad++; }
+    { FastArith f; const double q = f.div_by(x, y, FastArith::prep(y));       // shared-reciprocal form of the division
+      if (!f.good()) rej++; else if (__double_as_longlong(q) != __double_as_longlong(x / y)) bad++; }
     { FastArith f; const double q = f.rcp(y);
       if (!f.good()) rej++; else if (__double_as_longlong(q) != __double_as_longlong(1.0 / y)) bad++; }
     { FastArith f; const double q = f.root(fabs(x));

@@ -10,6 +10,7 @@
 // The reference's ~25 full-grid temporaries (:157-186) and six OpenMP passes collapse into
 // registers: each input is read once and each output written once.
 #pragma once
+#include "dccm_arith.cuh"
 #include "dccm_pmath.cuh"
 
 namespace dccm {
@@ -57,80 +58,9 @@ struct BulkOut {
     double SfcTemp3, SfcAlbedo3;
 };
 
-// ---- fp64 division / reciprocal / square root without the per-operation branch ------------------
-// nvcc expands every fp64 `a / b`, `1.0 / b` and `sqrt(x)` into a short Newton sequence on the
-// MUFU.RCP64H / MUFU.RSQ64H seed, followed by a test that accepts the result when the exponents are
-// in range and otherwise BRANCHES to an out-of-line routine (denormals, infinities, NaN, zero).  The
-// ~40 divisions of a column are then ~40 basic blocks and the scheduler cannot overlap their
-// dependent DFMA chains -- the fused surface kernel spent a quarter of its cycles waiting on them.
-// FastArith issues exactly the compiler's fast-path instruction sequence (same seeds, same
-// operations, hence the same, correctly rounded, bits) but only ACCUMULATES the acceptance test in
-// `ok`; a column for which any test failed is re-evaluated with IeeeArith (plain operators) by the
-// caller.  Results are therefore bit-identical to plain `/` and `sqrt` for every input.
-struct IeeeArith {
-    __device__ __forceinline__ double div(double a, double b) { return a / b; }
-    __device__ __forceinline__ double rcp(double b) { return 1.0 / b; }
-    __device__ __forceinline__ double root(double x) { return sqrt(x); }
-    __device__ __forceinline__ bool good() const { return true; }
-};
-
-struct FastArith {
-    bool ok = true;
-    __device__ __forceinline__ bool good() const { return ok; }
-
-    static __device__ __forceinline__ int rcp64h(double b)
-    {
-        double r;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));     // MUFU.RCP64H on the high word
-        return __double2hiint(r);
-    }
-    static __device__ __forceinline__ double newton_rcp(double r, double b)
-    {
-        double e = fma(-b, r, 1.0);
-        e = fma(e, e, e);
-        r = fma(r, e, r);
-        e = fma(-b, r, 1.0);
-        return fma(r, e, r);
-    }
-    __device__ __forceinline__ double div(double a, double b)
-    {
-        const double r = newton_rcp(__hiloint2double(rcp64h(b), 1), b);
-        double q = __dmul_rn(a, r);
-        const double rem = fma(-b, q, a);
-        q = fma(r, rem, q);
-        const float t = __fmaf_rn(0.0f, __int_as_float(__double2hiint(b)), __int_as_float(__double2hiint(q)));
-        ok = ok && (fabsf(__int_as_float(__double2hiint(a))) >= 6.5827683646048100446e-37f)
-                && (fabsf(t) > 1.469367938527859385e-39f);
-        return q;
-    }
-    __device__ __forceinline__ double rcp(double b)
-    {
-        const int lo = __double2hiint(b) + 0x300402;
-        ok = ok && (fabsf(__int_as_float(lo)) >= 5.8789094863358348022e-39f);
-        return newton_rcp(__hiloint2double(rcp64h(b), lo), b);
-    }
-    __device__ __forceinline__ double root(double x)
-    {
-        double s;
-        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(s) : "d"(x));   // MUFU.RSQ64H on the high word
-        const int lo = __double2hiint(x) - 0x03500000;
-        ok = ok && ((unsigned)lo < 0x7ca00000u || x == 0.0);      // sqrt(+-0) = +-0 (calm wind) is taken here too
-        const double r0 = __hiloint2double(__double2hiint(s), lo);
-        double t = __dmul_rn(r0, r0);
-        t = fma(x, -t, 1.0);
-        const double u = fma(t, 0.375, 0.5);
-        t = __dmul_rn(r0, t);
-        const double r = fma(u, t, r0);
-        const double g = __dmul_rn(x, r);
-        const double rh = __hiloint2double(__double2hiint(r) - 0x00100000, __double2loint(r));
-        const double rem = fma(g, -g, x);
-        return x == 0.0 ? x : fma(rem, rh, g);
-    }
-};
-
 // What the implicit update (phase 2) needs from the flux evaluation (phase 1) besides BulkOut.
 struct BulkMid {
-    double Exner, SfcExner;
+    double Exner, SfcExner, iEx;            // iEx: refined reciprocal of Exner (Arith::prep)
     double Frac[2], QVapSat[2];
 };
 
@@ -167,9 +97,13 @@ __device__ __forceinline__ void bulk_fluxes(const BulkIn &in, double sig1, BulkO
     const double VirTemp = in.SfcAirTemp * (1.0 + (((1.0 / EpsV) - 1.0) * in.QVap1));   // :215
     const double Press1 = in.SfcPress * sig1;                                        // :217
     // x**kappa = pexp(kappa*plog(x)): |kappa log x| << 1 here, so the result is within 1 ulp of the
-    // correctly rounded power.
-    const double Exner = ppow(ar.div(Press1, RefPress), GasRDry / CpDry, ar);               // :218
-    const double SfcExner = ppow(ar.div(in.SfcPress, RefPress), GasRDry / CpDry, ar);       // :219
+    // correctly rounded power.  Quotients that share a divisor share its refined reciprocal (prep / div_by:
+    // the bits of `a / b`, a third of the instructions).
+    const double iRef = ar.prep(RefPress);
+    const double Exner = ppow(ar.div_by(Press1, RefPress, iRef), GasRDry / CpDry, ar);        // :218
+    const double SfcExner = ppow(ar.div_by(in.SfcPress, RefPress, iRef), GasRDry / CpDry, ar);   // :219
+    const double iEx = ar.prep(Exner), iSEx = ar.prep(SfcExner);
+    mid.iEx = iEx;
     mid.Exner = Exner; mid.SfcExner = SfcExner;
     const double VelAbs = ar.root(in.WindU * in.WindU + in.WindV * in.WindV);           // :221
     const double Height = in.SfcHeight + GasRDry / Grav * VirTemp * (1.0 - sig1);    // :223-224
@@ -188,9 +122,12 @@ __device__ __forceinline__ void bulk_fluxes(const BulkIn &in, double sig1, BulkO
     const double lgh = (z0h == z0m) ? lgm : plog(hzh, ar);
     const double tmp = ar.div(FKarm, lgm);                                                 // :250-253
     const double CMn = tmp * tmp;
-    const double CHn = tmp * ar.div(FKarm, lgh);                                         // :255-259
+    const double CHn = tmp * ((z0h == z0m) ? tmp : ar.div(FKarm, lgh));                  // :255-259 (same expression, same bits)
     const double vr = fmax(VelAbs, VelMinForRi);
     const double vr2 = vr * vr;
+    const double ivr2 = ar.prep(vr2);
+    const double vtx = ar.div_by(VirTemp, Exner, iEx);            // slot-independent quotients of the loop body
+    const double atx = ar.div_by(in.SfcAirTemp, Exner, iEx);
 
 #pragma unroll
     for (int n = 0; n < 2; n++) {                                                    // :244
@@ -200,10 +137,10 @@ __device__ __forceinline__ void bulk_fluxes(const BulkIn &in, double sig1, BulkO
             o.LatHFlx[n] = 0.0; o.LUwRFlx[n] = 0.0; o.SUwRFlx[n] = 0.0;
             continue;
         }
-        const double svx = ar.div(SfcVirTemp[n], SfcExner);
-        const double Ri = ar.div(ar.div(Grav, svx)                                   // :261-266
-                                 * (ar.div(VirTemp, Exner) - svx),
-                                 vr2)
+        const double svx = ar.div_by(SfcVirTemp[n], SfcExner, iSEx);
+        const double Ri = ar.div_by(ar.div(Grav, svx)                                // :261-266
+                                    * (vtx - svx),
+                                    vr2, ivr2)
                         * (Height - in.SfcHeight);
         const bool flag = (n == 0) ? true : ice;                                     // :268-272
 
@@ -231,17 +168,18 @@ __device__ __forceinline__ void bulk_fluxes(const BulkIn &in, double sig1, BulkO
 
         // ---- transfer coefficients and fluxes (:286-349) ----
         const double rt = GasRDry * SfcVirTemp[n];
-        o.VelTC[n] = ar.div(CM * in.SfcPress, rt)
+        const double irt = ar.prep(rt);
+        o.VelTC[n] = ar.div_by(CM * in.SfcPress, rt, irt)
                    * fmin(fmax(VelAbs, VelMinForVel), VelMaxForVel);
-        o.TempTC[n] = ar.div(CH * in.SfcPress, rt)
+        o.TempTC[n] = ar.div_by(CH * in.SfcPress, rt, irt)
                     * fmin(fmax(VelAbs, VelMinForTemp), VelMaxForTemp);
-        o.QVapTC[n] = ar.div(CQ * in.SfcPress, rt)
+        o.QVapTC[n] = ar.div_by(CQ * in.SfcPress, rt, irt)
                     * fmin(fmax(VelAbs, VelMinForQVap), VelMaxForQVap);
         if (flag) {
             o.WindStressX[n] = -o.VelTC[n] * in.WindU;
             o.WindStressY[n] = -o.VelTC[n] * in.WindV;
             o.SenHFlx[n] = -CpDry * SfcExner * o.TempTC[n]
-                         * (ar.div(in.SfcAirTemp, Exner) - ar.div(in.SfcTemp[n], SfcExner));
+                         * (atx - ar.div_by(in.SfcTemp[n], SfcExner, iSEx));
             o.QVapMFlx[n] = -HumdCoef * o.QVapTC[n] * (in.QVap1 - QVapSat[n]);
             o.LatHFlx[n] = LatentHeatLocal[n] * o.QVapMFlx[n];
             const double t2 = in.SfcTemp[n] * in.SfcTemp[n];
@@ -280,7 +218,7 @@ __device__ __forceinline__ void bulk_implicit(const BulkIn &in, const BulkMid &m
 
     // ---- implicit surface-layer update (:353-382) ----
     {
-        const double DFsDT1 = ar.div(-CpDry * SfcExner * o.TempTC[2], Exner);
+        const double DFsDT1 = ar.div_by(-CpDry * SfcExner * o.TempTC[2], Exner, mid.iEx);
         const double g0 = ar.rcp(in.Coef1[0] + o.VelTC[2]);
         const double g1 = ar.rcp(in.Coef1[1] + o.VelTC[2]);
         const double g2 = ar.rcp(in.Coef1[2] - DFsDT1);
@@ -290,7 +228,7 @@ __device__ __forceinline__ void bulk_implicit(const BulkIn &in, const BulkMid &m
         o.Del[2] = g2 * (o.SenHFlx[2] + in.Coef2[2]);
         o.Del[3] = g3 * (o.QVapMFlx[2] + in.Coef2[3]);
         double lat3 = 0.0;
-        const double cee = ar.div(CpDry * SfcExner, Exner);
+        const double cee = ar.div_by(CpDry * SfcExner, Exner, mid.iEx);
 #pragma unroll
         for (int n = 0; n < 3; n++) {
             o.WindStressX[n] = o.WindStressX[n] - o.VelTC[n] * o.Del[0];

@@ -494,6 +494,79 @@ int create_from_table(dccm_table *t, int nxs, int nys, int nxd, int nyd, dccm_re
 }
 }  // namespace
 
+namespace {
+// Latitude band of an operator: destination rows [j0, j1) only, source rows renumbered from src_row0 (the band's
+// source buffer holds src_rows rows: own rows + halo).  The longitude factors are untouched; the latitude lists and
+// the per-row stencils are cut to the band's rows -- exactly the lines of the full table that belong to them.
+int band_check(int nyd, int nys, int j0, int j1, int src_row0, int src_rows)
+{
+    if (j0 < 0 || j1 > nyd || j0 >= j1 || src_row0 < 0 || src_rows < 1 || src_row0 + src_rows > nys)
+        return fail(DCCM_ERR_ARG, "dccm_remap_create (band): rows [%d,%d) of %d, source rows [%d,%d) of %d", j0, j1, nyd,
+                    src_row0, src_row0 + src_rows, nys);
+    return DCCM_OK;
+}
+
+// table route of a band: the band's lines of the table, indices made local
+int create_band_from_table(dccm_table *t, int nxs, int nxd, int j0, int j1, int src_row0, int src_rows, dccm_remap **out)
+{
+    const int64_t n = dccm_table_size(t);
+    std::vector<int32_t> si((size_t)n), ri((size_t)n);
+    std::vector<double> cf((size_t)n);
+    int rc = dccm_table_index(t, nxs, nxd, si.data(), ri.data(), cf.data());
+    dccm_table_free(t);
+    if (rc) return rc;
+    for (int64_t k = 0; k < n; k++) { si[k] -= src_row0 * nxs; ri[k] -= j0 * nxd; }
+    return dccm_remap_create_lonlat(n, si.data(), ri.data(), cf.data(), nxs * src_rows, nxd * (j1 - j0), nxs, nxd, out);
+}
+}  // namespace
+
+extern "C" int dccm_remap_create_jones99_band(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                                              int nxd, const double *x_LonD, int nyd, const double *y_LatD,
+                                              const double *y_LatIntWtS, const double *y_LatIntWtD,
+                                              int accuracy_order, int lon_mode,
+                                              int jD0, int jD1, int src_row0, int src_rows, dccm_remap **out)
+{
+    *out = nullptr;
+    int rc = band_check(nyd, nys, jD0, jD1, src_row0, src_rows);
+    if (rc) return rc;
+    SepFactors f;
+    rc = jones99_factors(nxs, x_LonS, nys, y_LatS, nxd, x_LonD, nyd, y_LatD, y_LatIntWtS, y_LatIntWtD,
+                         accuracy_order, lon_mode, f);
+    if (rc) return rc;
+    if (zonal_ok(f) || f.ok) {
+        rc = slice_rows(f, jD0, jD1, src_row0, src_rows);
+        if (rc) return rc;
+        return zonal_ok(f) ? create_zonal(f, out) : create_separable(f, out);
+    }
+    dccm_table *t = nullptr;
+    rc = dccm_table_gen_jones99_rows(nxs, x_LonS, nys, y_LatS, nxd, x_LonD, nyd, y_LatD, y_LatIntWtS, y_LatIntWtD,
+                                     accuracy_order, lon_mode, jD0 + 1, jD1, &t);
+    if (rc) return rc;
+    return create_band_from_table(t, nxs, nxd, jD0, jD1, src_row0, src_rows, out);
+}
+
+extern "C" int dccm_remap_create_bilinear_band(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                                               int nxr, const double *x_LonR, int nyr, const double *y_LatR,
+                                               int lon_mode, int jD0, int jD1, int src_row0, int src_rows,
+                                               dccm_remap **out)
+{
+    *out = nullptr;
+    int rc = band_check(nyr, nys, jD0, jD1, src_row0, src_rows);
+    if (rc) return rc;
+    SepFactors f;
+    rc = bilinear_factors(nxs, x_LonS, nys, y_LatS, nxr, x_LonR, nyr, y_LatR, lon_mode, f);
+    if (rc) return rc;
+    if (zonal_ok(f) || f.ok) {
+        rc = slice_rows(f, jD0, jD1, src_row0, src_rows);
+        if (rc) return rc;
+        return zonal_ok(f) ? create_zonal(f, out) : create_separable(f, out);
+    }
+    dccm_table *t = nullptr;
+    rc = dccm_table_gen_bilinear_rows(nxs, x_LonS, nys, y_LatS, nxr, x_LonR, nyr, y_LatR, lon_mode, jD0 + 1, jD1, &t);
+    if (rc) return rc;
+    return create_band_from_table(t, nxs, nxr, jD0, jD1, src_row0, src_rows, out);
+}
+
 extern "C" int dccm_remap_create_jones99(int nxs, const double *x_LonS, int nys, const double *y_LatS,
                                          int nxd, const double *x_LonD, int nyd, const double *y_LatD,
                                          const double *y_LatIntWtS, const double *y_LatIntWtD,

@@ -36,4 +36,8 @@ int jones99_factors(int nxs, const double *x_LonS, int nys, const double *y_LatS
 int bilinear_factors(int nxs, const double *x_LonS, int nys, const double *y_LatS,
                      int nxr, const double *x_LonR, int nyr, const double *y_LatR, int lon_mode, SepFactors &f);
 
+// Latitude band of the factors: destination rows [j0, j1) only, source rows renumbered from src_row0 (the band's
+// source buffer holds src_rows rows).  Real entries must lie inside that buffer (error otherwise).
+int slice_rows(SepFactors &f, int j0, int j1, int src_row0, int src_rows);
+
 }  // namespace dccm

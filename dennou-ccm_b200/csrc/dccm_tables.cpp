@@ -536,6 +536,36 @@ int dccm::bilinear_factors(int nxs, const double *x_LonS, int nys, const double 
     return bilinear_impl(nxs, x_LonS, nys, y_LatS, nxr, x_LonR, nyr, y_LatR, lon_mode, 1, nyr, nullptr, &f);
 }
 
+int dccm::slice_rows(SepFactors &f, int j0, int j1, int src_row0, int src_rows)
+{
+    auto cut = [&](std::vector<int32_t> &ptr, std::vector<int32_t> &rows, std::vector<double> &w,
+                   std::vector<int32_t> *extra) -> int {
+        if (ptr.empty()) return DCCM_OK;
+        const int e0 = ptr[j0], e1 = ptr[j1];
+        for (int e = e0; e < e1; e++) {
+            // padding entries of weight 0 may point anywhere; real entries must lie inside the band's source buffer
+            const int r = rows[e] - src_row0;
+            if ((r < 0 || r >= src_rows) && w[e] != 0.0)
+                return fail(DCCM_ERR_ARG, "dccm_remap_create (band): destination rows [%d,%d) read source row %d outside [%d,%d)",
+                            j0, j1, rows[e], src_row0, src_row0 + src_rows);
+            rows[e] = (r < 0 || r >= src_rows) ? 0 : r;
+        }
+        std::vector<int32_t> np(ptr.begin() + j0, ptr.begin() + j1 + 1);
+        for (auto &v : np) v -= e0;
+        ptr.swap(np);
+        rows.assign(rows.begin() + e0, rows.begin() + e1);
+        w.assign(w.begin() + e0, w.begin() + e1);
+        if (extra) extra->assign(extra->begin() + e0, extra->begin() + e1);
+        return DCCM_OK;
+    };
+    int rc = cut(f.yptr, f.yj, f.yw, nullptr);
+    if (rc) return rc;
+    if (f.zonal) { rc = cut(f.zptr, f.zjs, f.zw, &f.zdi); if (rc) return rc; }
+    f.nyd = j1 - j0; f.nys = src_rows;
+    return DCCM_OK;
+}
+
+
 // Host-side expansion of the separable factors into a table, entry by entry as the kernels do it (kind 2):
 // lets the CPU test-suite check factors + expansion order against the generators index for index.
 static int expand_zonal(const SepFactors &f, dccm_table **out)
@@ -594,6 +624,24 @@ extern "C" int dccm_table_gen_bilinear_separable(int nxs, const double *x_LonS, 
     *out = nullptr;
     SepFactors f;
     int rc = bilinear_factors(nxs, x_LonS, nys, y_LatS, nxr, x_LonR, nyr, y_LatR, lon_mode, f);
+    return rc ? rc : expand_factors(f, out);
+}
+
+// host-only check of the band operators (dccm_remap_create_*_band): the band's factors multiplied out, LOCAL indices
+extern "C" int dccm_table_gen_band_expanded(int conservative, int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                                            int nxd, const double *x_LonD, int nyd, const double *y_LatD,
+                                            const double *y_LatIntWtS, const double *y_LatIntWtD,
+                                            int accuracy_order, int lon_mode,
+                                            int jD0, int jD1, int src_row0, int src_rows, dccm_table **out)
+{
+    *out = nullptr;
+    SepFactors f;
+    int rc = conservative ? jones99_factors(nxs, x_LonS, nys, y_LatS, nxd, x_LonD, nyd, y_LatD, y_LatIntWtS, y_LatIntWtD,
+                                            accuracy_order, lon_mode, f)
+                          : bilinear_factors(nxs, x_LonS, nys, y_LatS, nxd, x_LonD, nyd, y_LatD, lon_mode, f);
+    if (rc) return rc;
+    if (jD0 < 0 || jD1 > nyd || jD0 >= jD1) return fail(DCCM_ERR_ARG, "dccm_table_gen_band_expanded: bad rows");
+    rc = slice_rows(f, jD0, jD1, src_row0, src_rows);
     return rc ? rc : expand_factors(f, out);
 }
 

@@ -25,6 +25,7 @@
 
 #include <algorithm>
 
+#include "dccm_arith.cuh"
 #include "dccm_common.h"
 
 using namespace dccm;
@@ -36,6 +37,8 @@ struct dccm_vdiff {
     int64_t NC = 0;
     int64_t coef_stride = 0;                                // 0 = NC
     double *bUV = nullptr, *bT = nullptr, *bQ = nullptr;   // swept diagonals, (NC, kmax)
+    static constexpr int kRedoCap = 1 << 16;
+    int *redo = nullptr;                                    // redo list of the reference-order forward solve (see FwdArgs)
     DevBuf in_buf, out_buf;                                 // scratch of the host entry points
     cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};     // H2D | kernel | D2H streams of the host entry points
 };
@@ -54,17 +57,19 @@ struct FwdArgs {
     int64_t c0, c1;               // columns [c0, c1) of this launch (host entry points pipeline over column chunks)
     int K, iq;
     double Grav, CpDry, GasRDry, DelTime;
+    int *redo;                    // [0] columns listed, [1] CTAs of the redo kernel done
+    int64_t *redo64;              // the listed columns
+    int redo_cap;
 };
 
-// 5 CTAs (20 warps) per SM for one or two tracers: 95 registers and 56 B of spills instead of 104 registers and 4 CTAs
-// -- more loads in flight, 4.83 -> 4.61 ms at config 5 (6 CTAs / 80 registers spills too much: 4.80 ms)
-template <int NQ, bool FAST, int MINB = (NQ <= 2 ? 5 : 1)>
-__global__ void __launch_bounds__(kThreads, MINB) vdiff_forward_kernel(const FwdArgs a)
+// One column.  Arith supplies the divisions of the reference-order mode: FastArith (branch-free, same bits; the
+// return value says whether every division stayed inside its fast path) or IeeeArith (plain operators).
+template <int NQ, bool FAST, class Arith>
+__device__ __forceinline__ bool forward_column(const FwdArgs &a, const int64_t c)
 {
-    const int64_t c = a.c0 + (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const int64_t NC = a.NC;
-    if (c >= a.c1) return;
     const int K = a.K;
+    Arith ar;
     const double Grav = a.Grav, CpDry = a.CpDry, GasRDry = a.GasRDry;
     const double twodt = 2.0 * a.DelTime;
 #define HL(p, l) __ldg(&(p)[c + NC * (int64_t)(l)])          /* half level l = 0..K */
@@ -84,6 +89,9 @@ __global__ void __launch_bounds__(kThreads, MINB) vdiff_forward_kernel(const Fwd
 #pragma unroll
     for (int n = 0; n < NQ; n++) rQn[n] = 0.0;
     double rU2 = 0.0, rV2 = 0.0, rT2 = 0.0, rQ2 = 0.0;
+    // reference-order mode: refined reciprocals of the constant divisors, and of zExner carried down with it
+    const double iGrav = FAST ? 0.0 : FastArith::prep(Grav), iTwodt = FAST ? 0.0 : FastArith::prep(twodt);
+    double iz_hi = FAST ? 0.0 : FastArith::prep(zE_hi), iz_hi2 = 0.0, iz_lo = 0.0;
 
     for (int k = K; k >= 2; --k) {
         const int l = k - 1;
@@ -95,43 +103,31 @@ __global__ void __launch_bounds__(kThreads, MINB) vdiff_forward_kernel(const Fwd
 #pragma unroll
         for (int n = 0; n < NQ; n++) FQ_lo[n] = QH(n, l);
 
-        // transfer coefficients at half level l (:196-203)
-        double tmp;
-        if (FAST) tmp = P_lo / (GasRDry * Tv * (H_hi - H_lo));
-        else      tmp = P_lo / (GasRDry * Tv) / (H_hi - H_lo);
-        const double TV_lo = dV * tmp, TT_lo = dT * tmp, TQ_lo = dQ * tmp;
-
-        // matrix rows k (:207-293) and right-hand sides (:297-311)
-        double mass, aT, bT, cT;
-        if (FAST) {
-            mass = -(P_hi - P_lo) * (1.0 / (Grav * twodt));
-            const double izhi = 1.0 / zE_hi;
-            aT = -CpDry * rE_lo * TT_lo / zE_lo;
-            bT = CpDry * mass + CpDry * rE_lo * TT_lo * izhi;
-            if (k < K) bT += CpDry * rE_hi * TT_hi * izhi;
-            cT = (k < K) ? -CpDry * rE_hi * TT_hi / zE_hi2 : 0.0;
-        } else {
-            mass = -(P_hi - P_lo) / Grav / twodt;
-            aT = -CpDry * rE_lo / zE_lo * TT_lo;
-            bT = -CpDry * (P_hi - P_lo) / Grav / twodt + CpDry * rE_lo / zE_hi * TT_lo;
-            if (k < K) bT = bT + CpDry * rE_hi / zE_hi * TT_hi;
-            cT = (k < K) ? -CpDry * rE_hi / zE_hi2 * TT_hi : 0.0;
-        }
-        const double aUV = -TV_lo, cUV = -TV_hi;
-        double bUV = mass + TV_lo;
-        if (k < K) bUV = bUV + TV_hi;
-        const double aQ = -TQ_lo, cQ = -TQ_hi;
-        double bQ = mass + TQ_lo;
-        if (k < K) bQ = bQ + TQ_hi;
+        double TV_lo, TT_lo, TQ_lo;
+        double bUVp, bTp, bQp, rUp, rVp, rTp, rQp[NQ];
         const double rU = -(FX_hi - FX_lo), rV = -(FY_hi - FY_lo), rT = -(FH_hi - FH_lo);
         double rQ[NQ];
 #pragma unroll
         for (int n = 0; n < NQ; n++) rQ[n] = -(FQ_hi[n] - FQ_lo[n]);
-
-        // top-down elimination of level k (:388-400)
-        double bUVp, bTp, bQp, rUp, rVp, rTp, rQp[NQ];
-        if (k == K) {
-            if (FAST) {
+        if constexpr (FAST) {
+            // transfer coefficients at half level l (:196-203)
+            const double tmp = P_lo / (GasRDry * Tv * (H_hi - H_lo));
+            TV_lo = dV * tmp; TT_lo = dT * tmp; TQ_lo = dQ * tmp;
+            // matrix rows k (:207-293)
+            const double mass = -(P_hi - P_lo) * (1.0 / (Grav * twodt));
+            const double izhi = 1.0 / zE_hi;
+            const double aT = -CpDry * rE_lo * TT_lo / zE_lo;
+            double bT = CpDry * mass + CpDry * rE_lo * TT_lo * izhi;
+            if (k < K) bT += CpDry * rE_hi * TT_hi * izhi;
+            const double cT = (k < K) ? -CpDry * rE_hi * TT_hi / zE_hi2 : 0.0;
+            const double aUV = -TV_lo, cUV = -TV_hi;
+            double bUV = mass + TV_lo;
+            if (k < K) bUV = bUV + TV_hi;
+            const double aQ = -TQ_lo, cQ = -TQ_hi;
+            double bQ = mass + TQ_lo;
+            if (k < K) bQ = bQ + TQ_hi;
+            // top-down elimination of level k (:388-400)
+            if (k == K) {
                 const double iu = 1.0 / aUV, it = 1.0 / aT, iq = 1.0 / aQ;
                 bUVp = bUV * iu; rUp = rU * iu; rVp = rV * iu;
                 bTp = bT * it; rTp = rT * it;
@@ -139,15 +135,7 @@ __global__ void __launch_bounds__(kThreads, MINB) vdiff_forward_kernel(const Fwd
 #pragma unroll
                 for (int n = 0; n < NQ; n++) rQp[n] = rQ[n] * iq;
             } else {
-                bUVp = bUV / aUV; rUp = rU / aUV; rVp = rV / aUV;
-                bTp = bT / aT; rTp = rT / aT;
-                bQp = bQ / aQ;
-#pragma unroll
-                for (int n = 0; n < NQ; n++) rQp[n] = rQ[n] / aQ;
-            }
-        } else {
-            const double dUV = aUV * bUVn, dT_ = aT * bTn, dQ_ = aQ * bQn;
-            if (FAST) {
+                const double dUV = aUV * bUVn, dT_ = aT * bTn, dQ_ = aQ * bQn;
                 const double iu = 1.0 / dUV, it = 1.0 / dT_, iq = 1.0 / dQ_;
                 bUVp = (bUV * bUVn - cUV) * iu;
                 rUp = (rU * bUVn - cUV * rUn) * iu;
@@ -157,15 +145,54 @@ __global__ void __launch_bounds__(kThreads, MINB) vdiff_forward_kernel(const Fwd
                 bQp = (bQ * bQn - cQ) * iq;
 #pragma unroll
                 for (int n = 0; n < NQ; n++) rQp[n] = (rQ[n] * bQn - cQ * rQn[n]) * iq;
-            } else {
-                bUVp = (bUV * bUVn - cUV) / dUV;
-                rUp = (rU * bUVn - cUV * rUn) / dUV;
-                rVp = (rV * bUVn - cUV * rVn) / dUV;
-                bTp = (bT * bTn - cT) / dT_;
-                rTp = (rT * bTn - cT * rTn) / dT_;
-                bQp = (bQ * bQn - cQ) / dQ_;
+            }
+        } else {
+            // Reference order, every quotient with the bits of the IEEE operator.  The ~17 divisions of a level have
+            // only 8 distinct divisors (two of them constants, two carried down from the level above): the refined
+            // reciprocal of the division sequence is computed once per divisor (FastArith::prep / div_by) and the
+            // per-division range test is accumulated instead of branched on; a column whose test failed anywhere
+            // (zero / denormal / non-finite operands) goes to the redo list and is solved again with the plain
+            // operators by vdiff_forward_redo_kernel.
+            iz_lo = FastArith::prep(zE_lo);
+            {
+                // transfer coefficients at half level l (:196-203)
+                const double gt = GasRDry * Tv, dH = H_hi - H_lo;
+                const double tmp = ar.div_by(ar.div_by(P_lo, gt, ar.prep(gt)), dH, ar.prep(dH));
+                TV_lo = dV * tmp; TT_lo = dT * tmp; TQ_lo = dQ * tmp;
+                // matrix rows k (:207-293)
+                const double dP = P_hi - P_lo;
+                const double mass = ar.div_by(ar.div_by(-dP, Grav, iGrav), twodt, iTwodt);
+                const double aT = ar.div_by(-CpDry * rE_lo, zE_lo, iz_lo) * TT_lo;
+                double bT = ar.div_by(ar.div_by(-CpDry * dP, Grav, iGrav), twodt, iTwodt)
+                          + ar.div_by(CpDry * rE_lo, zE_hi, iz_hi) * TT_lo;
+                if (k < K) bT = bT + ar.div_by(CpDry * rE_hi, zE_hi, iz_hi) * TT_hi;
+                const double cT = (k < K) ? ar.div_by(-CpDry * rE_hi, zE_hi2, iz_hi2) * TT_hi : 0.0;
+                const double aUV = -TV_lo, cUV = -TV_hi;
+                double bUV = mass + TV_lo;
+                if (k < K) bUV = bUV + TV_hi;
+                const double aQ = -TQ_lo, cQ = -TQ_hi;
+                double bQ = mass + TQ_lo;
+                if (k < K) bQ = bQ + TQ_hi;
+                // top-down elimination of level k (:388-400)
+                if (k == K) {
+                    const double tu = ar.prep(aUV), tt = ar.prep(aT), tq = ar.prep(aQ);
+                    bUVp = ar.div_by(bUV, aUV, tu); rUp = ar.div_by(rU, aUV, tu); rVp = ar.div_by(rV, aUV, tu);
+                    bTp = ar.div_by(bT, aT, tt); rTp = ar.div_by(rT, aT, tt);
+                    bQp = ar.div_by(bQ, aQ, tq);
 #pragma unroll
-                for (int n = 0; n < NQ; n++) rQp[n] = (rQ[n] * bQn - cQ * rQn[n]) / dQ_;
+                    for (int n = 0; n < NQ; n++) rQp[n] = ar.div_by(rQ[n], aQ, tq);
+                } else {
+                    const double dUV = aUV * bUVn, dT_ = aT * bTn, dQ_ = aQ * bQn;
+                    const double tu = ar.prep(dUV), tt = ar.prep(dT_), tq = ar.prep(dQ_);
+                    bUVp = ar.div_by(bUV * bUVn - cUV, dUV, tu);
+                    rUp = ar.div_by(rU * bUVn - cUV * rUn, dUV, tu);
+                    rVp = ar.div_by(rV * bUVn - cUV * rVn, dUV, tu);
+                    bTp = ar.div_by(bT * bTn - cT, dT_, tt);
+                    rTp = ar.div_by(rT * bTn - cT * rTn, dT_, tt);
+                    bQp = ar.div_by(bQ * bQn - cQ, dQ_, tq);
+#pragma unroll
+                    for (int n = 0; n < NQ; n++) rQp[n] = ar.div_by(rQ[n] * bQn - cQ * rQn[n], dQ_, tq);
+                }
             }
         }
         const int64_t o = c + NC * (int64_t)(k - 1);
@@ -176,6 +203,7 @@ __global__ void __launch_bounds__(kThreads, MINB) vdiff_forward_kernel(const Fwd
 
         // shift down one level
         P_hi = P_lo; H_hi = H_lo; zE_hi2 = zE_hi; zE_hi = zE_lo; rE_hi = rE_lo;
+        iz_hi2 = iz_hi; iz_hi = iz_lo;
         TV_hi = TV_lo; TT_hi = TT_lo; TQ_hi = TQ_lo;
         FX_hi = FX_lo; FY_hi = FY_lo; FH_hi = FH_lo;
         bUVn = bUVp; bTn = bTp; bQn = bQp; rUn = rUp; rVn = rVp; rTn = rTp;
@@ -221,6 +249,39 @@ __global__ void __launch_bounds__(kThreads, MINB) vdiff_forward_kernel(const Fwd
 #undef HL
 #undef FL
 #undef QH
+    return ar.good();
+}
+
+// 5 CTAs (20 warps) per SM for one or two tracers -- more loads in flight, 4.83 -> 4.61 ms at config 5
+template <int NQ, bool FAST, int MINB = (NQ <= 2 ? 5 : 1)>
+__global__ void __launch_bounds__(kThreads, MINB) vdiff_forward_kernel(const FwdArgs a)
+{
+    const int64_t c = a.c0 + (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (c >= a.c1) return;
+    if (!forward_column<NQ, FAST, FastArith>(a, c)) {
+        const int slot = atomicAdd(&a.redo[0], 1);
+        if (slot < a.redo_cap) a.redo64[slot] = c;
+    }
+}
+
+// The columns the branch-free divisions did not accept (normally none: an empty launch), solved again with the plain
+// IEEE operators; more columns than the list holds: every column of the launch is redone.  The last CTA clears the list.
+template <int NQ>
+__global__ void __launch_bounds__(kThreads) vdiff_forward_redo_kernel(const FwdArgs a)
+{
+    const int listed = a.redo[0];
+    if (listed <= 0) return;
+    const int64_t stride = (int64_t)gridDim.x * kThreads, t0 = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (listed <= a.redo_cap) {
+        for (int64_t t = t0; t < listed; t += stride) forward_column<NQ, false, IeeeArith>(a, a.redo64[t]);
+    } else {
+        for (int64_t c = a.c0 + t0; c < a.c1; c += stride) forward_column<NQ, false, IeeeArith>(a, c);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&a.redo[1], 1) == (int)gridDim.x - 1) { a.redo[0] = 0; a.redo[1] = 0; __threadfence(); }
+    }
 }
 
 struct BwdArgs {
@@ -294,6 +355,20 @@ __global__ void __launch_bounds__(kThreads) vdiff_backward_kernel(const BwdArgs 
     }
 }
 
+void launch_forward_redo(int nq, const FwdArgs &a, unsigned grid, cudaStream_t st)
+{
+    switch (nq) {
+    case 1: vdiff_forward_redo_kernel<1><<<grid, kThreads, 0, st>>>(a); break;
+    case 2: vdiff_forward_redo_kernel<2><<<grid, kThreads, 0, st>>>(a); break;
+    case 3: vdiff_forward_redo_kernel<3><<<grid, kThreads, 0, st>>>(a); break;
+    case 4: vdiff_forward_redo_kernel<4><<<grid, kThreads, 0, st>>>(a); break;
+    case 5: vdiff_forward_redo_kernel<5><<<grid, kThreads, 0, st>>>(a); break;
+    case 6: vdiff_forward_redo_kernel<6><<<grid, kThreads, 0, st>>>(a); break;
+    case 7: vdiff_forward_redo_kernel<7><<<grid, kThreads, 0, st>>>(a); break;
+    default: vdiff_forward_redo_kernel<8><<<grid, kThreads, 0, st>>>(a); break;
+    }
+}
+
 template <bool FAST>
 void launch_forward(int nq, const FwdArgs &a, unsigned grid, cudaStream_t st)
 {
@@ -331,6 +406,9 @@ extern "C" int dccm_vdiff_create(int imax, int jmax, int kmax, int ncmax, int in
     cudaError_t e = cudaMalloc(&h->bUV, bytes);
     if (e == cudaSuccess) e = cudaMalloc(&h->bT, bytes);
     if (e == cudaSuccess) e = cudaMalloc(&h->bQ, bytes);
+    const size_t redo_bytes = 16 + sizeof(int64_t) * dccm_vdiff::kRedoCap;
+    if (e == cudaSuccess) e = cudaMalloc(&h->redo, redo_bytes);
+    if (e == cudaSuccess) e = cudaMemset(h->redo, 0, redo_bytes);
     if (e != cudaSuccess) {
         dccm_vdiff_destroy(h);
         return fail(DCCM_ERR_CUDA, "dccm_vdiff_create: %s", cudaGetErrorString(e));
@@ -342,7 +420,7 @@ extern "C" int dccm_vdiff_create(int imax, int jmax, int kmax, int ncmax, int in
 extern "C" void dccm_vdiff_destroy(dccm_vdiff *h)
 {
     if (!h) return;
-    cudaFree(h->bUV); cudaFree(h->bT); cudaFree(h->bQ);
+    cudaFree(h->bUV); cudaFree(h->bT); cudaFree(h->bQ); cudaFree(h->redo);
     h->in_buf.release(); h->out_buf.release();
     for (cudaStream_t st : h->pipe) if (st) cudaStreamDestroy(st);
     delete h;
@@ -380,9 +458,14 @@ int forward_range(dccm_vdiff *h,
     a.NC = h->NC; a.K = h->kmax; a.iq = h->iq; a.c0 = c0; a.c1 = c1;
     a.cstride = h->coef_stride > 0 ? h->coef_stride : h->NC;
     a.Grav = h->Grav; a.CpDry = h->CpDry; a.GasRDry = h->GasRDry; a.DelTime = h->DelTime;
+    a.redo = h->redo; a.redo64 = reinterpret_cast<int64_t *>(h->redo + 4); a.redo_cap = dccm_vdiff::kRedoCap;
     const unsigned grid = (unsigned)((c1 - c0 + kThreads - 1) / kThreads);
     if (h->fast) launch_forward<true>(h->ncmax, a, grid, st);
-    else         launch_forward<false>(h->ncmax, a, grid, st);
+    else {
+        launch_forward<false>(h->ncmax, a, grid, st);
+        DCCM_CUDA_TRY(cudaGetLastError());
+        launch_forward_redo(h->ncmax, a, std::min(grid, 4u * (unsigned)num_sms()), st);
+    }
     DCCM_CUDA_TRY(cudaGetLastError());
     return DCCM_OK;
 }

@@ -53,7 +53,7 @@ class SurfaceExchange:
     """
 
     def __init__(self, A, O, S, kmax, ncmax=1, index_h2ovap=1, tabs=None, consts=None, members=1,
-                 fast=True, device=None, layout=None, structured=True):
+                 fast=True, device=None, layout=None, structured=True, ops=None):
         """layout (sharded runs, sharding.py): {"A"|"S"|"O": (n_own, n_ext, off)} -- cells this rank
         owns, cells of its source buffers (own + halo rows) and where the owned cells start in them;
         A/O/S are then objects with .im/.jm/.n of the LOCAL band."""
@@ -73,7 +73,10 @@ class SurfaceExchange:
         assert not (self.sharded and members > 1), "ensembles shard by member, not by latitude band"
         self.ops = {}
         self.nnz = {}
-        if tabs is None and not self.sharded and structured:
+        if ops is not None:            # prebuilt operators (sharding.py: band operators straight from the grid axes)
+            self.ops = dict(ops)
+            self.nnz = {k: op.nnz for k, op in self.ops.items()}
+        elif tabs is None and not self.sharded and structured:
             # straight from the grids (dccm_remap_create_jones99 / _bilinear): no table is built on the host;
             # the ocean-side pairs with different longitudes come back in separable form (kind 2)
             g = {"a": A, "s": S, "o": O}

@@ -30,13 +30,27 @@ class RemapOperator:
         self._h = h
 
     @classmethod
-    def from_grids(cls, src, dst, conservative, accuracy_order=1, lon_mode=1):
+    def from_grids(cls, src, dst, conservative, accuracy_order=1, lon_mode=1, rows=None, src_rows=None):
         """Generate-and-create in one step (dccm_remap_create_jones99 / _bilinear): the table is never built.
-        Different longitudes give the separable form (kind 2); equal longitudes a zonal stencil (kind 1)."""
+        Different longitudes give the separable form (kind 2); equal longitudes a zonal stencil (kind 1).
+        rows = (j0, j1), src_rows = (e0, e1): the operator of a latitude band -- destination rows [j0, j1) only, source
+        cells numbered inside a buffer that holds source rows [e0, e1) (dccm_remap_create_*_band)."""
         self = cls.__new__(cls)
         self.n_send, self.n_recv = src.n, dst.n
         h = C.c_void_p()
-        if conservative:
+        if rows is not None:
+            (j0, j1), (e0, e1) = rows, src_rows
+            self.n_send, self.n_recv = (e1 - e0) * src.im, (j1 - j0) * dst.im
+            if conservative:
+                L.check(L.lib().dccm_remap_create_jones99_band(src.im, L.dp(src.x_Lon), src.jm, L.dp(src.y_Lat),
+                                                               dst.im, L.dp(dst.x_Lon), dst.jm, L.dp(dst.y_Lat),
+                                                               L.dp(src.y_LatWt), L.dp(dst.y_LatWt),
+                                                               accuracy_order, lon_mode, j0, j1, e0, e1 - e0, C.byref(h)))
+            else:
+                L.check(L.lib().dccm_remap_create_bilinear_band(src.im, L.dp(src.x_Lon), src.jm, L.dp(src.y_Lat),
+                                                                dst.im, L.dp(dst.x_Lon), dst.jm, L.dp(dst.y_Lat),
+                                                                lon_mode, j0, j1, e0, e1 - e0, C.byref(h)))
+        elif conservative:
             L.check(L.lib().dccm_remap_create_jones99(src.im, L.dp(src.x_Lon), src.jm, L.dp(src.y_Lat),
                                                       dst.im, L.dp(dst.x_Lon), dst.jm, L.dp(dst.y_Lat),
                                                       L.dp(src.y_LatWt), L.dp(dst.y_LatWt),

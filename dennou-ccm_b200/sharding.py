@@ -124,6 +124,20 @@ class BandPlan:
                 out[f"{key}_{kind}"] = ((send - soff).astype(np.int32), (recv - doff).astype(np.int32), coef)
         return out
 
+    def local_operators(self, rank):
+        """the eight operators of the rank's bands straight from the grid axes (RemapOperator.from_grids with rows /
+        src_rows): zonal stencils where the longitudes agree, separable factors where they differ -- no table is
+        generated on the host and none is read by the kernels; same bits as the rows of the unsharded operators."""
+        from .interpolation_data_latlon_mod import RemapOperator
+        out = {}
+        for key in self.TABLES:
+            s, d = key[0].upper(), key[1].upper()
+            for kind in ("cons", "bil"):
+                order = self.order_as if (key == "as" and kind == "cons") else 1
+                out[f"{key}_{kind}"] = RemapOperator.from_grids(self.grid[s], self.grid[d], kind == "cons", order, self.lon_mode,
+                                                                rows=tuple(self.bands[d][rank]), src_rows=tuple(self.ext[s][rank]))
+        return out
+
     def layout(self, rank):
         lay = {}
         for g in self.GRIDS:
@@ -263,14 +277,19 @@ class ShardedExchange(SurfaceExchange):
     """SurfaceExchange on rank `rank` of `world`: local bands + halo exchange around the surface step."""
 
     def __init__(self, A, O, S, kmax, ncmax=1, index_h2ovap=1, rank=0, world=1, plan=None, dist=None,
-                 halo="sendrecv", **kw):
+                 halo="sendrecv", band_tables=False, **kw):
         """halo: "sendrecv" = grouped NCCL send/recv with the two neighbours, "allgather" = one all-gather of every
-        rank's boundary rows per phase (AllGatherHalo)"""
+        rank's boundary rows per phase (AllGatherHalo).  band_tables: generate the band's tables on the host and
+        keep them as CSR (the round-1 form; tests compare it with the table-free band operators)"""
         self.plan = plan or BandPlan(A, O, S, world)
         self.rank, self.world, self.dist = rank, world, dist
         lA, lO, lS = self.plan.local_grids(rank)
-        super().__init__(lA, lO, lS, kmax, ncmax, index_h2ovap, tabs=self.plan.local_tables(rank),
-                         layout=self.plan.layout(rank), **kw)
+        if band_tables:
+            super().__init__(lA, lO, lS, kmax, ncmax, index_h2ovap, tabs=self.plan.local_tables(rank),
+                             layout=self.plan.layout(rank), **kw)
+        else:
+            super().__init__(lA, lO, lS, kmax, ncmax, index_h2ovap, ops=self.plan.local_operators(rank),
+                             layout=self.plan.layout(rank), **kw)
         mA, mO, mS = (self.plan.halo_messages(g, rank) for g in ("A", "O", "S"))
         bufs_in = [(self.a2s_bil, mA), (self.a2s_cons, mA), (self.o2s_bil, mO), (self.o2s_cons, mO)]
         bufs_out = [(self.s2a, mS), (self.s2o, mS)]

@@ -146,6 +146,26 @@ int dccm_remap_create_jones99(int nxs, const double *x_LonS, int nys, const doub
 int dccm_remap_create_bilinear(int nxs, const double *x_LonS, int nys, const double *y_LatS,
                                int nxr, const double *x_LonR, int nyr, const double *y_LatR,
                                int lon_mode, dccm_remap **out);
+/* The same operators for a LATITUDE BAND of the destination grid (row-block sharding over GPUs; the
+ * reference partitions the remap by the receiving component's local cells, ref common/interpolation_data_latlon_mod.f90:
+ * 140-151): destination rows [jD0, jD1) (0-based, half open) become rows 0.. of the operator, and source cells are
+ * numbered inside the band's source buffer, which holds the src_rows source rows starting at row src_row0 (own rows +
+ * halo).  Exactly the lines of the full table that belong to those rows, in the same storage forms (zonal stencils /
+ * separable factors, no table built) -- results are bit-identical to the corresponding rows of the full operator. */
+int dccm_remap_create_jones99_band(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                                   int nxd, const double *x_LonD, int nyd, const double *y_LatD,
+                                   const double *y_LatIntWtS, const double *y_LatIntWtD,
+                                   int accuracy_order, int lon_mode,
+                                   int jD0, int jD1, int src_row0, int src_rows, dccm_remap **out);
+int dccm_remap_create_bilinear_band(int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                                    int nxr, const double *x_LonR, int nyr, const double *y_LatR,
+                                    int lon_mode, int jD0, int jD1, int src_row0, int src_rows, dccm_remap **out);
+/* host-only: what a band operator applies, multiplied out into a table with the band's LOCAL indices (checks) */
+int dccm_table_gen_band_expanded(int conservative, int nxs, const double *x_LonS, int nys, const double *y_LatS,
+                                 int nxd, const double *x_LonD, int nyd, const double *y_LatD,
+                                 const double *y_LatIntWtS, const double *y_LatIntWtD,
+                                 int accuracy_order, int lon_mode,
+                                 int jD0, int jD1, int src_row0, int src_rows, dccm_table **out);
 /* host-only: the storage form dccm_remap_create_lonlat would choose (kind, entries kept) */
 int dccm_remap_classify(int64_t nops, const int32_t *send_index, const int32_t *recv_index,
                         const double *coef, int n_send, int n_recv, int gnxs, int gnxr,

@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstring>
 #define __device__
+#define __constant__
 #define __forceinline__ inline
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }

@@ -223,7 +223,7 @@ def test_branch_free_division_and_sqrt_match_the_operators_bitwise(gpu, dccm):
             b[:8] = torch.tensor([1.0, 1.0, 1.0, 1.0, 0.0, float("inf"), 3.0, 1e-308], device=gpu)
         bad, rej = C.c_int64(-1), C.c_int64(-1)
         L.check(L.lib().dccm_selftest_fast_arith_device(L.tptr(a), L.tptr(b), n, C.byref(bad), C.byref(rej)))
-        print(f"exponent spread 2^+-{spread}: {rej.value} of {3 * n} operations rejected, {bad.value} mismatches")
+        print(f"exponent spread 2^+-{spread}: {rej.value} of {4 * n} operations rejected, {bad.value} mismatches")
         assert bad.value == 0
         if max_rej is not None:
             assert rej.value <= max_rej

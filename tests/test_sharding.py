@@ -109,3 +109,35 @@ def test_band_plan_T1279_halo_is_small(dccm):
         assert j0 - 1 <= lo <= j0 and j1 <= hi <= j1 + 1
     with pytest.raises(ValueError):
         sh.BandPlan(T.get_LonLatGrid(64, 32), T.get_LonLatGrid(1, 64), T.get_LonLatGrid(64, 32), 40)
+
+
+@pytest.mark.parametrize("name,world", [("T21_1deg", 3), ("T21_Pl42", 2), ("T42_T42", 4), ("T106_1deg", 5)])
+def test_band_operators_from_the_grid_axes_equal_the_band_tables(orc, dccm, name, world):
+    """dccm_remap_create_*_band (what ShardedExchange uploads: the band's rows of the zonal stencils / separable
+    factors, no table generated) multiplied out on the host == the band's table lines with local indices
+    (BandPlan.local_tables: generator restricted to the rows), entry for entry in table order -- for every rank, every
+    direction, both kinds, first and second order."""
+    import ctypes as C
+    from util import pair
+    L = dccm._lib
+    sh = importlib.import_module("dennou-ccm_b200.sharding")
+    T = dccm.tables
+    A, O, Sx = pair(orc, dccm, name)
+    for order_as in (1, 2):
+        plan = sh.BandPlan(A, O, Sx, world, order_as=order_as)
+        for rank in range(world):
+            want = plan.local_tables(rank)
+            for key in plan.TABLES:
+                s, d = plan.grid[key[0].upper()], plan.grid[key[1].upper()]
+                (j0, j1), (e0, e1) = plan.bands[key[1].upper()][rank], plan.ext[key[0].upper()][rank]
+                for kind in ("cons", "bil"):
+                    order = order_as if (key == "as" and kind == "cons") else 1
+                    h = C.c_void_p()
+                    rc = L.lib().dccm_table_gen_band_expanded(
+                        1 if kind == "cons" else 0, s.im, L.dp(s.x_Lon), s.jm, L.dp(s.y_Lat), d.im, L.dp(d.x_Lon), d.jm,
+                        L.dp(d.y_Lat), L.dp(s.y_LatWt), L.dp(d.y_LatWt), order, 1, j0, j1, e0, e1 - e0, C.byref(h))
+                    if rc != 0:
+                        continue             # pair not handled in factored form: the band operator takes the table route
+                    got = T.MappingTable(h).index(s.im, d.im)
+                    for a, b, what in zip(got, want[f"{key}_{kind}"], ("send", "recv", "coef")):
+                        assert np.array_equal(a, b), (name, world, rank, key, kind, order, what)
