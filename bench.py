@@ -474,26 +474,28 @@ class Workload:
         self.setup_s = time.time() - t0
         self.graph = None
 
-    def capture(self, torch, fused, no_graph):
-        """the whole step as ONE CUDA graph (kernels + halo): no per-launch host cost"""
+    def capture(self, torch, fused, no_graph, slabs=0):
+        """the whole step as ONE CUDA graph (kernels + halo): no per-launch host cost.  slabs > 0: the latitude-slab
+        pipeline (forward solve in slabs, surface kernel of each slab on a second stream next to it)"""
         ex = self.ex
+        step = (lambda: ex.step_pipelined(slabs)) if slabs > 0 else (lambda: ex.step(fused=fused))
         if not no_graph:
             try:
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
-                    ex.step(fused=fused)
+                    step()
                 torch.cuda.current_stream().wait_stream(side)
                 torch.cuda.synchronize()
                 self.graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.graph):
-                    ex.step(fused=fused)
+                    step()
                 self.graph.replay()
                 torch.cuda.synchronize()
             except Exception as e:
                 self.graph = None
                 sys.stderr.write(f"[bench] CUDA graph capture failed, running eagerly: {e!r}\n")
-        return self.graph.replay if self.graph is not None else (lambda: ex.step(fused=fused))
+        return self.graph.replay if self.graph is not None else step
 
     def time_steps(self, torch, dist, world, run_step, steps, bytes_per_gpu):
         """device time of `steps` exchanges (CUDA events; max over ranks): L2 flushed between iterations when the
@@ -617,7 +619,8 @@ def run_ours(args, rank, world):
     part_ms = {n: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in marks])) for i, n in enumerate(names)
                if not n.startswith("_")}
 
-    run_step = W.capture(torch, fused, args.no_graph)
+    slabs = args.slabs if (world == 1 and M == 1 and fused) else 0
+    run_step = W.capture(torch, fused, args.no_graph, slabs)
     graph = W.graph
     for _ in range(2):
         run_step()
@@ -643,6 +646,8 @@ def run_ours(args, rank, world):
                            else "reference-order (every stage bit-exact against the oracle)",
                    "surface_step": "unfused (4 remaps + bulk + pack)" if args.unfused else "fused (one kernel)",
                    "launch": "one CUDA graph per exchange" if graph is not None else "eager launches",
+                   "schedule": (f"latitude-slab pipeline: forward solve in {slabs} slabs, surface kernel of each slab on a second "
+                                "(high-priority) stream beside it" if slabs > 0 else "stage after stage on one stream"),
                    "setup_s": round(t_setup, 1)},
         "remapped_cell_fields_per_s": ex.remapped_cell_fields() * value * (world if by_member else 1),
         "exchange_algorithmic_gbytes": bytes_alg[total_key] / 1e9,
@@ -952,6 +957,8 @@ def main():
     ap.add_argument("--fast", action="store_true", help="forward solve with shared reciprocals (<= 1e-12, not bit-exact); "
                     "the default is the reference-order solve, bit-exact against the oracle")
     ap.add_argument("--reference-order", action="store_true", help="(default since round 2; kept for old command lines)")
+    ap.add_argument("--slabs", type=int, default=0, help="1 GPU: pipeline the exchange over this many latitude slabs "
+                    "(surface kernel beside the forward solve on a second stream); 0 = stage after stage")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle-band parity block")
     ap.add_argument("--no-others", action="store_true", help="skip the other_workloads block (BASELINE configs 1-4)")
     ap.add_argument("--no-full-grid", action="store_true", help="reference arm: skip the one whole-grid repetition")

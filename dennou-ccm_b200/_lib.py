@@ -160,10 +160,12 @@ _SIGS = {
                                            C.POINTER(SfcFields), vp]),
     "dccm_sfc_exchange_seg_device": (C.c_int, [vp] * 4 + [C.POINTER(SrcSeg)] * 4 + [C.c_int64, C.c_int64, C.c_int, C.c_double,
                                                vp, vp, C.c_int64, C.POINTER(SfcFields), vp]),
+    "dccm_sfc_exchange_rows_device": (C.c_int, [vp] * 4 + [C.POINTER(SrcSeg)] * 4 + [C.c_int64, C.c_int64, C.c_int, C.c_double,
+                                                vp, vp, C.c_int64, C.POINTER(SfcFields), C.c_int, C.c_int, vp]),
     "dccm_selftest_pmath_device": (C.c_int, [C.c_int, vp, C.c_int64, C.c_double, vp]),
     "dccm_selftest_fast_arith_device": (C.c_int, [vp, vp, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
-    "dccm_sfc_exchange_config": (C.c_int, [C.c_int, C.c_int]),
-    "dccm_sfc_exchange_last_form": (C.c_int, []),
+    "dccm_sfc_exchange_config": (C.c_int, [vp, C.c_int, C.c_int]),
+    "dccm_sfc_exchange_last_form": (C.c_int, [vp]),
     "dccm_ocn_put_assemble_device": (C.c_int, [C.c_int64] + [vp] * 5 + [C.c_double, C.c_double, vp, vp, C.c_int64, vp]),
     "dccm_ocn_get_assemble_device": (C.c_int, [C.c_int64, vp, C.c_int64, C.c_double] + [vp] * 6 + [vp]),
     "dccm_avg_accumulate_device": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp]),
@@ -180,6 +182,8 @@ _SIGS = {
     "dccm_vdiff_backward_host": (C.c_int, [vp] + [f64p] * 4),
     "dccm_vdiff_forward_device": (C.c_int, [vp] + [vp] * 18 + [vp]),
     "dccm_vdiff_backward_device": (C.c_int, [vp] + [vp] * 4 + [vp, vp]),
+    "dccm_vdiff_forward_cols_device": (C.c_int, [vp] + [vp] * 18 + [C.c_int64, C.c_int64, vp]),
+    "dccm_vdiff_backward_cols_device": (C.c_int, [vp] + [vp] * 4 + [vp, C.c_int64, C.c_int64, vp]),
 }
 
 _lib = None

@@ -97,6 +97,7 @@ extern "C" int dccm_atm_legacy_get_assemble_device(int64_t n, const double *o2a_
 extern "C" int dccm_atm_get_assemble_device(int64_t n, const double *a_recv, int64_t ld, double StB, double *SfcTemp,
                                             double *SfcAlbedo, double *SurfHeatFlux, double *SurfH2OVapFlux, void *stream)
 {
+    NvtxRange nvtx("dccm_atm_get_assemble_device");
     if (!a_recv || !SfcTemp) return fail(DCCM_ERR_ARG, "dccm_atm_get_assemble: null buffer");
     if (n < 1 || ld < n) return fail(DCCM_ERR_ARG, "dccm_atm_get_assemble: need 1 <= n <= ld");
     if (!(StB > 0.0)) return fail(DCCM_ERR_ARG, "dccm_atm_get_assemble: StB must be positive");
@@ -111,6 +112,7 @@ extern "C" int dccm_atm_get_assemble_device(int64_t n, const double *a_recv, int
 extern "C" int dccm_atm_store_surf_flx_device(int64_t n, const dccm_atm_sfcflx *f, double LatentHeat, double CpDry,
                                               double DelTime, void *stream)
 {
+    NvtxRange nvtx("dccm_atm_store_surf_flx_device");
     if (!f) return fail(DCCM_ERR_ARG, "dccm_atm_store_surf_flx: null field table");
     if (n < 1) return fail(DCCM_ERR_ARG, "dccm_atm_store_surf_flx: n must be >= 1");
     const void *const *p = reinterpret_cast<const void *const *>(f);

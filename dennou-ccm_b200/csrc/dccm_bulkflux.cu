@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kThreads) bulkflux_kernel(const BulkArgs a)
     f.SfcAlbedo[c + 2 * ss] = o.SfcAlbedo3;
 }
 
-DevBuf g_buf;   // scratch of the host entry point
+thread_local DevBuf g_buf;   // scratch of the host entry point (per calling thread)
 
 // FastArith against the plain operators, element by element: counts[0] = accepted quotients / reciprocals /
 // roots whose bits differ from `a/b`, `1.0/b`, `sqrt(|a|)` (must be 0), counts[1] = operations whose fast path
@@ -120,6 +120,7 @@ extern "C" int dccm_selftest_pmath_device(int which, const double *d_x, int64_t 
 extern "C" int dccm_bulkflux_device(int nx, int ny, int ld, int64_t off, int64_t slot_stride,
                                     const dccm_sfc_fields *f, double sig1, void *stream)
 {
+    NvtxRange nvtx("dccm_bulkflux_device");
     if (!f) return fail(DCCM_ERR_ARG, "dccm_bulkflux: null field table");
     if (nx < 1 || ny < 1 || ld < nx) return fail(DCCM_ERR_ARG, "dccm_bulkflux: bad extents nx=%d ny=%d ld=%d", nx, ny, ld);
     if (!f->WindU || !f->WindV || !f->SfcAirTemp || !f->QVap1 || !f->SDwRFlx || !f->LDwRFlx || !f->ImplCplCoef1 ||
@@ -164,6 +165,7 @@ extern "C" int dccm_bulkflux_get_host(int IA, int JA,
     double *SfcTemp, double *SfcAlbedo, const double *SIceCon,
     const double *Sig1Info, const double *SfcHeight, const double *SfcPress)
 {
+    NvtxRange nvtx("dccm_bulkflux_get_host");
     if (IA < 3 || JA < 3) return fail(DCCM_ERR_ARG, "dccm_bulkflux_get: IA, JA must include the halo (>= 3)");
     int rc = ensure_device();
     if (rc) return rc;
@@ -189,7 +191,7 @@ extern "C" int dccm_bulkflux_get_host(int IA, int JA,
     // Interior rows move in chunks: chunk j+1 on its way in (H2D stream) while the kernel runs on chunk j and
     // chunk j-1 is on its way out (D2H stream).  Inputs are whole rows of the (IA,JA) slots (contiguous), outputs
     // the interior columns only -- halo cells of the caller's arrays are never written, as in the reference.
-    static cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
+    static thread_local cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
     for (auto &ps : pipe)
         if (!ps) DCCM_CUDA_TRY(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
     cudaStream_t sin = pipe[0], sk = pipe[1], sout = pipe[2];

@@ -16,6 +16,17 @@ void set_error(const char *fmt, ...);
 int fail(int code, const char *fmt, ...);
 
 #ifdef __CUDACC__
+}  // namespace dccm
+#include <nvtx3/nvToolsExt.h>
+namespace dccm {
+// NVTX range around every stage of the exchange (SURVEY.md section 5 "Tracing"): shows up in Nsight Systems / ncu
+// timelines under the entry point's name; header-only NVTX v3, a no-op when no tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 #define DCCM_CUDA_TRY(expr)                                                              \
     do {                                                                                 \
         cudaError_t _e = (expr);                                                         \

@@ -60,6 +60,7 @@ struct SfcArgs {
     double sig1;
     int *redo;                    // [0] cells listed, [1] CTAs of the redo kernel done, [2..] (member, cell) pairs
     int redo_cap;
+    int64_t r0, r1;               // surface cells [r0, r1) of every member are evaluated by this launch (whole rows)
 };
 
 // source cell c of a send buffer; SEG: the buffer's boundary rows live in the neighbouring ranks' memory
@@ -363,10 +364,10 @@ template <int MINB, bool SEG, bool FULL>
 __global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_kernel(const SfcArgs a)
 {
     const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    const int64_t nS = a.nS;
-    if (t >= nS * a.M) return;
-    const int m = (int)(t / nS);
-    direct_cell<FastArith, SEG, FULL>(a, m, (int)(t - (int64_t)m * nS));
+    const int64_t nc = a.r1 - a.r0;
+    if (t >= nc * a.M) return;
+    const int m = (int)(t / nc);
+    direct_cell<FastArith, SEG, FULL>(a, m, (int)(a.r0 + t - (int64_t)m * nc));
 }
 
 // ---- redo: the cells the fast arithmetic did not accept (normally none), again with the plain IEEE
@@ -383,10 +384,10 @@ __global__ void __launch_bounds__(kThreads) sfc_exchange_redo_kernel(const SfcAr
             for (int64_t t = t0; t < listed; t += stride)
                 direct_cell<IeeeArith, SEG, FULL>(a, a.redo[2 + 2 * t], a.redo[3 + 2 * t]);
         } else {
-            const int64_t nS = a.nS;
-            for (int64_t t = t0; t < nS * a.M; t += stride) {
-                const int m = (int)(t / nS);
-                direct_cell<IeeeArith, SEG, FULL>(a, m, (int)(t - (int64_t)m * nS));
+            const int64_t nc = a.r1 - a.r0;
+            for (int64_t t = t0; t < nc * a.M; t += stride) {
+                const int m = (int)(t / nc);
+                direct_cell<IeeeArith, SEG, FULL>(a, m, (int)(a.r0 + t - (int64_t)m * nc));
             }
         }
         __syncthreads();
@@ -510,7 +511,7 @@ __device__ __forceinline__ void staged_accumulate(const ZStage &zs, const double
     }
 }
 
-struct StageArgs { int slots_bil, slots_cons, dmin_bil, dmax_bil, dmin_cons, dmax_cons, nxd; };
+struct StageArgs { int slots_bil, slots_cons, dmin_bil, dmax_bil, dmin_cons, dmax_cons, nxd, jD0; };
 
 template <int MINB, bool SEG, bool FULL>
 __global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_staged_kernel(const SfcArgs a, const StageArgs g)
@@ -521,7 +522,7 @@ __global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_staged_kernel(con
     double *tile_cons = tile_bil + g.slots_bil * (13 * kTileW);
     const uint32_t mbar = smem_u32(smem);
     const int tid = threadIdx.x;
-    const int jD = blockIdx.y, i0 = blockIdx.x * kThreads, m = blockIdx.z;
+    const int jD = g.jD0 + blockIdx.y, i0 = blockIdx.x * kThreads, m = blockIdx.z;
     const int nact = min(kThreads, g.nxd - i0);
     const int M = a.M;
 
@@ -591,22 +592,17 @@ Csr csr_of(const dccm_remap *h)
 
 }  // namespace
 
-namespace {
-int g_minb = getenv("DCCM_SFC_MINB") ? atoi(getenv("DCCM_SFC_MINB")) : 5;         // 5 measured best on B200 (profiles/)
-int g_staged = getenv("DCCM_SFC_STAGED") ? atoi(getenv("DCCM_SFC_STAGED")) : 1;
-int g_last_form = -1;
-}  // namespace
-
-extern "C" int dccm_sfc_exchange_config(int staged, int min_blocks)
+extern "C" int dccm_sfc_exchange_config(dccm_remap *as_bil, int staged, int min_blocks)
 {
+    if (!as_bil) return fail(DCCM_ERR_ARG, "dccm_sfc_exchange_config: null handle");
     if (min_blocks >= 0 && min_blocks != 4 && min_blocks != 5 && min_blocks != 6)
         return fail(DCCM_ERR_ARG, "dccm_sfc_exchange_config: min_blocks must be 4, 5 or 6");
-    if (staged >= 0) g_staged = staged ? 1 : 0;
-    if (min_blocks >= 0) g_minb = min_blocks;
+    if (staged >= 0) as_bil->sfc_staged = staged ? 1 : 0;
+    if (min_blocks >= 0) as_bil->sfc_minb = min_blocks;
     return DCCM_OK;
 }
 
-extern "C" int dccm_sfc_exchange_last_form(void) { return g_last_form; }
+extern "C" int dccm_sfc_exchange_last_form(const dccm_remap *as_bil) { return as_bil ? as_bil->sfc_last_form : -1; }
 
 extern "C" int dccm_sfc_exchange_device(const dccm_remap *as_bil, const dccm_remap *as_cons,
                                         const dccm_remap *os_bil, const dccm_remap *os_cons,
@@ -630,6 +626,19 @@ extern "C" int dccm_sfc_exchange_seg_device(const dccm_remap *as_bil, const dccm
                                             int members, double sig1, double *s2a, double *s2o, int64_t s_ld,
                                             const dccm_sfc_fields *full, void *stream)
 {
+    return dccm_sfc_exchange_rows_device(as_bil, as_cons, os_bil, os_cons, sa2s_bil, sa2s_cons, so2s_bil, so2s_cons,
+                                         a_ld, o_ld, members, sig1, s2a, s2o, s_ld, full, 0, -1, stream);
+}
+
+extern "C" int dccm_sfc_exchange_rows_device(const dccm_remap *as_bil, const dccm_remap *as_cons,
+                                             const dccm_remap *os_bil, const dccm_remap *os_cons,
+                                             const dccm_src_seg *sa2s_bil, const dccm_src_seg *sa2s_cons,
+                                             const dccm_src_seg *so2s_bil, const dccm_src_seg *so2s_cons,
+                                             int64_t a_ld, int64_t o_ld,
+                                             int members, double sig1, double *s2a, double *s2o, int64_t s_ld,
+                                             const dccm_sfc_fields *full, int row0, int row1, void *stream)
+{
+    NvtxRange nvtx("dccm_sfc_exchange");
     if (!sa2s_bil || !sa2s_cons || !so2s_bil || !so2s_cons) return fail(DCCM_ERR_ARG, "dccm_sfc_exchange: null buffer");
     const double *a2s_bil = sa2s_bil->own, *a2s_cons = sa2s_cons->own, *o2s_bil = so2s_bil->own, *o2s_cons = so2s_cons->own;
     if (!as_bil || !as_cons || !os_bil || !os_cons) return fail(DCCM_ERR_ARG, "dccm_sfc_exchange: null table handle");
@@ -654,9 +663,18 @@ extern "C" int dccm_sfc_exchange_seg_device(const dccm_remap *as_bil, const dccm
     if (s_ld != 0 && s_ld < nS) return fail(DCCM_ERR_ARG, "dccm_sfc_exchange: s_ld < surface cells");
     if ((a_ld && a_ld < nA) || (o_ld && o_ld < nO)) return fail(DCCM_ERR_ARG, "dccm_sfc_exchange: a_ld / o_ld smaller than the tables' source extent");
     a.nA = a_ld ? a_ld : nA; a.nO = o_ld ? o_ld : nO; a.nS = nS; a.sld = s_ld ? s_ld : nS; a.M = members; a.sig1 = sig1;
-    const int64_t n = (int64_t)nS * members;
+    // rows [row0, row1) of the exchange grid (row1 < 0: all of them); a row range needs the row length, i.e. structured tables
+    a.r0 = 0; a.r1 = nS;
+    if (row1 >= 0) {
+        const int nxr = as_bil->nxd;
+        if (nxr < 1 || nS % nxr != 0 || row0 < 0 || row1 <= row0 || row1 > nS / nxr)
+            return fail(DCCM_ERR_ARG, "dccm_sfc_exchange_rows: rows [%d,%d) of a grid with %d rows of %d cells", row0, row1,
+                        nxr > 0 ? nS / nxr : 0, nxr);
+        a.r0 = (int64_t)row0 * nxr; a.r1 = (int64_t)row1 * nxr;
+    }
+    const int64_t n = (a.r1 - a.r0) * members;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int minb = g_minb, want_staged = g_staged;
+    const int minb = as_bil->sfc_minb, want_staged = as_bil->sfc_staged;
     const bool seg = !(a.a2s_bil.b0 <= 0 && a.a2s_bil.b1 >= (int64_t)INT32_MAX && a.a2s_cons.b0 <= 0 &&
                        a.a2s_cons.b1 >= (int64_t)INT32_MAX && a.o2s_bil.b0 <= 0 && a.o2s_bil.b1 >= (int64_t)INT32_MAX &&
                        a.o2s_cons.b0 <= 0 && a.o2s_cons.b1 >= (int64_t)INT32_MAX);
@@ -684,13 +702,13 @@ extern "C" int dccm_sfc_exchange_seg_device(const dccm_remap *as_bil, const dccm
         g.slots_bil = as_bil->z_max_rows; g.slots_cons = as_cons->z_max_rows;
         g.dmin_bil = as_bil->z_dmin; g.dmax_bil = as_bil->z_dmax;
         g.dmin_cons = as_cons->z_dmin; g.dmax_cons = as_cons->z_dmax;
-        g.nxd = nx;
+        g.nxd = nx; g.jD0 = (int)(a.r0 / nx);
         smem = kStageHdr + sizeof(double) * kTileW * (size_t)(13 * g.slots_bil + 4 * g.slots_cons);
         if (smem > 200 * 1024) staged = false;
     }
-    g_last_form = staged ? 1 : 0;
+    const_cast<dccm_remap *>(as_bil)->sfc_last_form = staged ? 1 : 0;
     if (staged) {
-        dim3 grid((unsigned)((nx + kThreads - 1) / kThreads), (unsigned)as_bil->nyd, (unsigned)members);
+        dim3 grid((unsigned)((nx + kThreads - 1) / kThreads), (unsigned)((a.r1 - a.r0) / nx), (unsigned)members);
 #define DCCM_LAUNCH_STAGED(MB, FULL)                                                                             \
         do {                                                                                                     \
             auto kern = seg ? sfc_exchange_staged_kernel<MB, true, FULL> : sfc_exchange_staged_kernel<MB, false, FULL>; \

@@ -93,6 +93,7 @@ extern "C" int dccm_ocn_put_assemble_device(int64_t n, const double *SeaSfcTemp,
                                             double IceMaskMin, double degC2K, double *o2s_bil, double *o2s_cons,
                                             int64_t ld, void *stream)
 {
+    NvtxRange nvtx("dccm_ocn_put_assemble_device");
     if (n < 1 || ld < n) return fail(DCCM_ERR_ARG, "dccm_ocn_put_assemble: bad extents");
     if (!SeaSfcTemp || !SfcAlbedoAO || !SIceCon || !SIceSfcTempC || !SfcAlbedoAI || !o2s_bil || !o2s_cons)
         return fail(DCCM_ERR_ARG, "dccm_ocn_put_assemble: null pointer");
@@ -108,6 +109,7 @@ extern "C" int dccm_ocn_get_assemble_device(int64_t n, const double *o_recv, int
                                             double *FreshWtFlxS0, double *FreshWtFlx0, double *WindStressXAI,
                                             double *WindStressYAI, double *SfcHFlxAO0, double *DSfcHFlxAODTs, void *stream)
 {
+    NvtxRange nvtx("dccm_ocn_get_assemble_device");
     if (n < 1 || ld < n) return fail(DCCM_ERR_ARG, "dccm_ocn_get_assemble: bad extents");
     if (!o_recv || !FreshWtFlxS0 || !FreshWtFlx0 || !WindStressXAI || !WindStressYAI || !SfcHFlxAO0 || !DSfcHFlxAODTs)
         return fail(DCCM_ERR_ARG, "dccm_ocn_get_assemble: null pointer");

@@ -630,6 +630,7 @@ extern "C" int dccm_remap_apply_device(dccm_remap *h, const double *d_send, int 
 extern "C" int dccm_remap_apply_seg_device(dccm_remap *h, const dccm_src_seg *seg, int sn1,
                                            double *d_recv, int rn1, int rn2, int num_of_data, void *stream)
 {
+    NvtxRange nvtx("dccm_remap_apply_seg_device");
     if (!h || !seg) return fail(DCCM_ERR_ARG, "dccm_remap_apply: null handle");
     const SrcSeg d_send = seg_of(seg);
     if (sn1 < h->n_send || rn1 < h->n_recv)
@@ -660,7 +661,7 @@ extern "C" int dccm_remap_apply_seg_device(dccm_remap *h, const dccm_src_seg *se
     }
     // separable operators re-derive their entries from L1-resident factors, so splitting the fields over more
     // threads costs no table traffic and buys occupancy: blocks of at most kSepFB fields, one block per grid.y
-    static const int kSepFB = getenv("DCCM_SEP_FB") ? atoi(getenv("DCCM_SEP_FB")) : 13;
+    constexpr int kSepFB = 13;
     const bool split_sep = h->kind == 2 && num_of_data > kSepFB;
     if (split_sep) { FB = 2; for (int f : kFB) if (f <= kSepFB) FB = f; }
     int nfb = (num_of_data + FB - 1) / FB;
@@ -702,6 +703,7 @@ extern "C" int dccm_remap_apply_seg_device(dccm_remap *h, const dccm_src_seg *se
 extern "C" int dccm_remap_apply_host(dccm_remap *h, const double *send, int sn1, int sn2,
                                      double *recv, int rn1, int rn2, int num_of_data)
 {
+    NvtxRange nvtx("dccm_remap_apply_host");
     if (!h) return fail(DCCM_ERR_ARG, "dccm_remap_apply: null handle");
     if (num_of_data > sn2) return fail(DCCM_ERR_ARG, "dccm_remap_apply: num_of_data=%d exceeds sn2=%d", num_of_data, sn2);
     if (num_of_data < 0 || num_of_data > rn2)

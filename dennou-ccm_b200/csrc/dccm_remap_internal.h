@@ -63,5 +63,9 @@ struct dccm_remap {
     // the A->S bilinear handle is the one used.  Allocated at creation (never inside a stream capture).
     static constexpr int kRedoCap = 16384;
     int *d_redo = nullptr;         // [count, done, (member, cell) x kRedoCap]
+    // options / bookkeeping of the fused surface kernel, kept on the A->S bilinear handle of the call (per handle, so
+    // two exchanges configured differently do not see each other): form requested (1 staged, 0 direct), CTAs per SM
+    // the kernel is built for (4, 5 or 6) and the form the last call on this handle took (-1: none yet)
+    int sfc_staged = 1, sfc_minb = 5, sfc_last_form = -1;
     dccm::DevBuf send_buf, recv_buf;
 };

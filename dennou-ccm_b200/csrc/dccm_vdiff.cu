@@ -537,6 +537,7 @@ extern "C" int dccm_vdiff_forward_device(dccm_vdiff *h,
     const double *DiffV, const double *DiffT, const double *DiffQ,
     double *DU, double *DV, double *DT, double *DQ, double *Coef1, double *Coef2, void *stream)
 {
+    NvtxRange nvtx("dccm_vdiff_forward_device");
     if (!h) return fail(DCCM_ERR_ARG, "dccm_vdiff_forward: null handle");
     return forward_range(h, FX, FY, FH, FQ, Press, zExner, rExner, VirTemp, Height, DiffV, DiffT, DiffQ,
                          DU, DV, DT, DQ, Coef1, Coef2, 0, h->NC, reinterpret_cast<cudaStream_t>(stream));
@@ -545,8 +546,34 @@ extern "C" int dccm_vdiff_forward_device(dccm_vdiff *h,
 extern "C" int dccm_vdiff_backward_device(dccm_vdiff *h, double *DU, double *DV, double *DT, double *DQ,
                                           const double *level1, void *stream)
 {
+    NvtxRange nvtx("dccm_vdiff_backward_device");
     if (!h) return fail(DCCM_ERR_ARG, "dccm_vdiff_backward: null handle");
     return backward_range(h, DU, DV, DT, DQ, level1, 0, h->NC, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// columns [c0, c1) only: the pieces of a latitude-slab pipeline (exchange.SurfaceExchange.step_pipelined)
+extern "C" int dccm_vdiff_forward_cols_device(dccm_vdiff *h,
+    const double *FX, const double *FY, const double *FH, const double *FQ,
+    const double *Press, const double *zExner, const double *rExner,
+    const double *VirTemp, const double *Height,
+    const double *DiffV, const double *DiffT, const double *DiffQ,
+    double *DU, double *DV, double *DT, double *DQ, double *Coef1, double *Coef2,
+    int64_t c0, int64_t c1, void *stream)
+{
+    NvtxRange nvtx("dccm_vdiff_forward_cols_device");
+    if (!h) return fail(DCCM_ERR_ARG, "dccm_vdiff_forward: null handle");
+    if (c0 < 0 || c1 > h->NC || c0 >= c1) return fail(DCCM_ERR_ARG, "dccm_vdiff_forward_cols: bad column range");
+    return forward_range(h, FX, FY, FH, FQ, Press, zExner, rExner, VirTemp, Height, DiffV, DiffT, DiffQ,
+                         DU, DV, DT, DQ, Coef1, Coef2, c0, c1, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dccm_vdiff_backward_cols_device(dccm_vdiff *h, double *DU, double *DV, double *DT, double *DQ,
+                                               const double *level1, int64_t c0, int64_t c1, void *stream)
+{
+    NvtxRange nvtx("dccm_vdiff_backward_cols_device");
+    if (!h) return fail(DCCM_ERR_ARG, "dccm_vdiff_backward: null handle");
+    if (c0 < 0 || c1 > h->NC || c0 >= c1) return fail(DCCM_ERR_ARG, "dccm_vdiff_backward_cols: bad column range");
+    return backward_range(h, DU, DV, DT, DQ, level1, c0, c1, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int dccm_vdiff_forward_host(dccm_vdiff *h,
@@ -556,6 +583,7 @@ extern "C" int dccm_vdiff_forward_host(dccm_vdiff *h,
     const double *DiffV, const double *DiffT, const double *DiffQ,
     double *DU, double *DV, double *DT, double *DQ, double *Coef1, double *Coef2)
 {
+    NvtxRange nvtx("dccm_vdiff_forward_host");
     if (!h) return fail(DCCM_ERR_ARG, "dccm_vdiff_forward: null handle");
     const size_t NC = (size_t)h->NC, K = h->kmax, nc = h->ncmax;
     const size_t half = NC * (K + 1), full = NC * K;
@@ -606,6 +634,7 @@ extern "C" int dccm_vdiff_forward_host(dccm_vdiff *h,
 
 extern "C" int dccm_vdiff_backward_host(dccm_vdiff *h, double *DU, double *DV, double *DT, double *DQ)
 {
+    NvtxRange nvtx("dccm_vdiff_backward_host");
     if (!h) return fail(DCCM_ERR_ARG, "dccm_vdiff_backward: null handle");
     const size_t NC = (size_t)h->NC, K = h->kmax, nc = h->ncmax, full = NC * K;
     int rc = h->out_buf.reserve(sizeof(double) * (full * (3 + nc) + NC * 8));

@@ -65,6 +65,18 @@ class SfcImplicitCoupling:
             *[L.tptr(out[k]) for k in ("DUDt", "DVDt", "DTempDt", "DQMixDt", "ImplCplCoef1", "ImplCplCoef2")],
             L.current_stream()))
 
+    def forward_cols_device(self, inp, out, c0, c1):
+        """columns [c0, c1) only (latitude-slab pipelining)"""
+        L.check(L.lib().dccm_vdiff_forward_cols_device(
+            self._h, *[L.tptr(inp[k]) for k in IN_ORDER],
+            *[L.tptr(out[k]) for k in ("DUDt", "DVDt", "DTempDt", "DQMixDt", "ImplCplCoef1", "ImplCplCoef2")],
+            int(c0), int(c1), L.current_stream()))
+
+    def backward_cols_device(self, out, level1, c0, c1):
+        L.check(L.lib().dccm_vdiff_backward_cols_device(
+            self._h, *[L.tptr(out[k]) for k in ("DUDt", "DVDt", "DTempDt", "DQMixDt")],
+            L.tptr(level1), int(c0), int(c1), L.current_stream()))
+
     def backward_device(self, out, level1=None):
         L.check(L.lib().dccm_vdiff_backward_device(
             self._h, *[L.tptr(out[k]) for k in ("DUDt", "DVDt", "DTempDt", "DQMixDt")],

@@ -214,6 +214,13 @@ class SurfaceExchange:
             C.c_void_p(self.s2o.data_ptr() + 8 * self.offS), self.s2a.shape[1], full, L.current_stream()))
         self.launches += 2            # the surface kernel + the (normally empty) IEEE redo kernel
 
+    def configure_sfc(self, staged=-1, min_blocks=-1):
+        """form of the fused surface kernel for THIS exchange (dccm_sfc_exchange_config; per handle, not process-wide)"""
+        L.check(L.lib().dccm_sfc_exchange_config(self.ops["as_bil"]._h, staged, min_blocks))
+
+    def sfc_last_form(self):
+        return int(L.lib().dccm_sfc_exchange_last_form(self.ops["as_bil"]._h))
+
     def remap_from_sfc(self):
         M = self.M
         self.ops["sa_cons"].apply(self.s2a[:4 * M], self.a_recv[:4 * M])
@@ -227,6 +234,70 @@ class SurfaceExchange:
         lvl1 = self.a_recv[5 * M:9 * M].view(4, M * nA)
         self.vdiff.backward_device(self.tend, lvl1)
         self.launches += 1
+
+    # -- latitude-slab pipeline: the issue-bound surface kernel next to the HBM-bound forward solve ------------------
+    def _slab_plan(self, nslab):
+        """S-row slabs cut at ATM cell edges, and for each the ATM rows whose forward solve it reads (sharding.BandPlan
+        used for its row bookkeeping only -- everything stays in this object's buffers, no halo moves)"""
+        key = ("slabs", nslab)
+        if getattr(self, "_slab_cache", None) is None or self._slab_cache[0] != key:
+            from .sharding import BandPlan
+            plan = BandPlan(self.A, self.O, self.S, nslab)
+            self._slab_cache = (key, [(plan.bands["A"][k], plan.bands["S"][k], plan.ext["A"][k]) for k in range(nslab)])
+        return self._slab_cache[1]
+
+    def _sfc_rows(self, row0, row1):
+        import ctypes as C
+        o = self.ops
+        if getattr(self, "_whole_seg", None) is None:
+            def seg(t):
+                s = L.SrcSeg()
+                s.lo = s.own = s.hi = t.data_ptr()
+                s.b0, s.b1 = 0, 2 ** 63 - 1
+                return s
+            self._whole_seg = [seg(t) for t in (self.a2s_bil, self.a2s_cons, self.o2s_bil, self.o2s_cons)]
+        sg = self._whole_seg
+        L.check(L.lib().dccm_sfc_exchange_rows_device(
+            o["as_bil"]._h, o["as_cons"]._h, o["os_bil"]._h, o["os_cons"]._h,
+            C.byref(sg[0]), C.byref(sg[1]), C.byref(sg[2]), C.byref(sg[3]), 0, 0,
+            self.M, float(self.sig1), C.c_void_p(self.s2a.data_ptr()), C.c_void_p(self.s2o.data_ptr()),
+            self.s2a.shape[1], None, int(row0), int(row1), L.current_stream()))
+        self.launches += 2
+
+    def step_pipelined(self, nslab=16):
+        """One exchange with the forward solve cut into `nslab` latitude slabs on the current stream and the fused
+        surface kernel of every slab launched on a second, high-priority stream as soon as the ATM rows it reads are
+        solved: the surface kernel is instruction-issue bound, the column solve HBM bound, so run side by side they
+        share the SMs instead of taking turns.  Same kernels on row ranges -> same bits as step()."""
+        torch = self.torch
+        assert not self.sharded and self.M == 1, "slab pipelining: single-GPU, single-member exchanges"
+        slabs = self._slab_plan(nslab)
+        main = torch.cuda.current_stream(self.dev)
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(self.dev, priority=-1)
+        side, im = self._side, self.A.im
+        M, nA = self.M, self.A.n
+        out = dict(self.tend)
+        out["ImplCplCoef1"] = self.a2s_bil[5 * M:9 * M].view(4, M * nA)
+        out["ImplCplCoef2"] = self.a2s_bil[9 * M:13 * M].view(4, M * nA)
+        start = torch.cuda.Event(); start.record(main)
+        side.wait_event(start)                      # the side stream joins the work (and any stream capture) here
+        k_sfc = 0
+        for k, ((a0, a1), _, _) in enumerate(slabs):
+            self.vdiff.forward_cols_device(self.col_in, out, a0 * im, a1 * im)
+            self.launches += 1
+            ev = None
+            while k_sfc < nslab and (slabs[k_sfc][2][1] <= a1 or k == nslab - 1):
+                if ev is None:
+                    ev = torch.cuda.Event(); ev.record(main)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    self._sfc_rows(*slabs[k_sfc][1])
+                k_sfc += 1
+        done = torch.cuda.Event(); done.record(side)
+        main.wait_event(done)
+        self.remap_from_sfc()
+        self.backward()
 
     def halo_to_sfc(self):
         """hook: sharded runs exchange the halo rows of the ATM/OCN send buffers here"""

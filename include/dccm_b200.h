@@ -289,13 +289,15 @@ int dccm_sfc_exchange_device(const dccm_remap *as_bil, const dccm_remap *as_cons
                              int members, double sig1, double *s2a, double *s2o, int64_t s_ld,
                              const dccm_sfc_fields *full, void *stream);
 
-/* Which form of the kernel the next calls launch: staged = 1 (default) lets a CTA bring its atmosphere source
- * rows to shared memory with TMA bulk copies whenever both A->S tables are zonal stencils, 0 forces the
- * per-thread global gathers; min_blocks = CTAs per SM the kernel is compiled for (4, 5 or 6).  A negative value
- * keeps the current setting.  Results are bit-identical in every configuration. */
-int dccm_sfc_exchange_config(int staged, int min_blocks);
-/* 1 if the last dccm_sfc_exchange_*_device call launched the staged form, 0 if the direct one */
-int dccm_sfc_exchange_last_form(void);
+/* Which form of the kernel the calls made with this A->S bilinear handle launch (the setting lives on the handle:
+ * no process-wide state): staged = 1 (default) lets a CTA bring its atmosphere source rows to shared memory with
+ * TMA bulk copies whenever both A->S tables are zonal stencils, 0 forces the per-thread global gathers;
+ * min_blocks = CTAs per SM the kernel is compiled for (4, 5 or 6).  A negative value keeps the current setting.
+ * Results are bit-identical in every configuration.  A handle (its redo list, these options) serves one stream
+ * at a time: concurrent exchanges use separate handles. */
+int dccm_sfc_exchange_config(dccm_remap *as_bil, int staged, int min_blocks);
+/* 1 if the last dccm_sfc_exchange_*_device call with this handle launched the staged form, 0 the direct one, -1 none yet */
+int dccm_sfc_exchange_last_form(const dccm_remap *as_bil);
 
 /* same, source buffers given as peer-mapped segments; a_ld / o_ld = cells per row of the ATM / OCN
  * send buffers (0 = the tables' source extent) */
@@ -306,6 +308,16 @@ int dccm_sfc_exchange_seg_device(const dccm_remap *as_bil, const dccm_remap *as_
                                  int64_t a_ld, int64_t o_ld,
                                  int members, double sig1, double *s2a, double *s2o, int64_t s_ld,
                                  const dccm_sfc_fields *full, void *stream);
+/* same for rows [row0, row1) of the exchange grid only (row1 < 0: every row): lets a caller pipeline the exchange over
+ * latitude slabs -- the surface kernel of slab k next to the column solve of slab k+2 on another stream
+ * (exchange.SurfaceExchange.step_pipelined).  Needs structured A->S tables (row length known). */
+int dccm_sfc_exchange_rows_device(const dccm_remap *as_bil, const dccm_remap *as_cons,
+                                  const dccm_remap *os_bil, const dccm_remap *os_cons,
+                                  const dccm_src_seg *a2s_bil, const dccm_src_seg *a2s_cons,
+                                  const dccm_src_seg *o2s_bil, const dccm_src_seg *o2s_cons,
+                                  int64_t a_ld, int64_t o_ld,
+                                  int members, double sig1, double *s2a, double *s2o, int64_t s_ld,
+                                  const dccm_sfc_fields *full, int row0, int row1, void *stream);
 
 /* ------------------------------------------------------------------ implicit coupling (K3/K4)
  * Replaces dcpam_sfc_implicit_coupling_mod, ref atm/dcpam_sfc_implicit_coupling_mod.f90. */
@@ -348,6 +360,19 @@ int dccm_vdiff_forward_device(dccm_vdiff *h,
 int dccm_vdiff_backward_device(dccm_vdiff *h,
     double *xyz_DUDt, double *xyz_DVDt, double *xyz_DTempDt, double *xyzf_DQMixDt,
     const double *level1, void *stream);
+
+/* the same two calls for columns [c0, c1) only (0-based, half open): the pieces of a latitude-slab pipeline */
+int dccm_vdiff_forward_cols_device(dccm_vdiff *h,
+    const double *xyr_MomFluxX, const double *xyr_MomFluxY, const double *xyr_HeatFlux,
+    const double *xyrf_QMixFlux,
+    const double *xyr_Press, const double *xyz_Exner, const double *xyr_Exner,
+    const double *xyr_VirTemp, const double *xyz_Height,
+    const double *xyr_VelDiffCoef, const double *xyr_TempDiffCoef, const double *xyr_QMixDiffCoef,
+    double *xyz_DUDt, double *xyz_DVDt, double *xyz_DTempDt, double *xyzf_DQMixDt,
+    double *xya_ImplCplCoef1, double *xya_ImplCplCoef2, int64_t c0, int64_t c1, void *stream);
+int dccm_vdiff_backward_cols_device(dccm_vdiff *h,
+    double *xyz_DUDt, double *xyz_DVDt, double *xyz_DTempDt, double *xyzf_DQMixDt,
+    const double *level1, int64_t c0, int64_t c1, void *stream);
 
 /* ------------------------------------------------------------------ ocean / sea-ice side
  * Element-wise work of ocn/dccm_ocn_mod.f90 either side of the remaps, on the device.

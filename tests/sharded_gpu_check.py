@@ -51,7 +51,7 @@ def main():
     if not torch.equal(ex.tend["DQMixDt"], full.tend["DQMixDt"][:, :, ca]): bad.append("DQMixDt")
     t = torch.tensor([len(bad)], device=dev)
     dist.all_reduce(t)
-    form = {1: "staged", 0: "direct"}.get(dccm.lib().dccm_sfc_exchange_last_form(), "?")
+    form = {1: "staged", 0: "direct"}.get(ex.sfc_last_form(), "?")
     print(f"rank {rank}/{world} [{cls.__name__} halo={halo}, fused surface kernel: {form}]: bands A{(a0, a1)} O{(o0, o1)} mismatches {bad}", flush=True)
     dist.destroy_process_group()
     sys.exit(1 if int(t.item()) else 0)

@@ -575,7 +575,7 @@ def test_fused_surface_kernel_staged_and_direct_forms_bit_exact(gpu, orc, dccm, 
         for staged in (1, 0):
             for minb in (5, 4, 6):
                 for full in (False, True):
-                    L.check(L.lib().dccm_sfc_exchange_config(staged, minb))
+                    ex.configure_sfc(staged, minb)
                     ex.s2a.fill_(float("nan")); ex.s2o.fill_(float("nan"))
                     if full:
                         for v in ex.sfc_out.values():
@@ -583,7 +583,7 @@ def test_fused_surface_kernel_staged_and_direct_forms_bit_exact(gpu, orc, dccm, 
                         ex.s_obil[2 * M:].fill_(float("nan")); ex.s_ocons[3 * M:].fill_(float("nan"))
                     ex.sfc_fused(store_full=full)
                     torch.cuda.synchronize()
-                    forms.append(L.lib().dccm_sfc_exchange_last_form())
+                    forms.append(ex.sfc_last_form())
                     tag = f"staged={staged} minb={minb} full={full}"
                     assert torch.equal(ex.s2a, want["s2a"]), tag + " s2a"
                     assert torch.equal(ex.s2o, want["s2o"]), tag + " s2o"
@@ -594,7 +594,7 @@ def test_fused_surface_kernel_staged_and_direct_forms_bit_exact(gpu, orc, dccm, 
                         assert torch.equal(ex.s_obil, want_full["s_obil"]), tag
                         assert torch.equal(ex.s_ocons, want_full["s_ocons"]), tag
     finally:
-        L.check(L.lib().dccm_sfc_exchange_config(1, 5))
+        ex.configure_sfc(1, 5)
     # every A->S table of these grid pairs is a zonal stencil on even longitudes: the staged form must have run
     assert forms[:6] == [1] * 6 and forms[6:] == [0] * 6, forms
 
@@ -631,13 +631,13 @@ def test_fused_surface_kernel_redo_list_for_out_of_range_operands(gpu, orc, dccm
             want = (ex.s2a.clone(), ex.s2o.clone())
             assert inputs is clean or not bool(torch.isfinite(want[1]).all())
             for staged in (1, 0):
-                L.check(L.lib().dccm_sfc_exchange_config(staged, 5))
+                ex.configure_sfc(staged, 5)
                 ex.s2a.zero_(); ex.s2o.zero_()
                 ex.sfc_fused()
                 torch.cuda.synchronize()
                 assert same(ex.s2a, want[0]) and same(ex.s2o, want[1]), (how, staged, inputs is clean)
     finally:
-        L.check(L.lib().dccm_sfc_exchange_config(1, 5))
+        ex.configure_sfc(1, 5)
 
 
 @pytest.mark.parametrize("name,members", [("T21_1deg", 1), ("T106_1deg", 2), ("T42_T42", 1)])
@@ -667,7 +667,7 @@ def test_exchange_from_grids_equals_exchange_from_tables(gpu, orc, dccm, S, name
     ex.set_inputs(*inputs)
     try:
         for fused, staged in ((False, 1), (True, 1), (True, 0)):
-            L.check(L.lib().dccm_sfc_exchange_config(staged, 5))
+            ex.configure_sfc(staged, 5)
             for t in (ex.s2a, ex.s2o, ex.a_recv, ex.o_recv):
                 t.fill_(float("nan"))
             ex.step(fused=fused)
@@ -677,7 +677,7 @@ def test_exchange_from_grids_equals_exchange_from_tables(gpu, orc, dccm, S, name
             for k in ex.tend:
                 assert torch.equal(ex.tend[k], ref.tend[k]), (k, fused, staged)
     finally:
-        L.check(L.lib().dccm_sfc_exchange_config(1, 5))
+        ex.configure_sfc(1, 5)
 
 
 def test_exchange_ensemble_members_match_single_runs(gpu, orc, dccm, S):

@@ -46,15 +46,15 @@ def test_fused_surface_kernel_with_second_order_atmosphere_table(gpu, orc, dccm,
     forms = []
     try:
         for staged in (1, 0):
-            L.check(L.lib().dccm_sfc_exchange_config(staged, 5))
+            ex.configure_sfc(staged, 5)
             ex.s2a.fill_(float("nan")); ex.s2o.fill_(float("nan"))
             ex.sfc_fused()
             torch.cuda.synchronize()
-            forms.append(L.lib().dccm_sfc_exchange_last_form())
+            forms.append(ex.sfc_last_form())
             assert torch.equal(ex.s2a, want["s2a"]), f"staged={staged} s2a"
             assert torch.equal(ex.s2o, want["s2o"]), f"staged={staged} s2o"
     finally:
-        L.check(L.lib().dccm_sfc_exchange_config(1, 5))
+        ex.configure_sfc(1, 5)
     print(name, "forms launched (1 = staged):", forms)
     assert forms[1] == 0
 
@@ -127,3 +127,47 @@ def test_atm_legacy_get_side_assembly(gpu, orc, dccm):
     assert np.array_equal(got["SurfAlbedo"].cpu().numpy(), r[1, :n])
     assert np.array_equal(tb_dev.cpu().numpy(), tb_want)
 
+
+
+@pytest.mark.parametrize("name,nslab", [("T21_1deg", 4), ("T106_1deg", 7), ("T42_T42", 16)])
+def test_slab_pipelined_step_equals_the_plain_step(gpu, orc, dccm, S, name, nslab):
+    """SurfaceExchange.step_pipelined (forward solve in latitude slabs, the fused surface kernel of every slab on a
+    second stream as soon as the rows it reads are solved; row-range launches of the same kernels) gives the bits of
+    step(), eagerly and replayed from a CUDA graph."""
+    import torch
+    from util import pair
+    X = importlib.import_module("dennou-ccm_b200.exchange")
+    A, O, Sx = pair(orc, dccm, name)
+    K = 26
+    ex = X.SurfaceExchange(A, O, Sx, K, 1, 1, fast=False, device=gpu)
+    col, atm, ocn = S.column_inputs(torch, A, K, 1, dev=gpu), S.atm_surface_fields(torch, A, dev=gpu), S.ocn_surface_fields(torch, O, dev=gpu)
+    ex.set_inputs(col, {k: v[None] for k, v in atm.items()}, {k: v[None] for k, v in ocn.items()})
+    ex.step()
+    torch.cuda.synchronize()
+    names = ("s2a", "s2o", "a_recv", "o_recv")
+    keep = {k: getattr(ex, k).clone() for k in names}
+    keep.update({k: v.clone() for k, v in ex.tend.items()})
+
+    def check(tag):
+        torch.cuda.synchronize()
+        for k in names:
+            assert torch.equal(getattr(ex, k), keep[k]), (tag, k)
+        for k, v in ex.tend.items():
+            assert torch.equal(v, keep[k]), (tag, k)
+
+    def scrub():
+        for k in names:
+            getattr(ex, k).fill_(float("nan"))
+        for v in ex.tend.values():
+            v.fill_(float("nan"))
+    scrub(); ex.step_pipelined(nslab); check("eager")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ex.step_pipelined(nslab)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ex.step_pipelined(nslab)
+    scrub(); g.replay(); check("graph")
