@@ -53,7 +53,7 @@ class SurfaceExchange:
     """
 
     def __init__(self, A, O, S, kmax, ncmax=1, index_h2ovap=1, tabs=None, consts=None, members=1,
-                 fast=True, device=None, layout=None, structured=True, ops=None):
+                 fast=False, device=None, layout=None, structured=True, ops=None):
         """layout (sharded runs, sharding.py): {"A"|"S"|"O": (n_own, n_ext, off)} -- cells this rank
         owns, cells of its source buffers (own + halo rows) and where the owned cells start in them;
         A/O/S are then objects with .im/.jm/.n of the LOCAL band."""

@@ -24,7 +24,7 @@ OCN_SFC = ("SfcTempO", "SfcTempI", "SIceCon", "SfcAlbedoO", "SfcAlbedoI")
 
 
 class HostPipelinedExchange:
-    def __init__(self, A, O, S, kmax, ncmax=1, index_h2ovap=1, nslab=12, device=None, fast=True):
+    def __init__(self, A, O, S, kmax, ncmax=1, index_h2ovap=1, nslab=12, device=None, fast=False):
         import torch
         self.torch = torch
         self.n = nslab

@@ -709,3 +709,120 @@ def test_time_average_is_the_mean_of_the_puts(orc):
     got = orc.time_average(puts)
     assert np.array_equal(got, (((puts[0] + puts[1]) + puts[2]) + puts[3]) / 4.0)
     assert np.array_equal(orc.time_average(puts[:1]), puts[0])
+
+
+def test_bulk_flux_whole_field_against_the_scalar_restatement(orc, dccm, S):
+    """The independent scalar reading of DSFCM_Util_SfcBulkFlux_Get (_bulk_one_column: written from the equations,
+    libm exp / log / **) on EVERY column of a synthetic T42 surface field -- 8192 columns from ice-free tropics to
+    full ice cover, both Louis branches -- against the C oracle: fluxes, transfer coefficients, the implicit update
+    (DelVarImplCPL, ref :353-368), the corrected fluxes (:370-380), the net fluxes and dF/dTs (:384-415).  The two
+    differ in exp / log / ** (portable sequences vs libm, <= 1 ulp) and in association, which the routine's
+    conditioning amplifies: the bar is 5e-12 of max(|x|, 1e-3 max|layer|), three decades below any restatement error."""
+    from exchange_ref import floor_rel
+    g = dccm.tables.get_LonLatGrid(128, 64)
+    IA, JA, inp = _bulk_inputs(S, g)
+    got = orc.bulkflux(IA, JA, inp)
+    I = (slice(1, -1), slice(1, -1))
+    f = lambda k, *idx: inp[k][idx][I].reshape(-1) if idx else inp[k][I].reshape(-1)
+    u, v, T1, q1, sw, lw, ps, ice = (f(k) for k in ("WindU", "WindV", "SfcAirTemp", "QVap1", "SDwRFlx", "LDwRFlx", "SfcPress", "SIceCon"))
+    c1 = [f("ImplCplCoef1", k) for k in range(4)]
+    c2 = [f("ImplCplCoef2", k) for k in range(4)]
+    ts = [f("SfcTemp", n) for n in range(2)]
+    alb = [f("SfcAlbedo", n) for n in range(2)]
+    sig1 = float(inp["Sig1Info"][0])
+    n = u.size
+    names = {"taux": "WindStressX", "tauy": "WindStressY", "sh": "SenHFlx", "evap": "QVapMFlx", "lh": "LatHFlx",
+             "lwup": "LUwRFlx", "swup": "SUwRFlx", "cv": "SfcVelTransCoef", "ct": "SfcTempTransCoef", "cq": "SfcQVapTransCoef"}
+    want = {name: np.zeros((3, n)) for name in names.values()}
+    want.update(DelVarImplCPL=np.zeros((4, n)), SfcHFlx_ns=np.zeros((2, n)), SfcHFlx_sr=np.zeros((2, n)),
+                DSfcHFlxDTs=np.zeros((2, n)), SfcTemp3=np.zeros((1, n)), SfcAlbedo3=np.zeros((1, n)))
+    for c in range(n):
+        out, delta, net, Ts4, alb3 = _bulk_one_column(u[c], v[c], T1[c], q1[c], sw[c], lw[c], ps[c], ice[c],
+                                                      [x[c] for x in c1], [x[c] for x in c2], (ts[0][c], ts[1][c]),
+                                                      (alb[0][c], alb[1][c]), sig1)
+        for k, name in names.items():
+            want[name][:, c] = out[k]
+        want["DelVarImplCPL"][:, c] = delta
+        want["SfcHFlx_ns"][:, c], want["SfcHFlx_sr"][:, c], want["DSfcHFlxDTs"][:, c] = net["ns"], net["sr"], net["dfdt"]
+        want["SfcTemp3"][0, c], want["SfcAlbedo3"][0, c] = Ts4, alb3
+    flat = lambda a, rows: a[:rows][(slice(None),) + I].reshape(rows, -1)
+    worst = {}
+    for name, w in want.items():
+        if name == "SfcTemp3":
+            a = got["SfcTemp"][2:3][(slice(None),) + I].reshape(1, -1)
+        elif name == "SfcAlbedo3":
+            a = got["SfcAlbedo"][2:3][(slice(None),) + I].reshape(1, -1)
+        else:
+            rows = 2 if name == "LatHFlx" else w.shape[0]        # reference defect B-1: LatHFlx slot 3 undefined
+            a, w = flat(got[name], rows), w[:rows]
+        worst[name] = floor_rel(a, w)
+    print({k: float("%.1e" % x) for k, x in worst.items()})
+    assert max(worst.values()) <= 5e-12, worst
+    assert (ice == 0.0).sum() > 1000 and (ice > 0.9).sum() > 100
+
+
+def test_vdiff_matrices_and_sweep_in_exact_rational_arithmetic(orc, dccm, S):
+    """Second route for the three tridiagonal systems (ref atm/dcpam_sfc_implicit_coupling_mod.f90:207-293) and their
+    top-down sweep (:388-400): the matrix rows are rebuilt in Python from the discretised diffusion equation, converted
+    to exact rationals, swept exactly, and the oracle's stored diagonals b'(k), swept right-hand sides r'(k) and the
+    coupling coefficients Coef1 / Coef2 (:344-376) must equal the exact values to 1e-12 -- rounding is the only
+    difference an arithmetic-for-arithmetic restatement may show."""
+    from fractions import Fraction as Fr
+    g = dccm.tables.get_LonLatGrid(8, 2)
+    K, nc, iq = 9, 2, 2
+    inp = S.column_inputs(np, g, K, nc)
+    vd = orc.VDiff(g.im, g.jm, K, nc, iq, S.GRAV, S.CPDRY, S.GASRDRY, S.DELTIME)
+    out = vd.forward(inp)
+    diag = {"UV": vd.diag(0), "T": vd.diag(1), "Q": vd.diag(2)}
+    P, Tv, H, rEx, zEx = inp["Press"], inp["VirTemp"], inp["Height"], inp["rExner"], inp["zExner"]
+    cp, grav, R, dt2 = Fr(S.CPDRY), Fr(S.GRAV), Fr(S.GASRDRY), 2 * Fr(S.DELTIME)
+    rel = lambda a, b: abs(float(a) - b) / max(abs(float(a)), 1e-300)
+    worst = 0.0
+    for c in range(g.n):
+        x = lambda a, k: Fr(float(a[k, c]))
+        geom = [Fr(0)] * (K + 1)
+        for k in range(1, K):
+            geom[k] = x(P, k) / (R * x(Tv, k)) / (x(H, k) - x(H, k - 1))
+        T = {"UV": [x(inp["VelDiffCoef"], k) * geom[k] for k in range(K + 1)],
+             "T": [x(inp["TempDiffCoef"], k) * geom[k] for k in range(K + 1)],
+             "Q": [x(inp["QMixDiffCoef"], k) * geom[k] for k in range(K + 1)]}
+        rhs = {"U": [-(x(inp["MomFluxX"], k) - x(inp["MomFluxX"], k - 1)) for k in range(1, K + 1)],
+               "V": [-(x(inp["MomFluxY"], k) - x(inp["MomFluxY"], k - 1)) for k in range(1, K + 1)],
+               "T": [-(x(inp["HeatFlux"], k) - x(inp["HeatFlux"], k - 1)) for k in range(1, K + 1)],
+               "Q": [-(Fr(float(inp["QMixFlux"][iq - 1, k, c])) - Fr(float(inp["QMixFlux"][iq - 1, k - 1, c]))) for k in range(1, K + 1)]}
+        for sysname, rnames in (("UV", ("U", "V")), ("T", ("T",)), ("Q", ("Q",))):
+            a, b, cc = [Fr(0)] * (K + 1), [Fr(0)] * (K + 1), [Fr(0)] * (K + 1)      # sub / main / super diagonal, rows 1..K
+            for k in range(1, K + 1):
+                mass = -(x(P, k) - x(P, k - 1)) / grav / dt2
+                t_lo, t_hi = T[sysname][k - 1], T[sysname][k]
+                if sysname == "T":
+                    b[k] = cp * mass + cp * x(rEx, k - 1) / x(zEx, k - 1) * t_lo + cp * x(rEx, k) / x(zEx, k - 1) * t_hi
+                    a[k] = -cp * x(rEx, k - 1) / x(zEx, k - 2) * t_lo if k > 1 else Fr(0)
+                    cc[k] = -cp * x(rEx, k) / x(zEx, k) * t_hi if k < K else Fr(0)
+                else:
+                    b[k], a[k], cc[k] = mass + t_lo + t_hi, -t_lo, -t_hi
+            # top-down sweep (:388-400): row K first, then K-1 .. 2
+            bp = [Fr(0)] * (K + 2)
+            rp = {r: [Fr(0)] * (K + 2) for r in rnames}
+            bp[K] = b[K] / a[K]
+            for r in rnames:
+                rp[r][K] = rhs[r][K - 1] / a[K]
+            for k in range(K - 1, 1, -1):
+                den = a[k] * bp[k + 1]
+                bp[k] = (b[k] * bp[k + 1] - cc[k]) / den
+                for r in rnames:
+                    rp[r][k] = (rhs[r][k - 1] * bp[k + 1] - cc[k] * rp[r][k + 1]) / den
+            for k in range(2, K + 1):
+                worst = max(worst, rel(bp[k], diag[sysname][k - 1, c]))
+            arr = {"U": out["DUDt"], "V": out["DVDt"], "T": out["DTempDt"], "Q": out["DQMixDt"][iq - 1]}
+            for r in rnames:
+                for k in range(2, K + 1):
+                    worst = max(worst, rel(rp[r][k], arr[r][k - 1, c]))
+                slot = {"U": 0, "V": 1, "T": 2, "Q": 3}[r]
+                # Coef1 = m1 + K1 + K1/b'2 in the reference's notation == b1 - a2... written from the reduced row 1:
+                # (b1 - c1 / b'2) x1 = r1 - c1 r'2 / b'2
+                coef1 = b[1] - cc[1] / bp[2]
+                coef2 = rhs[r][0] - cc[1] * rp[r][2] / bp[2]
+                worst = max(worst, rel(coef1, out["ImplCplCoef1"][slot, c]), rel(coef2, out["ImplCplCoef2"][slot, c]))
+    print("worst relative distance from the exact rational sweep: %.2e" % worst)
+    assert worst <= 1e-12
