@@ -20,17 +20,17 @@
  *   pm_exp(x):  NaN -> NaN; x > 709.782712893384 -> +Inf; x < -745.1332191019412 -> +0
  *       k  = trunc(x * INVLN2 + (x < 0 ? -0.5 : 0.5))                     (int32)
  *       hi = x - k*LN2HI        (LN2HI has 21 trailing zero bits: the product is exact)
- *       lo = k*LN2LO ;  r = hi - lo
- *       q  = Horner in r, separate multiply and add, of  sum_{n=2..14} r^(n-2)/n!
- *            (coefficients = the doubles nearest 1/n!)
- *       y  = 1 + (hi + ((r*r)*q - lo))
- *       result = y * 2^k  (k in [-1021,1023]: exponent-field add; k > 1023: (y*2^1023)*2^(k-1023);
- *                          k < -1021: (y*2^(k+1000))*2^-1000 -- one rounding, into the subnormals)
+ *       lo = k*LN2LO ;  r = hi - lo ;  z = r*r
+ *       q  = E(z) + r*O(z),  E / O = even / odd part of  sum_{n=2..14} r^(n-2)/n!, each a Horner chain in z with
+ *            separate multiply and add (coefficients = the doubles nearest 1/n!)
+ *       y  = 1 + (hi + (z*q - lo))
+ *       result = (y * 2^(k/2)) * 2^(k - k/2)      (k/2 truncated toward zero; the first product is exact, the second
+ *                                                  rounds once, into the subnormals when it has to)
  *
  *   pm_log(x):  NaN, x < 0 -> NaN; +-0 -> -Inf; +Inf -> +Inf; subnormal x is first scaled by 2^54
  *       x = m * 2^k with m in [sqrt(2)/2, sqrt(2))  (split at high word 0x3fe6a09e)
- *       f = m - 1 ;  s = f / (2 + f) ;  z = s*s
- *       R = z * Horner in z of  sum_{n=1..11} 2 z^(n-1)/(2n+1)            (= log((1+s)/(1-s))/s - 2)
+ *       f = m - 1 ;  s = f / (2 + f) ;  z = s*s ;  w = z*z
+ *       R = z * (E(w) + z*O(w)),  E / O = even / odd part of  sum_{n=1..11} 2 z^(n-1)/(2n+1)   (= log((1+s)/(1-s))/s - 2)
  *       h = (0.5*f)*f
  *       result = k*LN2HI - ((h - (s*(h + R) + k*LN2LO)) - f)
  *
@@ -38,7 +38,7 @@
  *       (the path raises to GasRDry/CpDry ~ 0.2857 with |y ln x| < 0.1, where this is within 1 ulp
  *        of the correctly rounded power, and to 0.25 -- ref atm/dccm_atm_mod.f90:831)
  *
- * Measured distance from the correctly rounded result (mpmath, tests/test_pmath.py): exp < 0.80 ulp,
+ * Measured distance from the correctly rounded result (mpmath, tests/test_pmath.py): exp < 0.85 ulp,
  * log < 0.80 ulp over dense sweeps; from glibc's exp / log / pow: <= 1 ulp.
  */
 #ifndef ORC_PMATH_H
@@ -54,6 +54,8 @@ static inline double orc_pm_from_bits(uint64_t u) { double x; memcpy(&x, &u, 8);
 #define ORC_PM_LN2LO  1.90821492927058770002e-10   /* 0x3dea39ef35793c76 */
 #define ORC_PM_INVLN2 1.44269504088896338700e+00   /* 0x3ff71547652b82fe */
 
+static inline double orc_pm_pow2(int e) { return orc_pm_from_bits((uint64_t)(e + 1023) << 52); }   /* e in [-1022, 1023] */
+
 static inline double orc_pm_exp(double x)
 {
     if (x != x) return x + x;
@@ -64,25 +66,24 @@ static inline double orc_pm_exp(double x)
     const double hi = x - kd * ORC_PM_LN2HI;
     const double lo = kd * ORC_PM_LN2LO;
     const double r = hi - lo;
-    double q = 1.0 / 87178291200.0;              /* 1/14! */
-    q = q * r + 1.0 / 6227020800.0;              /* 1/13! */
-    q = q * r + 1.0 / 479001600.0;               /* 1/12! */
-    q = q * r + 1.0 / 39916800.0;                /* 1/11! */
-    q = q * r + 1.0 / 3628800.0;                 /* 1/10! */
-    q = q * r + 1.0 / 362880.0;                  /* 1/9!  */
-    q = q * r + 1.0 / 40320.0;                   /* 1/8!  */
-    q = q * r + 1.0 / 5040.0;                    /* 1/7!  */
-    q = q * r + 1.0 / 720.0;                     /* 1/6!  */
-    q = q * r + 1.0 / 120.0;                     /* 1/5!  */
-    q = q * r + 1.0 / 24.0;                      /* 1/4!  */
-    q = q * r + 1.0 / 6.0;                       /* 1/3!  */
-    q = q * r + 0.5;                             /* 1/2!  */
-    const double y = 1.0 + (hi + ((r * r) * q - lo));
-    if (k > 1023)
-        return (y * 0x1p1023) * orc_pm_from_bits((uint64_t)(k - 1023 + 1023) << 52);
-    if (k < -1021)
-        return (y * orc_pm_from_bits((uint64_t)(k + 1000 + 1023) << 52)) * 0x1p-1000;
-    return orc_pm_from_bits(orc_pm_bits(y) + ((uint64_t)(int64_t)k << 52));
+    const double z = r * r;
+    double e = 1.0 / 87178291200.0;              /* even powers of r: 1/14! z^6 + 1/12! z^5 + ... + 1/2! */
+    e = e * z + 1.0 / 479001600.0;
+    e = e * z + 1.0 / 3628800.0;
+    e = e * z + 1.0 / 40320.0;
+    e = e * z + 1.0 / 720.0;
+    e = e * z + 1.0 / 24.0;
+    e = e * z + 0.5;
+    double o = 1.0 / 6227020800.0;               /* odd powers of r: 1/13! z^5 + 1/11! z^4 + ... + 1/3! */
+    o = o * z + 1.0 / 39916800.0;
+    o = o * z + 1.0 / 362880.0;
+    o = o * z + 1.0 / 5040.0;
+    o = o * z + 1.0 / 120.0;
+    o = o * z + 1.0 / 6.0;
+    const double q = e + r * o;
+    const double y = 1.0 + (hi + (z * q - lo));
+    const int k1 = k / 2;                        /* C division truncates toward zero */
+    return (y * orc_pm_pow2(k1)) * orc_pm_pow2(k - k1);
 }
 
 static inline double orc_pm_log(double x)
@@ -104,18 +105,19 @@ static inline double orc_pm_log(double x)
     const double f = m - 1.0;
     const double s = f / (2.0 + f);
     const double z = s * s;
-    double p = 2.0 / 23.0;
-    p = p * z + 2.0 / 21.0;
-    p = p * z + 2.0 / 19.0;
-    p = p * z + 2.0 / 17.0;
-    p = p * z + 2.0 / 15.0;
-    p = p * z + 2.0 / 13.0;
-    p = p * z + 2.0 / 11.0;
-    p = p * z + 2.0 / 9.0;
-    p = p * z + 2.0 / 7.0;
-    p = p * z + 2.0 / 5.0;
-    p = p * z + 2.0 / 3.0;
-    const double R = z * p;
+    const double w = z * z;
+    double e = 2.0 / 23.0;                       /* even powers of z: 2/23 w^5 + 2/19 w^4 + ... + 2/3 */
+    e = e * w + 2.0 / 19.0;
+    e = e * w + 2.0 / 15.0;
+    e = e * w + 2.0 / 11.0;
+    e = e * w + 2.0 / 7.0;
+    e = e * w + 2.0 / 3.0;
+    double o = 2.0 / 21.0;                       /* odd powers of z: 2/21 w^4 + 2/17 w^3 + ... + 2/5 */
+    o = o * w + 2.0 / 17.0;
+    o = o * w + 2.0 / 13.0;
+    o = o * w + 2.0 / 9.0;
+    o = o * w + 2.0 / 5.0;
+    const double R = z * (e + z * o);
     const double h = (0.5 * f) * f;
     return kd * ORC_PM_LN2HI - ((h - (s * (h + R) + kd * ORC_PM_LN2LO)) - f);
 }
