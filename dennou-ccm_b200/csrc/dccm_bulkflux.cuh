@@ -67,16 +67,8 @@ struct BulkMid {
 // Phase 1 (:194-349): per-slot bulk coefficients, transfer coefficients, fluxes and their
 // area-weighted composite.  Reads neither ImplCplCoef1/2 nor LDwRFlx, so a caller that has those in
 // shared memory can fetch them afterwards (fewer live registers during the heavy part).
-// NS = surface slots evaluated: 2 where there is sea ice, 1 where there is none.  xy_CalcFlag (:268-272): in the sea-ice
-// slot of an ice-free column the reference still evaluates everything and multiplies by bulk coefficients that
-// BulkCoefL82 set to 0, so every output of that slot is an exact +0; with NS = 1 those zeros are written without
-// evaluating (saturation exp, Ri, Louis functions, divisions): same bits for finite inputs, a third of the column's
-// work saved (columns of a warp share a latitude row, so the choice is warp-coherent).  Inside, nothing branches: the
-// two slots of an ice column and the independent chains of a slot (the two Exner powers, the saturation exp, the
-// neutral-coefficient log) are one basic block that the scheduler interleaves -- the kernel is bound by the latency
-// of dependent fp64 chains, not by issue slots or bandwidth.
-template <class Arith, int NS>
-__device__ __forceinline__ void bulk_fluxes_slots(const BulkIn &in, double sig1, BulkOut &o, BulkMid &mid, Arith &ar)
+template <class Arith>
+__device__ __forceinline__ void bulk_fluxes(const BulkIn &in, double sig1, BulkOut &o, BulkMid &mid, Arith &ar)
 {
     using namespace sfc;
     const double LatentHeatLocal[2] = {LatentHeat, LatentHeat + LatentHeatFusion};   // :198-199
@@ -88,11 +80,18 @@ __device__ __forceinline__ void bulk_fluxes_slots(const BulkIn &in, double sig1,
     double SfcVirTemp[2];
     Frac[0] = 1.0 - in.SIceCon;                                                      // :205-206
     Frac[1] = in.SIceCon;
+    // xy_CalcFlag (:268-272): the sea-ice slot of an ice-free column.  The reference still evaluates the
+    // whole slot there and multiplies by bulk coefficients that BulkCoefL82 set to 0; every output of the
+    // slot is then an exact +0.  We write those zeros without evaluating (saturation exp, Ri, Louis
+    // functions, three divisions): same bits for finite inputs, ~1/3 of the column's work saved where
+    // there is no ice (columns of a warp share a latitude row, so the branch is warp-coherent).
+    const bool ice = Frac[1] > 1e-12;
     QVapSat[1] = 0.0; SfcVirTemp[1] = 1.0;
-    const double pq = ar.div(EpsV * Es0, in.SfcPress);                               // same expression for both slots
 #pragma unroll
-    for (int n = 0; n < NS; n++) {                                                   // :208-213
-        QVapSat[n] = pq * pexp(LatentHeatLocal[n] / GasRWet * (1.0 / 273.0 - ar.rcp(in.SfcTemp[n])));
+    for (int n = 0; n < 2; n++) {                                                    // :208-213
+        if (n == 1 && !ice) continue;
+        QVapSat[n] = ar.div(EpsV * Es0, in.SfcPress)
+                   * pexp(LatentHeatLocal[n] / GasRWet * (1.0 / 273.0 - ar.rcp(in.SfcTemp[n])));
         SfcVirTemp[n] = in.SfcTemp[n] * (1.0 + (((1.0 / EpsV) - 1.0) * QVapSat[n]));
     }
     const double VirTemp = in.SfcAirTemp * (1.0 + (((1.0 / EpsV) - 1.0) * in.QVap1));   // :215
@@ -129,31 +128,40 @@ __device__ __forceinline__ void bulk_fluxes_slots(const BulkIn &in, double sig1,
     const double ivr2 = ar.prep(vr2);
     const double vtx = ar.div_by(VirTemp, Exner, iEx);            // slot-independent quotients of the loop body
     const double atx = ar.div_by(in.SfcAirTemp, Exner, iEx);
-    const double velV = fmin(fmax(VelAbs, VelMinForVel), VelMaxForVel);
-    const double velT = fmin(fmax(VelAbs, VelMinForTemp), VelMaxForTemp);
-    const double velQ = fmin(fmax(VelAbs, VelMinForQVap), VelMaxForQVap);
 
 #pragma unroll
-    for (int n = 0; n < NS; n++) {                                                   // :244; CalcFlag is true in every slot evaluated
+    for (int n = 0; n < 2; n++) {                                                    // :244
+        if (n == 1 && !ice) {
+            o.VelTC[n] = 0.0; o.TempTC[n] = 0.0; o.QVapTC[n] = 0.0;
+            o.WindStressX[n] = 0.0; o.WindStressY[n] = 0.0; o.SenHFlx[n] = 0.0; o.QVapMFlx[n] = 0.0;
+            o.LatHFlx[n] = 0.0; o.LUwRFlx[n] = 0.0; o.SUwRFlx[n] = 0.0;
+            continue;
+        }
         const double svx = ar.div_by(SfcVirTemp[n], SfcExner, iSEx);
         const double Ri = ar.div_by(ar.div(Grav, svx)                                // :261-266
                                     * (vtx - svx),
                                     vr2, ivr2)
                         * (Height - in.SfcHeight);
+        const bool flag = (n == 0) ? true : ice;                                     // :268-272
 
-        // ---- BulkCoefL82 (:485-568): both Louis forms on benign operands, the one that applies selected --
-        // the formula not taken gets Ri = 1 (stable form) / -1 (unstable form), so neither can trip the
-        // arithmetic's range tests; what is selected has exactly the bits of the reference's if / else.
-        const bool stable = Ri > 0.0;
-        const double Rs = stable ? Ri : 1.0, Ru = stable ? -1.0 : Ri;
-        const double sq = ar.root(1.0 + 5.0 * Rs);                                   // :490-506
-        const double CMs = ar.div(CMn, 1.0 + ar.div(10.0 * Rs, sq));
-        const double CHs = ar.div(CHn, 1.0 + 15.0 * Rs * sq);
-        const double CMu = CMn * (1.0 - ar.div(10.0 * Ru,                            // :510-534
-                                               1.0 + 75.0 * CMn * ar.root(-hzm * Ru)));
-        const double CHu = CHn * (1.0 - ar.div(15.0 * Ru,
-                                               1.0 + 75.0 * CHn * ar.root(-hzh * Ru)));
-        double CM = stable ? CMs : CMu, CH = stable ? CHs : CHu, CQ = CH;
+        // ---- BulkCoefL82 (:485-568) ----
+        double CM, CH, CQ;
+        if (flag) {
+            if (Ri > 0.0) {
+                const double sq = ar.root(1.0 + 5.0 * Ri);
+                CM = ar.div(CMn, 1.0 + ar.div(10.0 * Ri, sq));
+                CH = ar.div(CHn, 1.0 + 15.0 * Ri * sq);
+                CQ = CH;
+            } else {
+                CM = CMn * (1.0 - ar.div(10.0 * Ri,
+                                         1.0 + 75.0 * CMn * ar.root(-hzm * Ri)));
+                CH = CHn * (1.0 - ar.div(15.0 * Ri,
+                                         1.0 + 75.0 * CHn * ar.root(-hzh * Ri)));
+                CQ = CH;
+            }
+        } else {
+            CM = 0.0; CH = 0.0; CQ = 0.0;
+        }
         CM = fmax(fmin(CM, VelBulkCoefMax), VelBulkCoefMin);
         CH = fmax(fmin(CH, TempBulkCoefMax), TempBulkCoefMin);
         CQ = fmax(fmin(CQ, QVapBulkCoefMax), QVapBulkCoefMin);
@@ -161,45 +169,41 @@ __device__ __forceinline__ void bulk_fluxes_slots(const BulkIn &in, double sig1,
         // ---- transfer coefficients and fluxes (:286-349) ----
         const double rt = GasRDry * SfcVirTemp[n];
         const double irt = ar.prep(rt);
-        o.VelTC[n] = ar.div_by(CM * in.SfcPress, rt, irt) * velV;
-        o.TempTC[n] = ar.div_by(CH * in.SfcPress, rt, irt) * velT;
-        o.QVapTC[n] = ar.div_by(CQ * in.SfcPress, rt, irt) * velQ;
-        o.WindStressX[n] = -o.VelTC[n] * in.WindU;
-        o.WindStressY[n] = -o.VelTC[n] * in.WindV;
-        o.SenHFlx[n] = -CpDry * SfcExner * o.TempTC[n]
-                     * (atx - ar.div_by(in.SfcTemp[n], SfcExner, iSEx));
-        o.QVapMFlx[n] = -HumdCoef * o.QVapTC[n] * (in.QVap1 - QVapSat[n]);
-        o.LatHFlx[n] = LatentHeatLocal[n] * o.QVapMFlx[n];
-        const double t2 = in.SfcTemp[n] * in.SfcTemp[n];
-        const double t4 = t2 * t2;
-        o.LUwRFlx[n] = StB * t4;
-        o.SUwRFlx[n] = in.SfcAlbedo[n] * in.SDwRFlx;
+        o.VelTC[n] = ar.div_by(CM * in.SfcPress, rt, irt)
+                   * fmin(fmax(VelAbs, VelMinForVel), VelMaxForVel);
+        o.TempTC[n] = ar.div_by(CH * in.SfcPress, rt, irt)
+                    * fmin(fmax(VelAbs, VelMinForTemp), VelMaxForTemp);
+        o.QVapTC[n] = ar.div_by(CQ * in.SfcPress, rt, irt)
+                    * fmin(fmax(VelAbs, VelMinForQVap), VelMaxForQVap);
+        if (flag) {
+            o.WindStressX[n] = -o.VelTC[n] * in.WindU;
+            o.WindStressY[n] = -o.VelTC[n] * in.WindV;
+            o.SenHFlx[n] = -CpDry * SfcExner * o.TempTC[n]
+                         * (atx - ar.div_by(in.SfcTemp[n], SfcExner, iSEx));
+            o.QVapMFlx[n] = -HumdCoef * o.QVapTC[n] * (in.QVap1 - QVapSat[n]);
+            o.LatHFlx[n] = LatentHeatLocal[n] * o.QVapMFlx[n];
+            const double t2 = in.SfcTemp[n] * in.SfcTemp[n];
+            const double t4 = t2 * t2;
+            o.LUwRFlx[n] = StB * t4;
+            o.SUwRFlx[n] = in.SfcAlbedo[n] * in.SDwRFlx;
 
-        o.SfcTemp3 = o.SfcTemp3 + Frac[n] * t4;
-        o.SfcAlbedo3 = o.SfcAlbedo3 + Frac[n] * in.SfcAlbedo[n];
-        o.WindStressX[2] = o.WindStressX[2] + Frac[n] * o.WindStressX[n];
-        o.WindStressY[2] = o.WindStressY[2] + Frac[n] * o.WindStressY[n];
-        o.SenHFlx[2] = o.SenHFlx[2] + Frac[n] * o.SenHFlx[n];
-        o.QVapMFlx[2] = o.QVapMFlx[2] + Frac[n] * o.QVapMFlx[n];
-        o.LatHFlx[2] = o.LatHFlx[2] + Frac[n] * o.LatHFlx[n];
-        o.LUwRFlx[2] = o.LUwRFlx[2] + Frac[n] * o.LUwRFlx[n];
-        o.SUwRFlx[2] = o.SUwRFlx[2] + Frac[n] * o.SUwRFlx[n];
-        o.VelTC[2] = o.VelTC[2] + Frac[n] * o.VelTC[n];
-        o.TempTC[2] = o.TempTC[2] + Frac[n] * o.TempTC[n];
-        o.QVapTC[2] = o.QVapTC[2] + Frac[n] * o.QVapTC[n];
+            o.SfcTemp3 = o.SfcTemp3 + Frac[n] * t4;
+            o.SfcAlbedo3 = o.SfcAlbedo3 + Frac[n] * in.SfcAlbedo[n];
+            o.WindStressX[2] = o.WindStressX[2] + Frac[n] * o.WindStressX[n];
+            o.WindStressY[2] = o.WindStressY[2] + Frac[n] * o.WindStressY[n];
+            o.SenHFlx[2] = o.SenHFlx[2] + Frac[n] * o.SenHFlx[n];
+            o.QVapMFlx[2] = o.QVapMFlx[2] + Frac[n] * o.QVapMFlx[n];
+            o.LatHFlx[2] = o.LatHFlx[2] + Frac[n] * o.LatHFlx[n];
+            o.LUwRFlx[2] = o.LUwRFlx[2] + Frac[n] * o.LUwRFlx[n];
+            o.SUwRFlx[2] = o.SUwRFlx[2] + Frac[n] * o.SUwRFlx[n];
+            o.VelTC[2] = o.VelTC[2] + Frac[n] * o.VelTC[n];
+            o.TempTC[2] = o.TempTC[2] + Frac[n] * o.TempTC[n];
+            o.QVapTC[2] = o.QVapTC[2] + Frac[n] * o.QVapTC[n];
+        } else {
+            o.WindStressX[n] = 0.0; o.WindStressY[n] = 0.0; o.SenHFlx[n] = 0.0; o.QVapMFlx[n] = 0.0;
+            o.LatHFlx[n] = 0.0; o.LUwRFlx[n] = 0.0; o.SUwRFlx[n] = 0.0;
+        }
     }
-    if (NS == 1) {                                                                   // ice-free column: CalcFlag false in slot 2
-        o.VelTC[1] = 0.0; o.TempTC[1] = 0.0; o.QVapTC[1] = 0.0;
-        o.WindStressX[1] = 0.0; o.WindStressY[1] = 0.0; o.SenHFlx[1] = 0.0; o.QVapMFlx[1] = 0.0;
-        o.LatHFlx[1] = 0.0; o.LUwRFlx[1] = 0.0; o.SUwRFlx[1] = 0.0;
-    }
-}
-
-template <class Arith>
-__device__ __forceinline__ void bulk_fluxes(const BulkIn &in, double sig1, BulkOut &o, BulkMid &mid, Arith &ar)
-{
-    if (in.SIceCon > 1e-12) bulk_fluxes_slots<Arith, 2>(in, sig1, o, mid, ar);       // Frac(2) > 1e-12, :272
-    else bulk_fluxes_slots<Arith, 1>(in, sig1, o, mid, ar);
 }
 
 // Phase 2 (:353-415): implicit surface-layer update, flux correction, net heat fluxes and dF/dTs.
