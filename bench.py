@@ -340,7 +340,7 @@ def parity_rows(A, M, own):
     return (j1 - n, j1)
 
 
-def parity_check(torch, dccm, syn, ex, wl, grids, K, nc, M, member0, own_a, own_o, dev, fast):
+def parity_check(torch, dccm, syn, ex, wl, grids, K, nc, M, member0, own_a, own_o, dev, fast, order_as=1):
     """The GPU's outputs on a latitude band against the oracle (oracle/band.BandExchange) fed with THE SAME INPUT BITS:
     the band's inputs are produced on the device by the generator that produced the resident inputs (checked to be
     identical where they overlap), copied to the host and handed to the oracle.  Compared: a_recv (9 layers), o_recv (12),
@@ -355,7 +355,7 @@ def parity_check(torch, dccm, syn, ex, wl, grids, K, nc, M, member0, own_a, own_
             if not np.array_equal(getattr(g, k), getattr(h, k)):
                 return {"error": f"grid axis {k} differs between product and oracle"}
     rows = parity_rows(A, M, own_a)
-    bx = BandExchange(oracle, Ao, Oo, So, K, nc, rows, consts_of(syn), ranks=host_cores())
+    bx = BandExchange(oracle, Ao, Oo, So, K, nc, rows, consts_of(syn), order_as=order_as, ranks=host_cores())
     (ae0, ae1), (oe0, oe1) = bx.input_rows()
     col = syn.column_inputs(torch, A, K, nc, ae0, ae1, dev=dev, member=member0)
     atm = syn.atm_surface_fields(torch, A, ae0, ae1, dev=dev, member=member0)
@@ -433,6 +433,8 @@ class Workload:
         A, O, S, K, nc, M = make_grids(dccm, wl)
         self.grids, self.K, self.nc, self.M_total = (A, O, S), K, nc, M
         fast = args.fast
+        order = getattr(args, "order_as", 1)
+        self.order_as = order
         t0 = time.time()
         self.member0, self.by_member, self.halo_mode = 0, world > 1 and M > 1, "none"
         if self.by_member:
@@ -440,24 +442,24 @@ class Workload:
             if M % world:
                 raise SystemExit(f"--gpus {world} does not divide the {M} ensemble members")
             M, self.member0 = M // world, rank * (M // world)
-            ex = exch_mod.SurfaceExchange(A, O, S, K, nc, 1, members=M, fast=fast, device=dev)
+            ex = exch_mod.SurfaceExchange(A, O, S, K, nc, 1, members=M, fast=fast, device=dev, order_as=order)
             self.own_a, self.own_o = (0, A.jm), (0, O.jm)
         elif world > 1:
             sh = importlib.import_module("dennou-ccm_b200.sharding")
             ex, self.halo_mode = None, args.halo
             if args.halo == "peer":
                 try:
-                    ex = sh.PeerShardedExchange(A, O, S, K, nc, 1, rank=rank, world=world, dist=dist, fast=fast, device=dev)
+                    ex = sh.PeerShardedExchange(A, O, S, K, nc, 1, rank=rank, world=world, dist=dist, fast=fast, device=dev, order_as=order)
                 except Exception as e:          # no peer access / symmetric memory: NCCL send/recv halo instead
                     sys.stderr.write(f"[bench] peer-memory halo unavailable ({e!r}); using NCCL send/recv\n")
                     self.halo_mode = "nccl"
             if ex is None:
                 ex = sh.ShardedExchange(A, O, S, K, nc, 1, rank=rank, world=world, dist=dist,
                                         halo="allgather" if self.halo_mode == "allgather" else "sendrecv",
-                                        fast=fast, device=dev)
+                                        fast=fast, device=dev, order_as=order)
             self.own_a, self.own_o = ex.plan.bands["A"][rank], ex.plan.bands["O"][rank]
         else:
-            ex = exch_mod.SurfaceExchange(A, O, S, K, nc, 1, members=M, fast=fast, device=dev)
+            ex = exch_mod.SurfaceExchange(A, O, S, K, nc, 1, members=M, fast=fast, device=dev, order_as=order)
             self.own_a, self.own_o = (0, A.jm), (0, O.jm)
         self.ex, self.M = ex, M
         (ja0, ja1), (jo0, jo1) = self.own_a, self.own_o
@@ -550,7 +552,7 @@ def other_workloads(args, torch, dccm, dev, skip):
                        "description": DESCR[wl], "l2": note, "setup_s": round(w.setup_s, 2),
                        "exchange_hbm_gbs": b / (ms * 1e-3) / 1e9,
                        "output_hash": output_hash(torch, w.ex, None, 1),
-                       "parity": parity_check(torch, dccm, w.syn, w.ex, wl, w.grids, w.K, w.nc, w.M, 0, w.own_a, w.own_o, dev, args.fast)}
+                       "parity": parity_check(torch, dccm, w.syn, w.ex, wl, w.grids, w.K, w.nc, w.M, 0, w.own_a, w.own_o, dev, args.fast, w.order_as)}
             del w, run
             torch.cuda.empty_cache()
         except Exception as e:
@@ -576,6 +578,8 @@ def run_ours(args, rank, world):
     col_in, atm_sfc, ocn_sfc = W.col_in, W.atm_sfc, W.ocn_sfc
     t_setup = W.setup_s
 
+    if args.sfc_minb > 0:
+        ex.configure_sfc(-1, args.sfc_minb)
     bytes_alg = ex.algorithmic_bytes()
     if world > 1:                                  # whole-job bytes: sum over ranks
         keys = sorted(bytes_alg)
@@ -640,7 +644,7 @@ def run_ours(args, rank, world):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl, "description": DESCR[wl], "columns_atm": A.n * M * (world if by_member else 1),
                    "cells_sfc": S.n * M * (world if by_member else 1), "cells_ocn": O.n * M * (world if by_member else 1),
-                   "kmax": K, "ncmax": nc, "remapped_layers": 43,
+                   "kmax": K, "ncmax": nc, "remapped_layers": 43, "order_as": W.order_as,
                    "l2": l2_note,
                    "mode": "fast (shared reciprocals in the forward solve; <= 1e-12, not bit-exact)" if args.fast
                            else "reference-order (every stage bit-exact against the oracle)",
@@ -676,7 +680,7 @@ def run_ours(args, rank, world):
     if not args.no_parity:
         if rank == 0:
             try:
-                line["parity"] = parity_check(torch, dccm, syn, ex, wl, W.grids, K, nc, M, W.member0, W.own_a, W.own_o, dev, args.fast)
+                line["parity"] = parity_check(torch, dccm, syn, ex, wl, W.grids, K, nc, M, W.member0, W.own_a, W.own_o, dev, args.fast, W.order_as)
             except Exception as e:
                 line["parity"] = {"error": repr(e)}
         if world > 1:
@@ -959,6 +963,9 @@ def main():
     ap.add_argument("--reference-order", action="store_true", help="(default since round 2; kept for old command lines)")
     ap.add_argument("--slabs", type=int, default=0, help="1 GPU: pipeline the exchange over this many latitude slabs "
                     "(surface kernel beside the forward solve on a second stream); 0 = stage after stage")
+    ap.add_argument("--order-as", type=int, default=1, choices=[1, 2], help="accuracy order of the conservative A->S table "
+                    "(BASELINE: first order; 2 = gmapgen's default interp_order_AS, three source rows per stencil)")
+    ap.add_argument("--sfc-minb", type=int, default=-1, help="CTAs per SM the fused surface kernel is built for (4, 5, 6; tuning)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle-band parity block")
     ap.add_argument("--no-others", action="store_true", help="skip the other_workloads block (BASELINE configs 1-4)")
     ap.add_argument("--no-full-grid", action="store_true", help="reference arm: skip the one whole-grid repetition")

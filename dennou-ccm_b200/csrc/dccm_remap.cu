@@ -802,7 +802,9 @@ namespace {
 void default_f77_error(const char *msg)
 {
     fprintf(stderr, "interpolate_data: %s\n", msg);
-    exit(1);                                       // the reference leaves through jcup_error, which aborts the run
+    fflush(stderr);
+    abort();       // the reference leaves through jcup_error, which aborts the WHOLE run: under MPI a plain exit(1) of one
+                   // rank would leave the others hanging in Jcup's collectives; hosts install dccm_f77_set_error_handler
 }
 void (*g_f77_error)(const char *) = default_f77_error;
 }  // namespace

@@ -658,7 +658,8 @@ extern "C" int dccm_table_write_text(const dccm_table *t, const char *filename)
 }
 
 // list-directed read of "ir jr is js coef" (ref common/grid_mapping_util_jones99.f90:479-504);
-// blanks or commas separate, D exponents accepted, short/garbled lines end the read silently
+// blanks or commas separate, D exponents accepted; blank lines are skipped as a list-directed read skips them, and so
+// is a line that does not parse (the reference would die of a run-time I/O error there); end of file ends the read
 // like the reference's end=200.
 extern "C" int dccm_table_read_text(const char *filename, dccm_table **out)
 {

@@ -53,10 +53,13 @@ class SurfaceExchange:
     """
 
     def __init__(self, A, O, S, kmax, ncmax=1, index_h2ovap=1, tabs=None, consts=None, members=1,
-                 fast=False, device=None, layout=None, structured=True, ops=None):
+                 fast=False, device=None, layout=None, structured=True, ops=None, order_as=1, lon_mode=1):
         """layout (sharded runs, sharding.py): {"A"|"S"|"O": (n_own, n_ext, off)} -- cells this rank
         owns, cells of its source buffers (own + halo rows) and where the owned cells start in them;
-        A/O/S are then objects with .im/.jm/.n of the LOCAL band."""
+        A/O/S are then objects with .im/.jm/.n of the LOCAL band.
+        order_as: accuracy order of the conservative A->S table (gmapgen's interp_order_AS: 1, or 2 = the reference
+        tool's default, three source rows per stencil); lon_mode: 0 = the reference generator's equal-longitude rule,
+        1 = generalised longitude overlap (needed when ocean and atmosphere longitudes differ)."""
         import torch
         self.torch = torch
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
@@ -82,10 +85,11 @@ class SurfaceExchange:
             g = {"a": A, "s": S, "o": O}
             for key in ("as", "sa", "os", "so"):
                 for kind in ("cons", "bil"):
-                    self.ops[f"{key}_{kind}"] = RemapOperator.from_grids(g[key[0]], g[key[1]], kind == "cons", 1, 1)
+                    order = order_as if (key == "as" and kind == "cons") else 1
+                    self.ops[f"{key}_{kind}"] = RemapOperator.from_grids(g[key[0]], g[key[1]], kind == "cons", order, lon_mode)
             self.nnz = {k: op.nnz for k, op in self.ops.items()}
         else:
-            tabs = tabs or build_tables(A, O, S)
+            tabs = tabs or build_tables(A, O, S, order_as=order_as, lon_mode=lon_mode)
             for key, (send_i, recv_i, coef) in tabs.items():
                 s, d = key[0].upper(), key[1].upper()
                 gx = {"A": A.im, "S": S.im, "O": O.im}

@@ -277,11 +277,11 @@ class ShardedExchange(SurfaceExchange):
     """SurfaceExchange on rank `rank` of `world`: local bands + halo exchange around the surface step."""
 
     def __init__(self, A, O, S, kmax, ncmax=1, index_h2ovap=1, rank=0, world=1, plan=None, dist=None,
-                 halo="sendrecv", band_tables=False, **kw):
+                 halo="sendrecv", band_tables=False, order_as=1, lon_mode=1, **kw):
         """halo: "sendrecv" = grouped NCCL send/recv with the two neighbours, "allgather" = one all-gather of every
         rank's boundary rows per phase (AllGatherHalo).  band_tables: generate the band's tables on the host and
         keep them as CSR (the round-1 form; tests compare it with the table-free band operators)"""
-        self.plan = plan or BandPlan(A, O, S, world)
+        self.plan = plan or BandPlan(A, O, S, world, order_as=order_as, lon_mode=lon_mode)
         self.rank, self.world, self.dist = rank, world, dist
         lA, lO, lS = self.plan.local_grids(rank)
         if band_tables:

@@ -17,15 +17,20 @@ subroutine dccm_register_operation(recv_comp_name, send_comp_name, mapping_tag)
   character(*), intent(in) :: recv_comp_name, send_comp_name
   integer, intent(in) :: mapping_tag
   type(c_ptr) :: handle
-  integer :: rid, sid
+  integer :: rid, sid, n_send, n_recv
   rid = jcup_get_comp_num_from_name(recv_comp_name)
   sid = jcup_get_comp_num_from_name(send_comp_name)
   associate (c => operation_index(rid, sid, mapping_tag))
-    ! local 1-based indices + coefS in operation (= table) order; n_send / n_recv are the local
-    ! array extents sn1 / rn1 Jcup will pass to interpolate_data
+    ! local 1-based indices + coefS in operation (= table) order.  n_send / n_recv only have to cover the indices
+    ! used: interpolate_data accepts any sn1 >= n_send, rn1 >= n_recv and zero-fills every row of recv_data beyond
+    ! them, as the reference does (ref :293).  A rank without operations (maxval of an empty array is -huge) gets a
+    ! valid operator that only zero-fills.
+    n_send = 1; n_recv = 1
+    if (size(c%send_data_index) > 0) then
+       n_send = max(1, maxval(c%send_data_index)); n_recv = max(1, maxval(c%recv_data_index))
+    end if
     call dccm_check( dccm_remap_create(int(size(c%send_data_index), c_int64_t), c%send_data_index, &
-         & c%recv_data_index, c%coefS, maxval(c%send_data_index), maxval(c%recv_data_index), handle), &
-         & "dccm_remap_create")
+         & c%recv_data_index, c%coefS, n_send, n_recv, handle), "dccm_remap_create")
     call dccm_check( dccm_interp_register(rid, sid, mapping_tag, handle), "dccm_interp_register")
   end associate
 end subroutine dccm_register_operation

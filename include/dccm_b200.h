@@ -204,7 +204,7 @@ int dccm_interpolate_data(int recv_model, int send_model, int mapping_tag,
  * reference, the two CHARACTER(*) lengths appended by value -- so leaving interpolate_data.o out of the link line
  * and adding -ldccm_b200 is enough.  Component names are translated through a table the host fills once with
  * what jcup_get_comp_num_from_name returns (ref common/interpolation_data_latlon_mod.f90:289).  The subroutine has
- * no status argument: a failure goes to the error handler (default: message to stderr and exit(1), the behaviour of
+ * no status argument: a failure goes to the error handler (default: message to stderr and abort(), the behaviour of
  * the reference's jcup_error); dccm_interpolate_data_named is the same call with a status for C callers. */
 int dccm_interp_set_model_name(int model_id, const char *name);
 int dccm_interpolate_data_named(const char *recv_model, int64_t recv_len,
