@@ -182,6 +182,7 @@ _SIGS = {
     "dccm_vdiff_backward_host": (C.c_int, [vp] + [f64p] * 4),
     "dccm_vdiff_forward_device": (C.c_int, [vp] + [vp] * 18 + [vp]),
     "dccm_vdiff_backward_device": (C.c_int, [vp] + [vp] * 4 + [vp, vp]),
+    "dccm_vdiff_redo_total": (C.c_int, [vp, C.POINTER(C.c_int64)]),
     "dccm_vdiff_forward_cols_device": (C.c_int, [vp] + [vp] * 18 + [C.c_int64, C.c_int64, vp]),
     "dccm_vdiff_backward_cols_device": (C.c_int, [vp] + [vp] * 4 + [vp, C.c_int64, C.c_int64, vp]),
 }

@@ -66,6 +66,6 @@ struct dccm_remap {
     // options / bookkeeping of the fused surface kernel, kept on the A->S bilinear handle of the call (per handle, so
     // two exchanges configured differently do not see each other): form requested (1 staged, 0 direct), CTAs per SM
     // the kernel is built for (4, 5 or 6) and the form the last call on this handle took (-1: none yet)
-    int sfc_staged = 1, sfc_minb = 5, sfc_last_form = -1;
+    int sfc_staged = 1, sfc_minb = 6, sfc_last_form = -1;      // 6 CTAs/SM (80 registers): the kernel is latency bound, warps beat spills (profiles/r02d)
     dccm::DevBuf send_buf, recv_buf;
 };

@@ -57,7 +57,7 @@ struct FwdArgs {
     int64_t c0, c1;               // columns [c0, c1) of this launch (host entry points pipeline over column chunks)
     int K, iq;
     double Grav, CpDry, GasRDry, DelTime;
-    int *redo;                    // [0] columns listed, [1] CTAs of the redo kernel done
+    int *redo;                    // [0] columns listed, [1] CTAs of the redo kernel done, [2] columns redone since creation
     int64_t *redo64;              // the listed columns
     int redo_cap;
 };
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(kThreads) vdiff_forward_redo_kernel(const FwdA
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(&a.redo[1], 1) == (int)gridDim.x - 1) { a.redo[0] = 0; a.redo[1] = 0; __threadfence(); }
+        if (atomicAdd(&a.redo[1], 1) == (int)gridDim.x - 1) { a.redo[2] += listed; a.redo[0] = 0; a.redo[1] = 0; __threadfence(); }
     }
 }
 
@@ -430,6 +430,16 @@ extern "C" int dccm_vdiff_set_mode(dccm_vdiff *h, int fast)
 {
     if (!h) return fail(DCCM_ERR_ARG, "dccm_vdiff_set_mode: null handle");
     h->fast = fast ? 1 : 0;
+    return DCCM_OK;
+}
+
+extern "C" int dccm_vdiff_redo_total(dccm_vdiff *h, int64_t *columns)
+{
+    if (!h || !columns) return fail(DCCM_ERR_ARG, "dccm_vdiff_redo_total: null argument");
+    int v = 0;
+    DCCM_CUDA_TRY(cudaDeviceSynchronize());
+    DCCM_CUDA_TRY(cudaMemcpy(&v, h->redo + 2, sizeof v, cudaMemcpyDeviceToHost));
+    *columns = v;
     return DCCM_OK;
 }
 

@@ -29,6 +29,12 @@ class SfcImplicitCoupling:
     def set_fast(self, fast):
         L.check(L.lib().dccm_vdiff_set_mode(self._h, 1 if fast else 0))
 
+    def redo_total(self):
+        """columns re-solved with plain IEEE operators so far (operands outside the branch-free division's range)"""
+        n = C.c_int64(0)
+        L.check(L.lib().dccm_vdiff_redo_total(self._h, C.byref(n)))
+        return int(n.value)
+
     def set_coef_stride(self, slot_stride):
         L.check(L.lib().dccm_vdiff_set_coef_stride(self._h, int(slot_stride)))
 

@@ -361,6 +361,10 @@ int dccm_vdiff_backward_device(dccm_vdiff *h,
     double *xyz_DUDt, double *xyz_DVDt, double *xyz_DTempDt, double *xyzf_DQMixDt,
     const double *level1, void *stream);
 
+/* Columns that the reference-order forward solve handed to its plain-IEEE redo kernel since the handle was created
+ * (columns whose operands left the range of the branch-free division: zero / denormal / non-finite values).  Results
+ * are the IEEE operators' either way; the counter is for tests and diagnostics.  Synchronises the device. */
+int dccm_vdiff_redo_total(dccm_vdiff *h, int64_t *columns);
 /* the same two calls for columns [c0, c1) only (0-based, half open): the pieces of a latitude-slab pipeline */
 int dccm_vdiff_forward_cols_device(dccm_vdiff *h,
     const double *xyr_MomFluxX, const double *xyr_MomFluxY, const double *xyr_HeatFlux,

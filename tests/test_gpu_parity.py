@@ -355,6 +355,41 @@ def test_vdiff_reference_order_mode_is_bit_exact(gpu, orc, dccm, S, im, jm, K, n
         assert np.array_equal(a, b), f"backward {k}: rel err {relerr(a, b)}"
 
 
+def test_vdiff_redo_list_takes_the_columns_the_branch_free_division_rejects(gpu, orc, dccm, S):
+    """Reference-order forward solve on columns whose operands leave the range of the branch-free division sequence
+    (fluxes of 1e-300 -> numerators below 2^-969; a zero diffusion coefficient -> division by zero): those columns go
+    to the redo list and are solved again with the plain IEEE operators, the others keep the fast path; every finite
+    value has the oracle's bits, Inf / NaN appear in the same places (NaN payloads differ between x86 and the GPU)."""
+    g, inp = _vdiff_case(S, dccm, 64, 32, 12, 2)
+    inp = {k: np.array(v, copy=True) for k, v in inp.items()}
+    tiny, zero = slice(100, 164), slice(700, 764)
+    inp["MomFluxX"][:, tiny] *= 1e-300
+    inp["HeatFlux"][:, tiny] *= 1e-290
+    inp["TempDiffCoef"][:, zero] = 0.0
+    args = (g.im, g.jm, 12, 2, 1, S.GRAV, S.CPDRY, S.GASRDRY, S.DELTIME)
+    with np.errstate(all="ignore"):
+        ref = orc.VDiff(*args).forward(inp)
+    h = dccm.SfcImplicitCoupling(*args)
+    assert h.redo_total() == 0
+    got = h.VDiffForward(inp)
+    n = h.redo_total()
+    print("columns redone with IEEE operators:", n, "of", g.n)
+    assert 128 <= n < g.n // 2
+    for k in ref:
+        a, b = got[k], ref[k]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), k
+        m = ~np.isnan(b)
+        assert np.array_equal(a[m].view(np.int64), b[m].view(np.int64)), f"{k}: rel err {relerr(a[m], b[m])}"
+    assert np.isfinite(ref["DUDt"][:, tiny]).all() and (ref["DUDt"][1:, tiny] != 0).any()
+    # a second, ordinary call on the same handle: the list was cleared, nothing is redone
+    g2, ok = _vdiff_case(S, dccm, 64, 32, 12, 2)
+    got2 = h.VDiffForward(ok)
+    assert h.redo_total() == n
+    ref2 = orc.VDiff(*args).forward(ok)
+    for k in ref2:
+        assert np.array_equal(got2[k], ref2[k]), k
+
+
 @pytest.mark.parametrize("chunks", [3, 7, 1000])
 def test_vdiff_host_calls_pipelined_over_column_chunks(gpu, orc, dccm, S, chunks, monkeypatch):
     """The *_host entry points move their arguments in column chunks (H2D | kernel | D2H on three streams, 2-D
