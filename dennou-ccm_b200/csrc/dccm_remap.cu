@@ -712,7 +712,7 @@ extern "C" int dccm_remap_apply_host(dccm_remap *h, const double *send, int sn1,
     if (rc) return rc;
     rc = h->recv_buf.reserve(sizeof(double) * (size_t)rn1 * std::max(1, rn2));
     if (rc) return rc;
-    static cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
+    static thread_local cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
     for (auto &ps : pipe)
         if (!ps) DCCM_CUDA_TRY(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
     cudaStream_t sin = pipe[0], sk = pipe[1], sout = pipe[2];
