@@ -24,7 +24,6 @@ using namespace dccm;
 
 #include "dccm_remap_internal.h"
 #include "dccm_sep.h"
-#include "dccm_tma.cuh"
 
 SepTab sep_of(const dccm_remap *h);
 
@@ -193,116 +192,6 @@ remap_sep_kernel(const SepTab t, const SrcSeg send, int64_t sn1, double *__restr
         for (int d = 0; d < FB; d++)
             if (d < nf) recv[r + (int64_t)(d0 + d) * rn1] = acc[d];
     }
-}
-
-// kind 2, staged: the same arithmetic as remap_sep_kernel with the source values coming from shared memory.
-// remap_sep_kernel is bound by two to three DEPENDENT global round trips per thread (factor lists -> source values of
-// longitude entry 1 -> of entry 2 ...).  Here a CTA owns kSepStageCols consecutive cells of ONE destination row: warp 0
-// reads the row's latitude list, and its lanes issue one TMA bulk copy (cp.async.bulk + mbarrier) per (source row,
-// field) for the contiguous range of source columns the CTA's cells touch (wrapped piece by piece; the whole row when
-// the range wraps around the globe); meanwhile all threads bring the CTA's longitude lists to shared memory.  One
-// round trip, no registers tied up by loads in flight; the accumulation then reads shared memory in the generator's
-// order (longitude entry outer, latitude entry inner; bilinear: (m0,n0) (m1,n0) (m1,n1) (m0,n1)) with the same
-// product xw*yw and the same 1e-14 drop test => the bits of remap_sep_kernel (tests/test_gpu_parity.py).
-constexpr int kST = dccm_remap::kSepStageCols;
-constexpr int kSepMaxRows = 8;
-struct SepStage {
-    double yw[kSepMaxRows];
-    int row[kSepMaxRows];
-    int nrows, a, len, pad_;
-};
-constexpr int kSepHdr = 128;       // mbarrier (16 B) + SepStage
-static_assert(16 + sizeof(SepStage) <= kSepHdr, "separable stage header too small");
-
-template <int FB, bool SEG>
-__global__ void __launch_bounds__(kST)
-remap_sep_staged_kernel(const SepTab t, const SrcSeg send, int64_t sn1, double *__restrict__ recv, int64_t rn1,
-                        int nfield, int W)
-{
-    extern __shared__ __align__(128) unsigned char smem[];
-    const uint32_t mbar = smem_u32(smem);
-    SepStage *st = reinterpret_cast<SepStage *>(smem + 16);
-    double *sxw = reinterpret_cast<double *>(smem + kSepHdr);                  // kST * wx longitude factors
-    int *sxi = reinterpret_cast<int *>(sxw + kST * t.wx);                      // ... and source columns
-    double *tile = reinterpret_cast<double *>(smem + ((kSepHdr + kST * t.wx * 12 + 127) & ~127));
-    const int tid = threadIdx.x, jD = blockIdx.y, i0 = blockIdx.x * kST;
-    const int nact = min(kST, t.nxd - i0);
-    const int nf = min(FB, nfield);
-
-    for (int idx = tid; idx < nact * t.wx; idx += kST) {
-        sxi[idx] = __ldg(&t.xi[i0 * t.wx + idx]);
-        sxw[idx] = __ldg(&t.xw[i0 * t.wx + idx]);
-    }
-    if (tid < 32) {
-        const int y0 = jD * t.wy;
-        int yj = 0;
-        double yw = 0.0;
-        bool real = false;
-        if (tid < t.wy) {
-            yj = __ldg(&t.yj[y0 + tid]); yw = __ldg(&t.yw[y0 + tid]);
-            real = t.mode == 1 || yw != 0.0;        // a zero latitude factor (padding) makes every product fail the drop test
-        }
-        const unsigned mask = __ballot_sync(0xffffffffu, real);
-        const int nrows = __popc(mask), slot = __popc(mask & ((1u << tid) - 1u));
-        const bool full = W >= t.nxs;               // the CTA's range wraps around the globe: stage whole rows
-        const int a = full ? 0 : (__ldg(&t.xi[i0 * t.wx]) & ~1);
-        const int len = full ? t.nxs : W;
-        if (real) { st->yw[slot] = yw; st->row[slot] = yj; }
-        if (tid == 0) {
-            mbar_init(mbar, 1);
-            st->nrows = nrows; st->a = a; st->len = len;
-            mbar_arrive_expect_tx(mbar, 8u * (uint32_t)(nrows * nf * len));
-        }
-        __syncwarp();
-        for (int idx = tid; idx < nrows * nf; idx += 32) {
-            const int s = idx / nf, d = idx - s * nf;
-            const double *rowp = cell<SEG>(send, (int64_t)st->row[s] * t.nxs) + (int64_t)d * sn1;
-            const uint32_t dst = smem_u32(tile + (size_t)idx * W);
-            int cur = a;
-            while (cur < a + len) {
-                const int wc = cur % t.nxs;
-                const int l = min(a + len - cur, t.nxs - wc);
-                bulk_g2s(dst + 8u * (uint32_t)(cur - a), rowp + wc, 8u * (uint32_t)l, mbar);
-                cur += l;
-            }
-        }
-    }
-    __syncthreads();                       // stage records, longitude lists and barrier initialisation visible to every warp
-    mbar_wait(mbar, 0);                    // tiles complete (every thread waits: no copy outlives the CTA)
-    if (tid >= nact) return;
-
-    double acc[FB];
-#pragma unroll
-    for (int d = 0; d < FB; d++) acc[d] = 0.0;
-    const int nrows = st->nrows, a = st->a;
-    auto add = [&](int s, int off, double w) {
-        const double *p = tile + (size_t)s * nf * W + off;
-#pragma unroll
-        for (int d = 0; d < FB; d++)
-            if (d < nf) acc[d] = __dadd_rn(acc[d], __dmul_rn(p[(size_t)d * W], w));
-    };
-    auto offset = [&](int i) { int o = i - a; return o < 0 ? o + t.nxs : o; };
-    const int x0 = tid * t.wx;
-    if (t.mode == 1) {                     // bilinear: (m0,n0) (m1,n0) (m1,n1) (m0,n1), nothing dropped
-        const int o0 = offset(sxi[x0]), o1 = offset(sxi[x0 + 1]);
-        const double a0 = sxw[x0], a1 = sxw[x0 + 1], b0 = st->yw[0], b1 = st->yw[1];
-        add(0, o0, __dmul_rn(a0, b0)); add(0, o1, __dmul_rn(a1, b0));
-        add(1, o1, __dmul_rn(a1, b1)); add(1, o0, __dmul_rn(a0, b1));
-    } else {
-        for (int m = 0; m < t.wx; m++) {
-            const double aw = sxw[x0 + m];
-            if (aw == 0.0) continue;       // padding: all its products fail the drop test
-            const int off = offset(sxi[x0 + m]);
-            for (int n = 0; n < nrows; n++) {
-                const double w = __dmul_rn(aw, st->yw[n]);
-                if (fabs(w) > 1e-14) add(n, off, w);
-            }
-        }
-    }
-    const int64_t r = (int64_t)jD * t.nxd + i0 + tid;
-#pragma unroll
-    for (int d = 0; d < FB; d++)
-        if (d < nf) recv[r + (int64_t)d * rn1] = acc[d];
 }
 
 // Is the (row-sorted) table a zonal stencil on an (nxs x .) -> (nxd x nyd) grid pair?  Exact test:
@@ -533,32 +422,6 @@ int create_separable(const SepFactors &f, dccm_remap **out)
         }
     }
     h->nnz = nnz; h->max_row_nnz = maxrow;
-    // what the staged kernel must provision: the widest range of source columns one CTA of kSepStageCols destination
-    // columns touches (measured from the first entry of its first column, wrapping eastwards) and the most latitude
-    // entries with a non-zero factor in one destination row
-    {
-        const int T = dccm_remap::kSepStageCols;
-        bool ok = f.nxs >= 2 && f.nxs % 2 == 0 && f.nxd >= 1;
-        int span = 0, rows = 0;
-        for (int i0 = 0; i0 < f.nxd && ok; i0 += T) {
-            if (f.xptr[i0 + 1] == f.xptr[i0]) { ok = false; break; }
-            const int first = f.xi[f.xptr[i0]];
-            for (int iD = i0; iD < std::min(f.nxd, i0 + T); iD++)
-                for (int m = f.xptr[iD]; m < f.xptr[iD + 1]; m++)
-                    if (f.mode == 1 || f.xw[m] != 0.0)
-                        span = std::max(span, ((f.xi[m] - first) % f.nxs + f.nxs) % f.nxs + 1);
-        }
-        for (int jD = 0; jD < f.nyd; jD++) {
-            int k = 0;
-            for (int n = f.yptr[jD]; n < f.yptr[jD + 1]; n++) k += (f.mode == 1 || f.yw[n] != 0.0);
-            rows = std::max(rows, k);
-            if (f.mode == 1 && f.yptr[jD + 1] - f.yptr[jD] != 2) ok = false;
-        }
-        if (f.mode == 1)
-            for (int iD = 0; iD < f.nxd; iD++) if (f.xptr[iD + 1] - f.xptr[iD] != 2) ok = false;
-        h->sep_span = span; h->sep_rows = rows;
-        h->sep_stage = ok && rows >= 1 && rows <= 8;
-    }
     // fixed-width lists: pad with (index 0, weight 0.0)
     auto pad = [](const std::vector<int32_t> &ptr, const std::vector<int32_t> &idx, const std::vector<double> &w, int n,
                   int &width, std::vector<int32_t> &pidx, std::vector<double> &pw) {
@@ -785,34 +648,6 @@ extern "C" int dccm_remap_apply_seg_device(dccm_remap *h, const dccm_src_seg *se
     if (num_of_data == 0) return DCCM_OK;
     const int gx = (h->n_recv + kThreads - 1) / kThreads;
     const bool use_seg = !(d_send.b0 <= 0 && d_send.b1 >= (int64_t)INT32_MAX);
-    // separable operators: the staged form whenever the call is one block of fields and every bulk copy is 16-byte
-    // aligned (even source row length and field stride, aligned bases, band cuts on row boundaries)
-    if (h->kind == 2 && h->sep_stage && num_of_data <= 13 && sn1 % 2 == 0 && h->sep_wy <= 32 && h->nyd <= 65535 &&
-        ((((uintptr_t)d_send.lo | (uintptr_t)d_send.own | (uintptr_t)d_send.hi) & 15u) == 0) &&
-        (d_send.b0 <= 0 || d_send.b0 % h->nxs == 0) && (d_send.b1 >= (int64_t)INT32_MAX || d_send.b1 % h->nxs == 0)) {
-        const int T = dccm_remap::kSepStageCols;
-        const int W = (h->sep_span + 2 + 1 > h->nxs) ? h->nxs : ((h->sep_span + 2 + 1) & ~1);   // even; + 1 for the even start
-        const size_t smem = (size_t)((kSepHdr + T * h->sep_wx * 12 + 127) & ~127) +
-                            sizeof(double) * (size_t)W * h->sep_rows * num_of_data;
-        if (smem <= 200 * 1024) {
-            dim3 sgrid((unsigned)((h->nxd + T - 1) / T), (unsigned)h->nyd);
-#define DCCM_SEP_STAGED(F)                                                                                        \
-            do {                                                                                                  \
-                auto kern = use_seg ? remap_sep_staged_kernel<F, true> : remap_sep_staged_kernel<F, false>;       \
-                DCCM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                kern<<<sgrid, T, smem, st>>>(sep_of(h), d_send, sn1, d_recv, rn1, num_of_data, W);                \
-            } while (0)
-            if (num_of_data <= 2) DCCM_SEP_STAGED(2);
-            else if (num_of_data <= 4) DCCM_SEP_STAGED(4);
-            else if (num_of_data <= 5) DCCM_SEP_STAGED(5);
-            else if (num_of_data <= 8) DCCM_SEP_STAGED(8);
-            else if (num_of_data <= 10) DCCM_SEP_STAGED(10);
-            else DCCM_SEP_STAGED(13);
-#undef DCCM_SEP_STAGED
-            DCCM_CUDA_TRY(cudaGetLastError());
-            return DCCM_OK;
-        }
-    }
     // field block: the smallest compiled size that takes the whole call in one pass; when rows are too few
     // to fill the machine the fields are split over grid.y instead (blocks of 2)
     static const int kFB[] = {2, 4, 5, 8, 10, 13};

@@ -57,12 +57,6 @@ struct dccm_remap {
     // longitude factor), per destination row a list of (source row, latitude factor); the kernels rebuild each
     // entry as the generator did (weight = xw * yw, mode 0 drops |w| <= 1e-14).  nxs / nxd / nyd as for kind 1.
     int sep_mode = 0, sep_wx = 0, sep_wy = 0;
-    // staged form of the kind-2 kernel (remap_sep_staged_kernel): a CTA of kSepStageCols destination columns of one
-    // destination row brings the source rows of the row's latitude list to shared memory by TMA bulk copies.
-    // sep_span = most source columns any such CTA touches (both ends included), sep_rows = most latitude entries with
-    // a non-zero factor in one row, sep_stage = the operator qualifies (even source row length, non-empty lists)
-    static constexpr int kSepStageCols = 128;
-    int sep_span = 0, sep_rows = 0, sep_stage = 0;
     int32_t *d_xi = nullptr, *d_yj = nullptr;
     double *d_xw = nullptr, *d_yw = nullptr;
     // fused surface kernel: cells to re-evaluate with plain IEEE operators (csrc/dccm_exchange.cu); the list of
