@@ -12,3 +12,10 @@ done
 # the late tests (second-order stencils: three source rows per tile) under memcheck as well
 ( timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_zz_late_gpu.py -m gpu -x -q ) > $OUT/memcheck_late.log 2>&1
 echo "memcheck late tests exit $?" | tee -a $OUT/memcheck_late.log
+# round 2: the forward solve's redo path, the slab pipeline (row-range launches on two streams) and the portable exp / log
+( timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_zz_late_gpu.py -m gpu -x -q \
+    -k "redo or slab or portable or extreme or reference_order" ) > $OUT/memcheck_round2.log 2>&1
+echo "memcheck round-2 tests exit $?" | tee -a $OUT/memcheck_round2.log
+( timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_zz_late_gpu.py -m gpu -x -q -k "slab" ) > $OUT/racecheck_slab.log 2>&1
+echo "racecheck slab pipeline exit $?" | tee -a $OUT/racecheck_slab.log
+

@@ -171,3 +171,34 @@ def test_slab_pipelined_step_equals_the_plain_step(gpu, orc, dccm, S, name, nsla
     with torch.cuda.graph(g):
         ex.step_pipelined(nslab)
     scrub(); g.replay(); check("graph")
+
+
+@pytest.mark.parametrize("name,K,nc,iq", [("T21_1deg", 9, 3, 2), ("T21_Pl42", 12, 2, 1)])
+def test_exchange_with_several_tracers_vs_oracle(gpu, orc, dccm, S, name, K, nc, iq):
+    """Whole exchange with ncmax > 1 and the water-vapour tracer not first (composition: IndexH2OVap, ref
+    atm/dcpam_sfc_implicit_coupling_mod.f90:316, :371-374; the level-1 update goes to tracer IndexH2OVap only,
+    atm/dccm_atm_mod.f90:835): every stage output has the oracle's bits, unfused and fused alike."""
+    import torch
+    from exchange_ref import compare_exchange, oracle_exchange
+    X = importlib.import_module("dennou-ccm_b200.exchange")
+    A, O, Sx = pair(orc, dccm, name)
+    tabs = X.build_tables(A, O, Sx)
+    ex = X.SurfaceExchange(A, O, Sx, K, nc, iq, tabs=tabs, fast=False, device=gpu)
+    col, atm, ocn = S.column_inputs(np, A, K, nc), S.atm_surface_fields(np, A), S.ocn_surface_fields(np, O)
+    tt = lambda d: {k: torch.as_tensor(v, device=gpu).contiguous() for k, v in d.items()}
+    ex.set_inputs(tt(col), {k: v[None] for k, v in tt(atm).items()}, {k: v[None] for k, v in tt(ocn).items()})
+    ref = oracle_exchange(orc, S, A, O, Sx, K, nc, iq, tabs, col, atm, ocn)
+    for fused in (False, True):
+        for t in (ex.s2a, ex.s2o, ex.a_recv, ex.o_recv, *ex.tend.values()):
+            t.fill_(float("nan"))
+        ex.step(fused=fused)
+        torch.cuda.synchronize()
+        same = {}
+        compare_exchange(ex, ref, bitwise=same)
+        if fused:                                   # the fused kernel does not store the remapped surface inputs
+            same = {k: v for k, v in same.items() if not k.startswith("s_")}
+        assert all(same.values()), (fused, same)
+    # the other tracers' level 1 is NOT touched by the surface update
+    other = [n for n in range(nc) if n != iq - 1]
+    lvl1 = ref["fwd"]["DQMixDt"][other, 0] / (2.0 * S.DELTIME)
+    assert np.array_equal(ex.tend["DQMixDt"][other, 0].cpu().numpy(), lvl1)
