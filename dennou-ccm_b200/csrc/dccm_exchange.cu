@@ -505,6 +505,7 @@ __global__ void __launch_bounds__(kThreads, MINB) sfc_exchange_staged_kernel(con
 
     if (tid < 32) {
         if (tid == 0) mbar_init(mbar, 1);
+        __syncwarp();                      // the barrier object exists before any lane of the warp goes on
         const StagePlan pb = stage_plan<13>(a.as_bil, g.dmin_bil, g.dmax_bil, jD, i0, nact, zs[0], tid);
         const StagePlan pc = stage_plan<4>(a.as_cons, g.dmin_cons, g.dmax_cons, jD, i0, nact, zs[1], tid);
         if (tid == 0)
