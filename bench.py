@@ -449,7 +449,8 @@ class Workload:
             ex, self.halo_mode = None, args.halo
             if args.halo == "peer":
                 try:
-                    ex = sh.PeerShardedExchange(A, O, S, K, nc, 1, rank=rank, world=world, dist=dist, fast=fast, device=dev, order_as=order)
+                    ex = sh.PeerShardedExchange(A, O, S, K, nc, 1, rank=rank, world=world, dist=dist, fast=fast, device=dev, order_as=order,
+                                                sync=args.peer_sync)
                 except Exception as e:          # no peer access / symmetric memory: NCCL send/recv halo instead
                     sys.stderr.write(f"[bench] peer-memory halo unavailable ({e!r}); using NCCL send/recv\n")
                     self.halo_mode = "nccl"
@@ -693,7 +694,8 @@ def run_ours(args, rank, world):
         line["roofline"]["algorithmic_bytes_per_launch"] = ex.algorithmic_bytes()["fwd"]
     elif world > 1:
         how = ("read in place from the neighbours' buffers over NVLink peer memory inside the surface / remap kernels, "
-               "2 device barriers per exchange" if halo_mode == "peer" else
+               + ("2 pairwise neighbour handshakes per exchange" if args.peer_sync == "neighbour" else "2 all-rank device barriers per exchange")
+               if halo_mode == "peer" else
                "one NCCL all-gather of every rank's boundary rows per phase" if halo_mode == "allgather" else
                "packed NCCL send/recv, one message per neighbour")
         line["config"]["sharding"] = (f"{world} latitude bands (row blocks); halo rows {how}; "
@@ -956,6 +958,8 @@ def main():
     ap.add_argument("--no-dropin", action="store_true", help="skip the reference-interface-only e2e leg")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl", "allgather"],
                     help="multi-GPU halo: peer-memory reads, NCCL send/recv, or one NCCL all-gather of the boundary rows")
+    ap.add_argument("--peer-sync", default="barrier", choices=["neighbour", "barrier"],
+                    help="peer-memory halo: pairwise signals with the two neighbouring ranks, or the all-rank device barrier")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of as a CUDA graph")
     ap.add_argument("--unfused", action="store_true", help="surface step as 4 remaps + bulk flux + pack")
     ap.add_argument("--fast", action="store_true", help="forward solve with shared reciprocals (<= 1e-12, not bit-exact); "

@@ -34,13 +34,15 @@ def main():
     halo = os.environ.get("DCCM_HALO", "peer")           # peer | nccl | allgather
     cls = sh.PeerShardedExchange if halo == "peer" else sh.ShardedExchange
     kw = {"halo": "allgather"} if halo == "allgather" else {}
+    if halo == "peer" and os.environ.get("DCCM_SYNC"):
+        kw["sync"] = os.environ["DCCM_SYNC"]
     ex = cls(A, O, S, K, nc, 1, rank=rank, world=world, dist=dist, device=dev, **kw)
     (a0, a1), (o0, o1) = ex.plan.bands["A"][rank], ex.plan.bands["O"][rank]
     ex.set_inputs(syn.column_inputs(torch, A, K, nc, a0, a1, dev=dev),
                   {k: v[None] for k, v in syn.atm_surface_fields(torch, A, a0, a1, dev=dev).items()},
                   {k: v[None] for k, v in syn.ocn_surface_fields(torch, O, o0, o1, dev=dev).items()})
-    ex.step()
-    ex.step()            # twice: buffer reuse across exchanges is ordered by the two barriers
+    for _ in range(6):   # repeatedly: buffer reuse across exchanges is ordered by the two handshakes
+        ex.step()
     torch.cuda.synchronize()
     bad = []
     ca, co = slice(a0 * A.im, a1 * A.im), slice(o0 * O.im, o1 * O.im)
