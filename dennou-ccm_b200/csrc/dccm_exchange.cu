@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(kThreads) sfc_exchange_redo_kernel(const SfcAr
 }
 
 // ---- staged form: atmosphere rows brought to shared memory by TMA bulk copies
-constexpr int kTileW = 136;        // doubles per staged source row: 128 cells + stencil reach + alignment slack
+constexpr int kTileW = 132;        // doubles per staged source row: 128 cells + stencil reach + alignment slack (7 CTAs/SM fit)
 constexpr int kMaxEnt = 16;        // longest stencil the staged form takes (bilinear 4, conservative 1-3 (+pairs))
 constexpr int kStageHdr = 640;     // mbarrier + two ZStage records, then the 128-byte aligned tiles
 
@@ -567,8 +567,8 @@ Csr csr_of(const dccm_remap *h)
 extern "C" int dccm_sfc_exchange_config(dccm_remap *as_bil, int staged, int min_blocks)
 {
     if (!as_bil) return fail(DCCM_ERR_ARG, "dccm_sfc_exchange_config: null handle");
-    if (min_blocks >= 0 && min_blocks != 4 && min_blocks != 5 && min_blocks != 6)
-        return fail(DCCM_ERR_ARG, "dccm_sfc_exchange_config: min_blocks must be 4, 5 or 6");
+    if (min_blocks >= 0 && (min_blocks < 4 || min_blocks > 7))
+        return fail(DCCM_ERR_ARG, "dccm_sfc_exchange_config: min_blocks must be 4, 5, 6 or 7");
     if (staged >= 0) as_bil->sfc_staged = staged ? 1 : 0;
     if (min_blocks >= 0) as_bil->sfc_minb = min_blocks;
     return DCCM_OK;
@@ -691,6 +691,7 @@ extern "C" int dccm_sfc_exchange_rows_device(const dccm_remap *as_bil, const dcc
         else switch (minb) {
         case 4: DCCM_LAUNCH_STAGED(4, false); break;
         case 6: DCCM_LAUNCH_STAGED(6, false); break;
+        case 7: DCCM_LAUNCH_STAGED(7, false); break;
         default: DCCM_LAUNCH_STAGED(5, false); break;
         }
 #undef DCCM_LAUNCH_STAGED
