@@ -103,6 +103,26 @@ module dccm_b200_c
        type(c_ptr), intent(out) :: handle
        integer(c_int) :: rc
      end function
+     !> the operator of ONE rank's latitude band (destination rows jD0 .. jD1-1, 0-based; source cells numbered inside the
+     !! rank's source buffer of src_rows rows starting at row src_row0): what the receiving component's MPI rank needs
+     !! (ref common/interpolation_data_latlon_mod.f90:140-151), straight from the grid axes
+     function dccm_remap_create_jones99_band(nxs, x_LonS, nys, y_LatS, nxd, x_LonD, nyd, y_LatD, &
+          & y_LatIntWtS, y_LatIntWtD, accuracy_order, lon_mode, jD0, jD1, src_row0, src_rows, handle) &
+          & bind(C, name="dccm_remap_create_jones99_band") result(rc)
+       import
+       integer(c_int), value :: nxs, nys, nxd, nyd, accuracy_order, lon_mode, jD0, jD1, src_row0, src_rows
+       real(c_double), intent(in) :: x_LonS(nxs), y_LatS(nys), x_LonD(nxd), y_LatD(nyd), y_LatIntWtS(nys), y_LatIntWtD(nyd)
+       type(c_ptr), intent(out) :: handle
+       integer(c_int) :: rc
+     end function
+     function dccm_remap_create_bilinear_band(nxs, x_LonS, nys, y_LatS, nxr, x_LonR, nyr, y_LatR, lon_mode, &
+          & jD0, jD1, src_row0, src_rows, handle) bind(C, name="dccm_remap_create_bilinear_band") result(rc)
+       import
+       integer(c_int), value :: nxs, nys, nxr, nyr, lon_mode, jD0, jD1, src_row0, src_rows
+       real(c_double), intent(in) :: x_LonS(nxs), y_LatS(nys), x_LonR(nxr), y_LatR(nyr)
+       type(c_ptr), intent(out) :: handle
+       integer(c_int) :: rc
+     end function
      !> table generators, files and the index arithmetic of set_mappingTable_interpCoef
      !! (ref common/grid_mapping_util_jones99.f90:35-54, :446-506; common/grid_mapping_util.f90:32-48, :181-241)
      function dccm_table_gen_jones99(nxs, x_LonS, nys, y_LatS, nxd, x_LonD, nyd, y_LatD, &
