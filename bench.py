@@ -733,13 +733,21 @@ def run_ours(args, rank, world):
         line["loaded_repo_libraries"] = loaded_repo_libraries()
         print(json.dumps(line), flush=True)
     if world > 1:
-        # Tear down without dist.destroy_process_group(): with NCCL work captured in a CUDA graph the
-        # communicator teardown can block forever.  Drain, meet at a barrier, then leave.
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush(); sys.stderr.flush()
-        os._exit(0)
+        if halo_mode in ("nccl", "allgather") and graph is not None:
+            # NCCL collectives were captured in the CUDA graph: tearing the communicator down under a live graph can
+            # block forever (the graph owns work on the communicator's streams).  Results are out; leave.
+            os._exit(0)
+        # peer-memory halo / member blocks: no NCCL work in the graph -- ordinary teardown
+        if os.environ.get("DCCM_BENCH_HARD_EXIT"):
+            os._exit(0)
+        W.graph = None
+        del run_step, graph
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
 
 
 def run_e2e(torch, ex, col_in, atm_sfc, ocn_sfc, args, local=0):
