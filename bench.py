@@ -581,6 +581,8 @@ def run_ours(args, rank, world):
 
     if args.sfc_minb > 0:
         ex.configure_sfc(-1, args.sfc_minb)
+    if args.overlap_remaps:
+        ex.overlap_remaps = True
     bytes_alg = ex.algorithmic_bytes()
     if world > 1:                                  # whole-job bytes: sum over ranks
         keys = sorted(bytes_alg)
@@ -977,6 +979,7 @@ def main():
                     "(surface kernel beside the forward solve on a second stream); 0 = stage after stage")
     ap.add_argument("--order-as", type=int, default=1, choices=[1, 2], help="accuracy order of the conservative A->S table "
                     "(BASELINE: first order; 2 = gmapgen's default interp_order_AS, three source rows per stencil)")
+    ap.add_argument("--overlap-remaps", action="store_true", help="S->O remaps on a second stream beside S->A / backward (measured neutral)")
     ap.add_argument("--sfc-minb", type=int, default=-1, help="CTAs per SM the fused surface kernel is built for (4, 5, 6; tuning)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle-band parity block")
     ap.add_argument("--no-others", action="store_true", help="skip the other_workloads block (BASELINE configs 1-4)")

@@ -225,12 +225,46 @@ class SurfaceExchange:
     def sfc_last_form(self):
         return int(L.lib().dccm_sfc_exchange_last_form(self.ops["as_bil"]._h))
 
-    def remap_from_sfc(self):
+    # Option: the S->O / S->I remaps (latency bound, half the SM's warp slots and registers unused) on a second stream next
+    # to the S->A remaps and the backward solve, which does not need them; backward() joins the two streams again.
+    # Measured neutral at config 5 (9.38 vs 9.37-9.40 ms per exchange: the block scheduler hardly mixes the grids), so off.
+    overlap_remaps = False
+
+    def _fork_side(self):
+        torch = self.torch
+        main = torch.cuda.current_stream(self.dev)
+        if getattr(self, "_rside", None) is None:
+            self._rside = torch.cuda.Stream(self.dev)
+        ev = torch.cuda.Event(); ev.record(main)
+        self._rside.wait_event(ev)
+        return self._rside
+
+    def _join_side(self):
+        ev = getattr(self, "_rpending", None)
+        if ev is not None:
+            self.torch.cuda.current_stream(self.dev).wait_event(ev)
+            self._rpending = None
+
+    def _remaps_to_ocean(self):
+        M = self.M
+        self.ops["so_cons"].apply(self.s2o[:10 * M], self.o_recv[:10 * M])
+        self.ops["so_bil"].apply(self.s2o[10 * M:], self.o_recv[10 * M:])
+
+    def _remaps_to_atmosphere(self):
         M = self.M
         self.ops["sa_cons"].apply(self.s2a[:4 * M], self.a_recv[:4 * M])
         self.ops["sa_bil"].apply(self.s2a[4 * M:], self.a_recv[4 * M:])
-        self.ops["so_cons"].apply(self.s2o[:10 * M], self.o_recv[:10 * M])
-        self.ops["so_bil"].apply(self.s2o[10 * M:], self.o_recv[10 * M:])
+
+    def remap_from_sfc(self):
+        if self.overlap_remaps:
+            side = self._fork_side()
+            with self.torch.cuda.stream(side):
+                self._remaps_to_ocean()
+                self._rpending = self.torch.cuda.Event(); self._rpending.record(side)
+            self._remaps_to_atmosphere()
+        else:
+            self._remaps_to_atmosphere()
+            self._remaps_to_ocean()
         self.launches += 4
 
     def backward(self):
@@ -238,6 +272,7 @@ class SurfaceExchange:
         lvl1 = self.a_recv[5 * M:9 * M].view(4, M * nA)
         self.vdiff.backward_device(self.tend, lvl1)
         self.launches += 1
+        self._join_side()
 
     # -- latitude-slab pipeline: the issue-bound surface kernel next to the HBM-bound forward solve ------------------
     def _slab_plan(self, nslab):

@@ -421,8 +421,16 @@ class PeerShardedExchange(ShardedExchange):
             L.check(L.lib().dccm_remap_apply_seg_device(self.ops[key]._h, C.byref(seg), self.rowlen["S"],
                                                         L.tptr(recv), recv.shape[1], recv.shape[0], nrow,
                                                         L.current_stream()))
+        def to_ocean():
+            apply("so_cons", "s2o", 0, 10, self.o_recv[:10])
+            apply("so_bil", "s2o", 10, 2, self.o_recv[10:])
+        if self.overlap_remaps:              # S->O / S->I next to S->A and the backward solve (exchange.py)
+            side = self._fork_side()
+            with self.torch.cuda.stream(side):
+                to_ocean()
+                self._rpending = self.torch.cuda.Event(); self._rpending.record(side)
         apply("sa_cons", "s2a", 0, 4, self.a_recv[:4])
         apply("sa_bil", "s2a", 4, 5, self.a_recv[4:])
-        apply("so_cons", "s2o", 0, 10, self.o_recv[:10])
-        apply("so_bil", "s2o", 10, 2, self.o_recv[10:])
+        if not self.overlap_remaps:
+            to_ocean()
         self.launches += 4
