@@ -682,7 +682,6 @@ def run_ours(args, rank, world):
     launches = launches_per_step * args.steps
 
     value = 1e3 / ms
-    moved = dict(bytes_alg)            # bytes the kernels actually move: zonal / separable operators read no table
     fwd_gbs = bytes_alg["fwd"] / (part_ms["fwd"] * 1e-3) / 1e9
     line = {
         "metric": "coupling exchanges/sec", "value": value, "unit": "exchanges/s", "n_gpus": world,
