@@ -63,8 +63,8 @@ def load_peaks():
 
 
 class ClockSampler:
-    """SM clock, power and throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled every 10 ms from a
-    thread of this process (the timed region is a fraction of a second); `nvidia-smi -lms 100` as the fallback when the
+    """SM clock, power and throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled back to back from a
+    thread of this process (the timed region is 25 ms - 0.2 s); `nvidia-smi -lms 100` as the fallback when the
     NVML bindings are missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -116,7 +116,7 @@ class ClockSampler:
                 self.power.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.001)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -127,7 +127,7 @@ class ClockSampler:
             self.stop_flag = True
             self.t.join(timeout=1.0)
             return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
-                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "NVML, 10 ms",
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "NVML, polled back to back (~1-2 ms)",
                     "power_w_max": max(self.power) if self.power else None}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
