@@ -65,6 +65,7 @@ class SurfaceExchange:
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
         self.A, self.O, self.S = A, O, S
         self.K, self.nc, self.iq, self.M = kmax, ncmax, index_h2ovap, members
+        self.fast = bool(fast)
         from . import synthetic as syn
         c = consts or {}
         self.Grav = c.get("Grav", syn.GRAV); self.CpDry = c.get("CpDry", syn.CPDRY)
@@ -150,7 +151,7 @@ class SurfaceExchange:
             out["ImplCplCoef1"] = self.a2s_bil[5 * M:9 * M].view(4, M * nA)
             out["ImplCplCoef2"] = self.a2s_bil[9 * M:13 * M].view(4, M * nA)
         self.vdiff.forward_device(self.col_in, out)
-        self.launches += 1
+        self.launches += 1 if self.fast else 2          # reference order: the solve + its (normally empty) IEEE redo kernel
 
     def remap_to_sfc(self):
         assert not self.sharded, "the unfused surface step is single-GPU only"
@@ -324,7 +325,7 @@ class SurfaceExchange:
         k_sfc = 0
         for k, ((a0, a1), _, _) in enumerate(slabs):
             self.vdiff.forward_cols_device(self.col_in, out, a0 * im, a1 * im)
-            self.launches += 1
+            self.launches += 1 if self.fast else 2
             ev = None
             while k_sfc < nslab and (slabs[k_sfc][2][1] <= a1 or k == nslab - 1):
                 if ev is None:
